@@ -1,0 +1,120 @@
+/* log_b200_raster.h -- C ABI of the B200-native differentiable Gaussian-splatting rasteriser.
+ *
+ * This is the drop-in boundary for the hot path of zju3dv/LoG.  Plain pointers and sizes only; no torch types.
+ * All pointers named *_d are DEVICE pointers (fp32 / int32, contiguous, 16-byte aligned); `stream` is a
+ * cudaStream_t passed as void*.  Every function returns 0 on success, a positive cudaError_t value if the CUDA
+ * runtime reported one, or a negative LGR_E_* code.  Nothing here ever falls back to the CPU.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   lgr_compute_radius     LoG/cuda/compute_radius_kernel.cu:107-183 (`compute_radius`, bound at :185-187) and the
+ *                          fork's `rasterizer.compute_radius(xyz, scaling, rotation)` (LoG/model/level_of_gaussian.py:59)
+ *   lgr_forward_project +
+ *   lgr_forward_render     forward of `GaussianRasterizer.__call__` of diff_gaussian_rasterization[_wodilate]
+ *                          (call sites LoG/render/renderer.py:153,190; LoG/model/level_of_gaussian.py:211)
+ *   lgr_backward           its autograd backward (triggered at LoG/utils/trainer.py:158)
+ * The Python binding a LoG maintainer uses is log_b200/rasterizer.py (ctypes); see INTEGRATION.md.
+ */
+#ifndef LOG_B200_RASTER_H
+#define LOG_B200_RASTER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGR_ABI_VERSION 1
+#define LGR_TILE 16
+
+/* low-pass filter on the 2D covariance */
+#define LGR_FILTER_ADD 0  /* stock 3DGS: cov_xx += 0.3, cov_yy += 0.3                                          */
+#define LGR_FILTER_MAX 1  /* LoG fork ("wodilate"): cov_xx = max(cov_xx, 0.3) -- compute_radius_kernel.cu:100-103 */
+#define LGR_FILTER_NONE 2 /* fork with use_filter=False (renderer.py:151-152)                                    */
+
+#define LGR_E_BADARG (-1)
+#define LGR_E_CAPACITY (-2) /* instance buffers smaller than the D the project stage reported */
+#define LGR_E_UNSUPPORTED (-3)
+
+/* Per-view constants.  Mirrors GaussianRasterizationSettings (kwargs at LoG/render/renderer.py:63-76).
+ * viewmatrix/projmatrix/campos/bg stay on the device exactly as LoG hands them over (no host read-back). */
+typedef struct lgr_view {
+  int32_t image_height, image_width;
+  float tanfovx, tanfovy;
+  float scale_modifier;
+  int32_t sh_degree;    /* active SH degree 0..3 (ignored when colors_precomp is given) */
+  int32_t sh_coeffs;    /* K: coefficients per Gaussian stored in `shs` (N,K,3) */
+  int32_t filter_mode;  /* LGR_FILTER_* */
+  int32_t want_aux;     /* 1: also produce point_id_pixel / point_weight_pixel / point_weight (fork 5-tuple) */
+  int32_t tile_row_begin, tile_row_end; /* this call renders tile rows [begin,end); 0,0 = all (multi-GPU shard) */
+  const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
+  const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
+  const float* campos_d;     /* (3,) */
+  const float* bg_d;         /* (3,) */
+} lgr_view;
+
+/* Sizes of the buffers the caller must provide. */
+#define LGR_SPLAT_FLOATS 12 /* per-Gaussian projected record: 3 x float4 */
+#define LGR_GRAD_FLOATS 12  /* per-Gaussian 2D-gradient accumulator: 3 x float4 */
+#define LGR_META_INTS 8     /* meta_d: [0]=D binned instances [1]=longest tile list [2..3]=D by the stock
+                               radius-square rule (lo,hi 32 bits) [4]=#Gaussians with radius>0 */
+
+int lgr_abi_version(void);
+
+/* radii_d[i] = 3*sqrt(lambda_max) of the projected Gaussian, 0 if culled.  Semantics of
+ * compute_radius_cuda (compute_radius_kernel.cu:107-156): NDC cull +-1.3, no near cull, max(.,0.3) filter. */
+int lgr_compute_radius(int64_t n, const float* means3D_d, const float* scales_d, const float* rotations_d,
+                       const float* projmatrix_d, const float* viewmatrix_d, float focal_x, float focal_y,
+                       float tan_fovx, float tan_fovy, float* radii_d, void* stream);
+
+/* Stage 1 of the forward: per-Gaussian projection + EWA covariance + colour, tile counting, tile scan.
+ *   in : means3D (N,3) opacities (N) scales (N,3) rotations (N,4); colors_precomp (N,3) XOR shs (N,K,3)
+ *   out: splat_d (N,12) radii_d (N) int32; clamped_d (N) uint8 (SH only, may be NULL with colors_precomp);
+ *        tile_start_d (tiles+1) int32 exclusive scan of per-tile counts (tiles = gx * rows rendered);
+ *        tile_cursor_d (tiles) int32 scratch; meta_d (LGR_META_INTS) int32.
+ * The caller reads meta_d[0..1] (one 8-byte D2H) to size the instance buffers for lgr_forward_render. */
+int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d, const float* opacities_d,
+                        const float* scales_d, const float* rotations_d, const float* colors_precomp_d,
+                        const float* shs_d, float* splat_d, int32_t* radii_d, uint8_t* clamped_d,
+                        int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, void* stream);
+
+/* Stage 2 of the forward: bin (Gaussian,tile) instances, per-tile (depth,index) radix sort, front-to-back blend.
+ *   num_instances / max_tile_len : the values read from meta_d[0], meta_d[1]
+ *   scratch: inst_key_d, inst_val_d (num_instances) uint32; inst_tmp_d (2*num_instances) uint32, only needed when
+ *            max_tile_len exceeds the shared-memory sort capacity (lgr_sort_smem_capacity()), else may be NULL
+ *   out: sorted_ids_d (num_instances) int32 (kept for backward); image_d (3,H,W); final_T_d (H,W);
+ *        n_contrib_d (H,W) int32; when view->want_aux: point_id_pixel_d (H,W) int32, point_weight_pixel_d (H,W),
+ *        point_weight_d (N) -- must be zero-filled by the caller. */
+int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, int32_t max_tile_len,
+                       const float* splat_d, const int32_t* radii_d, const int32_t* tile_start_d,
+                       int32_t* tile_cursor_d, uint32_t* inst_key_d, uint32_t* inst_val_d, uint32_t* inst_tmp_d,
+                       int32_t* sorted_ids_d, float* image_d, float* final_T_d, int32_t* n_contrib_d,
+                       int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d, void* stream);
+int32_t lgr_sort_smem_capacity(void);
+
+/* Backward: per-tile back-to-front gradient sweep, then per-Gaussian projection backward.
+ *   dsplat_d (N,12) scratch, zero-filled by the caller.
+ *   out (each written for every Gaussian; culled ones get 0): dmeans3D (N,3) dmeans2D (N,3; d/d(ndc x,y), z = 0)
+ *        dopacities (N) dscales (N,3) drotations (N,4) and dcolors (N,3) XOR dshs (N,K,3). */
+int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const float* means3D_d,
+                 const float* opacities_d, const float* scales_d, const float* rotations_d,
+                 const float* colors_precomp_d, const float* shs_d, const float* splat_d, const int32_t* radii_d,
+                 const uint8_t* clamped_d, const int32_t* tile_start_d, const int32_t* sorted_ids_d,
+                 const float* final_T_d, const int32_t* n_contrib_d, const float* dL_dimage_d, float* dsplat_d,
+                 float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
+                 float* dcolors_d, float* dshs_d, void* stream);
+
+/* Diagnostics (not on the data path): per-kernel CUDA-event timing on the launching stream.
+ * lgr_profile_enable(1) starts recording; lgr_profile_collect() synchronises the recorded events, writes the summed
+ * milliseconds and the launch counts per kernel id (LGR_PROFILE_KERNELS entries) and resets the counters. */
+#define LGR_PROFILE_KERNELS 8
+int lgr_profile_enable(int on);
+int lgr_profile_collect(double* ms_out, int32_t* launches_out, int32_t capacity);
+const char* lgr_profile_kernel_name(int kernel_id);
+
+/* Multi-GPU helper (tile-sharded ranks): out[i] += in[i] for the per-Gaussian gradient exchange is done with NCCL
+ * by the host side (log_b200/sharded.py); no entry point is needed here for it. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOG_B200_RASTER_H */

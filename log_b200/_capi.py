@@ -1,0 +1,87 @@
+"""ctypes binding of include/log_b200_raster.h (the C ABI).  Fails loudly if the library is missing:
+there is no CPU path in this package."""
+import ctypes
+import os
+
+from .build import LIB_PATH
+
+_i32, _i64, _f32, _vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+LGR_FILTER_ADD, LGR_FILTER_MAX, LGR_FILTER_NONE = 0, 1, 2
+LGR_SPLAT_FLOATS = 12
+LGR_GRAD_FLOATS = 12
+LGR_META_INTS = 8
+LGR_ABI_VERSION = 1
+
+EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
+           'lgr_forward_render', 'lgr_backward', 'lgr_profile_enable', 'lgr_profile_collect',
+           'lgr_profile_kernel_name')
+LGR_PROFILE_KERNELS = 8
+
+
+class LgrView(ctypes.Structure):
+    """struct lgr_view (include/log_b200_raster.h)."""
+    _fields_ = [('image_height', _i32), ('image_width', _i32), ('tanfovx', _f32), ('tanfovy', _f32),
+                ('scale_modifier', _f32), ('sh_degree', _i32), ('sh_coeffs', _i32), ('filter_mode', _i32),
+                ('want_aux', _i32), ('tile_row_begin', _i32), ('tile_row_end', _i32),
+                ('viewmatrix_d', _vp), ('projmatrix_d', _vp), ('campos_d', _vp), ('bg_d', _vp)]
+
+
+class LgrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load liblog_b200_raster.so; raise (never fall back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LgrError(f'{LIB_PATH} not found: run `python -m log_b200.build` (or __graft_entry__.build()). '
+                       'log_b200 has no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.lgr_abi_version.restype = ctypes.c_int
+    lib.lgr_sort_smem_capacity.restype = _i32
+    lib.lgr_compute_radius.restype = ctypes.c_int
+    lib.lgr_compute_radius.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp]
+    lib.lgr_forward_project.restype = ctypes.c_int
+    lib.lgr_forward_project.argtypes = [ctypes.POINTER(LgrView), _i64] + [_vp] * 13
+    lib.lgr_forward_render.restype = ctypes.c_int
+    lib.lgr_forward_render.argtypes = [ctypes.POINTER(LgrView), _i64, _i64, _i32] + [_vp] * 15
+    lib.lgr_backward.restype = ctypes.c_int
+    lib.lgr_backward.argtypes = [ctypes.POINTER(LgrView), _i64, _i64] + [_vp] * 23
+    lib.lgr_profile_enable.restype = ctypes.c_int
+    lib.lgr_profile_enable.argtypes = [ctypes.c_int]
+    lib.lgr_profile_collect.restype = ctypes.c_int
+    lib.lgr_profile_collect.argtypes = [_vp, _vp, _i32]
+    lib.lgr_profile_kernel_name.restype = ctypes.c_char_p
+    lib.lgr_profile_kernel_name.argtypes = [ctypes.c_int]
+    if lib.lgr_abi_version() != LGR_ABI_VERSION:
+        raise LgrError('liblog_b200_raster.so ABI version mismatch: rebuild with `python -m log_b200.build --force`')
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc > 0:
+        raise LgrError(f'{what}: CUDA error {rc}')
+    names = {-1: 'bad argument', -2: 'instance buffer capacity', -3: 'unsupported'}
+    raise LgrError(f'{what}: {names.get(rc, rc)}')
+
+
+def profile_enable(on=True):
+    check(load().lgr_profile_enable(1 if on else 0), 'lgr_profile_enable')
+
+
+def profile_collect():
+    """-> {kernel_name: (total_ms, launches)} since the last enable/collect."""
+    lib = load()
+    ms = (ctypes.c_double * LGR_PROFILE_KERNELS)()
+    cnt = (_i32 * LGR_PROFILE_KERNELS)()
+    check(lib.lgr_profile_collect(ms, cnt, LGR_PROFILE_KERNELS), 'lgr_profile_collect')
+    return {lib.lgr_profile_kernel_name(k).decode(): (ms[k], cnt[k]) for k in range(LGR_PROFILE_KERNELS)}

@@ -1,0 +1,249 @@
+// Tile binning: exclusive scan of the per-tile counts, scatter of (depth, id) instances into per-tile bins,
+// and the per-tile stable LSD radix sort by (depth, id).
+//
+// Design (B200): instead of one global 64-bit key sort over all D instances (6+ passes x 24 B/instance through
+// HBM), instances are counting-sorted into tile bins (one 8-byte scattered write each) and every tile's list is
+// then radix-sorted entirely in shared memory by one CTA (one 8-byte read + one 4-byte write per instance).
+// Lists that do not fit the 227 KB of shared memory take the same code path over global scratch.
+#include "lgr_common.cuh"
+#include "lgr_prof.cuh"
+
+namespace lgr {
+
+// ---------------------------------------------------------------------------------------------------------
+// exclusive scan of tile counts (a few thousand tiles: one CTA)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* in: counts[0..ntiles) ; out: starts[0..ntiles] */,
+                 int32_t* __restrict__ cursor, int32_t* __restrict__ meta) {
+  __shared__ int warp_sum[SCAN_THREADS / 32];
+  __shared__ int carry_s, maxl_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { carry_s = 0; maxl_s = 0; }
+  __syncthreads();
+  int local_max = 0;
+  for (int base = 0; base < ntiles; base += SCAN_THREADS) {
+    const int i = base + tid;
+    const int c = (i < ntiles) ? tile_start[i] : 0;
+    local_max = max(local_max, c);
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_sum[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + (wid ? warp_sum[wid - 1] : 0) + x - c;
+    if (i < ntiles) { tile_start[i] = excl; cursor[i] = 0; }
+    __syncthreads();
+    if (tid == SCAN_THREADS - 1) carry_s = carry + warp_sum[31];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+  if (lane == 0) atomicMax(&maxl_s, local_max);
+  __syncthreads();
+  if (tid == 0) { tile_start[ntiles] = carry_s; meta[0] = carry_s; meta[1] = maxl_s; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// scatter instances into tile bins (order inside a bin is arbitrary; the sort fixes it)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SCATTER_THREADS = 256;
+
+__global__ void __launch_bounds__(SCATTER_THREADS)
+bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
+                   const int32_t* __restrict__ tile_start, int32_t* __restrict__ cursor, uint32_t* __restrict__ inst_key,
+                   uint32_t* __restrict__ inst_val) {
+  const int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const int rad = radii[i];
+  if (rad <= 0) return;
+  const float4 r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);
+  const float4 r1 = ldg4(splat + i * LGR_SPLAT_FLOATS + 4);
+  if (!(r1.z > 0.f)) return;     // hx == 0: opacity below 1/255, contributes nowhere
+  const float depth = __ldg(splat + i * LGR_SPLAT_FLOATS + 11);
+  int x0, y0, x1, y1;
+  tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
+  const uint32_t key = __float_as_uint(depth);   // depth > 0.2 : IEEE bits are order preserving
+  for (int ty = y0; ty < y1; ty++)
+    for (int tx = x0; tx < x1; tx++) {
+      const int t = (ty - v.row0) * v.gx + tx;
+      const int pos = tile_start[t] + atomicAdd(cursor + t, 1);
+      inst_key[pos] = key;
+      inst_val[pos] = (uint32_t)i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-tile stable LSD radix sort
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+
+// One pass over `len` items on digit (src[sel][i] >> shift) & 255, stable.  Warp w owns the contiguous segment
+// [w*seg, (w+1)*seg): it histograms it, then re-walks it 32 items at a time ranking equal digits with match.any.
+// `whist` is [SORT_WARPS][RADIX] ints in shared memory.  Returns true (uniformly) if the pass was the identity.
+__device__ __forceinline__ bool radix_pass(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                           uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, int len, int shift,
+                                           bool on_val, int* __restrict__ whist) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int seg = ((len + SORT_WARPS * 32 - 1) / (SORT_WARPS * 32)) * 32;   // multiple of 32
+  const int beg = min(len, wid * seg), end = min(len, beg + seg);
+  for (int j = tid; j < SORT_WARPS * RADIX; j += SORT_THREADS) whist[j] = 0;
+  __syncthreads();
+  int* myh = whist + wid * RADIX;
+  for (int i = beg + lane; i < end; i += 32) {
+    const uint32_t d = ((on_val ? vin[i] : kin[i]) >> shift) & (RADIX - 1);
+    atomicAdd(myh + d, 1);
+  }
+  __syncthreads();
+  // thread d: totals over warps -> exclusive scan over digits -> per-warp bases
+  {
+    const int d = tid;   // SORT_THREADS == RADIX
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) tot += whist[w * RADIX + d];
+    int x = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    __shared__ int wsum[SORT_WARPS];
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    int base = x - tot;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) if (w < wid) base += wsum[w];
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) { const int c = whist[w * RADIX + d]; whist[w * RADIX + d] = base; base += c; }
+    // every key has the same digit -> identity pass (barrier + vote in one)
+    if (__syncthreads_or(tot == len)) return true;
+  }
+  for (int i0 = beg; i0 < end; i0 += 32) {
+    const int i = i0 + lane;
+    const bool ok = i < end;
+    uint32_t k = 0, val = 0;
+    if (ok) { k = kin[i]; val = vin[i]; }
+    const uint32_t d = ok ? (((on_val ? val : k) >> shift) & (RADIX - 1)) : (RADIX + lane);   // distinct for idle lanes
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int base = 0;
+    if (ok) base = myh[d];
+    __syncwarp();
+    if (ok && rank == 0) myh[d] = base + __popc(peers);
+    __syncwarp();
+    if (ok) { kout[base + rank] = k; vout[base + rank] = val; }
+  }
+  __syncthreads();
+  return false;
+}
+
+// Sort one tile.  kA/vA hold the input; kB/vB are scratch of the same size.  Result ends in (kA,vA).
+__device__ __forceinline__ void sort_tile(uint32_t* kA, uint32_t* vA, uint32_t* kB, uint32_t* vB, int len, int id_bits,
+                                          int* whist) {
+  // 1) stable sort by depth (4 x 8 bits); bins arrive in arbitrary order, so equal depths are still unordered
+  uint32_t *ki = kA, *vi = vA, *ko = kB, *vo = vB;
+  auto run = [&](int shift, bool on_val) {
+    const bool ident = radix_pass(ki, vi, ko, vo, len, shift, on_val, whist);
+    if (!ident) { uint32_t* t = ki; ki = ko; ko = t; t = vi; vi = vo; vo = t; }
+  };
+  // does any depth repeat?  (checked after the depth sort; almost never true)
+  for (int s = 0; s < 32; s += RADIX_BITS) run(s, false);
+  __shared__ int tie;
+  if (threadIdx.x == 0) tie = 0;
+  __syncthreads();
+  for (int i = threadIdx.x + 1; i < len; i += SORT_THREADS) if (ki[i] == ki[i - 1]) tie = 1;
+  __syncthreads();
+  if (tie) {   // full (depth, id) order: ids first (LSD), then the depth passes again
+    for (int s = 0; s < id_bits; s += RADIX_BITS) run(s, true);
+    for (int s = 0; s < 32; s += RADIX_BITS) run(s, false);
+  }
+  if (ki != kA) {
+    for (int i = threadIdx.x; i < len; i += SORT_THREADS) { kA[i] = ki[i]; vA[i] = vi[i]; }
+    __syncthreads();
+  }
+}
+
+// mode 0: lists with len <= cap live in shared memory (dynamic smem = 16*cap bytes); longer lists are skipped.
+// mode 1: lists with lo < len are sorted in global memory (inst_* in place, tmp_* scratch).
+template <int MODE>
+__global__ void __launch_bounds__(SORT_THREADS)
+tile_sort_kernel(int ntiles, const int32_t* __restrict__ tile_start, uint32_t* __restrict__ inst_key,
+                 uint32_t* __restrict__ inst_val, uint32_t* __restrict__ tmp, int32_t* __restrict__ sorted_ids, int lo,
+                 int cap, int id_bits) {
+  extern __shared__ uint32_t smem_u32[];
+  __shared__ int whist[SORT_WARPS * RADIX];
+  const int t = blockIdx.x;
+  const int beg = tile_start[t], len = tile_start[t + 1] - beg;
+  if (len <= lo || (MODE == 0 && len > cap)) return;
+  if (MODE == 0) {
+    uint32_t* kA = smem_u32; uint32_t* vA = kA + cap; uint32_t* kB = vA + cap; uint32_t* vB = kB + cap;
+    for (int i = threadIdx.x; i < len; i += SORT_THREADS) { kA[i] = inst_key[beg + i]; vA[i] = inst_val[beg + i]; }
+    __syncthreads();
+    if (len > 1) sort_tile(kA, vA, kB, vB, len, id_bits, whist);
+    for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
+  } else {
+    uint32_t* kA = inst_key + beg; uint32_t* vA = inst_val + beg;
+    uint32_t* kB = tmp + 2 * (int64_t)beg; uint32_t* vB = kB + len;
+    __syncthreads();
+    sort_tile(kA, vA, kB, vB, len, id_bits, whist);
+    for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
+  }
+}
+
+constexpr int SORT_CAP_SMALL = 2560;    // 40 KB dynamic smem: 4 CTAs / SM
+constexpr int SORT_CAP_LARGE = 13312;   // 208 KB dynamic smem: 1 CTA / SM
+
+int sort_smem_capacity() { return SORT_CAP_LARGE; }
+
+int launch_tile_scan(int ntiles, int32_t* tile_start, int32_t* cursor, int32_t* meta, cudaStream_t st) {
+  ProfScope ps(K_TILE_SCAN, st);
+  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(ntiles, tile_start, cursor, meta);
+  LGR_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len, const float* splat,
+                        const int32_t* radii, const int32_t* tile_start, int32_t* cursor, uint32_t* inst_key,
+                        uint32_t* inst_val, uint32_t* inst_tmp, int32_t* sorted_ids, cudaStream_t st) {
+  if (n == 0 || num_inst == 0) return 0;
+  const int ntiles = v.gx * (v.row1 - v.row0);
+  const unsigned blocks = (unsigned)((n + SCATTER_THREADS - 1) / SCATTER_THREADS);
+  {
+    ProfScope ps(K_BIN_SCATTER, st);
+    bin_scatter_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val);
+  }
+  LGR_CHECK_LAUNCH();
+  int id_bits = 8;
+  while (id_bits < 32 && (n - 1) >> id_bits) id_bits += 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SORT_CAP_LARGE);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  ProfScope ps(K_TILE_SORT, st, 1 + (max_len > SORT_CAP_SMALL) + (max_len > SORT_CAP_LARGE));
+  tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * SORT_CAP_SMALL, st>>>(ntiles, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, SORT_CAP_SMALL, id_bits);
+  LGR_CHECK_LAUNCH();
+  if (max_len > SORT_CAP_SMALL) {
+    tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * SORT_CAP_LARGE, st>>>(ntiles, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_SMALL, SORT_CAP_LARGE, id_bits);
+    LGR_CHECK_LAUNCH();
+  }
+  if (max_len > SORT_CAP_LARGE) {
+    if (!inst_tmp) return LGR_E_CAPACITY;
+    tile_sort_kernel<1><<<ntiles, SORT_THREADS, 0, st>>>(ntiles, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_LARGE, 0, id_bits);
+    LGR_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // namespace lgr

@@ -1,0 +1,155 @@
+// extern "C" entry points declared in include/log_b200_raster.h.  Thin: argument checks + kernel launches on the
+// caller's stream.  No allocation, no host synchronisation, no CPU fallback.
+#include "lgr_common.cuh"
+#include "lgr_prof.cuh"
+
+namespace lgr {
+int launch_compute_radius(int64_t, const float*, const float*, const float*, const float*, const float*, float, float,
+                          float, float, float*, cudaStream_t);
+int launch_project_fwd(const View&, int64_t, const float*, const float*, const float*, const float*, const float*,
+                       const float*, float*, int32_t*, uint8_t*, int32_t*, int32_t*, cudaStream_t);
+int launch_project_bwd(const View&, int64_t, const float*, const float*, const float*, const float*, bool,
+                       const int32_t*, const uint8_t*, const float*, float*, float*, float*, float*, float*, float*,
+                       float*, cudaStream_t);
+int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int launch_bin_and_sort(const View&, int64_t, int64_t, int, const float*, const int32_t*, const int32_t*, int32_t*,
+                        uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
+int sort_smem_capacity();
+int launch_blend_fwd(const View&, const int32_t*, const int32_t*, const float*, float*, float*, int32_t*, int32_t*,
+                     float*, float*, cudaStream_t);
+int launch_blend_bwd(const View&, const int32_t*, const int32_t*, const float*, const float*, const int32_t*,
+                     const float*, float*, cudaStream_t);
+}  // namespace lgr
+
+using namespace lgr;
+
+static bool view_ok(const lgr_view* v) {
+  if (!v || v->image_height <= 0 || v->image_width <= 0) return false;
+  if (!v->viewmatrix_d || !v->projmatrix_d || !v->bg_d) return false;
+  if (v->filter_mode < 0 || v->filter_mode > 2) return false;
+  if (v->tile_row_begin < 0 || v->tile_row_end < v->tile_row_begin) return false;
+  const int gy = (v->image_height + TILE - 1) / TILE;
+  if (v->tile_row_end > gy) return false;
+  return true;
+}
+
+extern "C" {
+
+int lgr_abi_version(void) { return LGR_ABI_VERSION; }
+
+int32_t lgr_sort_smem_capacity(void) { return sort_smem_capacity(); }
+
+int lgr_compute_radius(int64_t n, const float* means3D_d, const float* scales_d, const float* rotations_d,
+                       const float* projmatrix_d, const float* viewmatrix_d, float focal_x, float focal_y,
+                       float tan_fovx, float tan_fovy, float* radii_d, void* stream) {
+  if (n < 0 || (n > 0 && (!means3D_d || !scales_d || !rotations_d || !radii_d)) || !projmatrix_d || !viewmatrix_d)
+    return LGR_E_BADARG;
+  return launch_compute_radius(n, means3D_d, scales_d, rotations_d, projmatrix_d, viewmatrix_d, focal_x, focal_y,
+                               tan_fovx, tan_fovy, radii_d, (cudaStream_t)stream);
+}
+
+int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d, const float* opacities_d,
+                        const float* scales_d, const float* rotations_d, const float* colors_precomp_d,
+                        const float* shs_d, float* splat_d, int32_t* radii_d, uint8_t* clamped_d,
+                        int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, void* stream) {
+  if (!view_ok(view) || n < 0 || !tile_start_d || !tile_cursor_d || !meta_d) return LGR_E_BADARG;
+  if ((colors_precomp_d != nullptr) == (shs_d != nullptr) && n > 0) return LGR_E_BADARG;   // exactly one colour source
+  if (shs_d) {
+    if (!view->campos_d || !clamped_d) return LGR_E_BADARG;
+    if (view->sh_degree < 0 || view->sh_degree > 3) return LGR_E_UNSUPPORTED;
+    if (view->sh_coeffs < (view->sh_degree + 1) * (view->sh_degree + 1)) return LGR_E_BADARG;
+  }
+  if (n > 0 && (!means3D_d || !opacities_d || !scales_d || !rotations_d || !splat_d || !radii_d)) return LGR_E_BADARG;
+  if (n > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const View v = make_view(view);
+  const int ntiles = v.gx * (v.row1 - v.row0);
+  cudaError_t e = cudaMemsetAsync(tile_start_d, 0, sizeof(int32_t) * (size_t)(ntiles + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(meta_d, 0, sizeof(int32_t) * LGR_META_INTS, st);
+  if (e != cudaSuccess) return (int)e;
+  int rc = launch_project_fwd(v, n, means3D_d, opacities_d, scales_d, rotations_d, colors_precomp_d, shs_d, splat_d,
+                              radii_d, clamped_d, tile_start_d, meta_d, st);
+  if (rc) return rc;
+  return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, st);
+}
+
+int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, int32_t max_tile_len,
+                       const float* splat_d, const int32_t* radii_d, const int32_t* tile_start_d,
+                       int32_t* tile_cursor_d, uint32_t* inst_key_d, uint32_t* inst_val_d, uint32_t* inst_tmp_d,
+                       int32_t* sorted_ids_d, float* image_d, float* final_T_d, int32_t* n_contrib_d,
+                       int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d, void* stream) {
+  if (!view_ok(view) || n < 0 || num_instances < 0 || !tile_start_d || !tile_cursor_d || !image_d || !final_T_d ||
+      !n_contrib_d)
+    return LGR_E_BADARG;
+  if (num_instances > 0 && (!inst_key_d || !inst_val_d || !sorted_ids_d || !splat_d || !radii_d)) return LGR_E_BADARG;
+  if (view->want_aux && (!point_id_pixel_d || !point_weight_pixel_d || (n > 0 && !point_weight_d))) return LGR_E_BADARG;
+  if (num_instances > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const View v = make_view(view);
+  int rc = launch_bin_and_sort(v, n, num_instances, max_tile_len, splat_d, radii_d, tile_start_d, tile_cursor_d,
+                               inst_key_d, inst_val_d, inst_tmp_d, sorted_ids_d, st);
+  if (rc) return rc;
+  return launch_blend_fwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, final_T_d, n_contrib_d, point_id_pixel_d,
+                          point_weight_pixel_d, point_weight_d, st);
+}
+
+int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const float* means3D_d,
+                 const float* opacities_d, const float* scales_d, const float* rotations_d,
+                 const float* colors_precomp_d, const float* shs_d, const float* splat_d, const int32_t* radii_d,
+                 const uint8_t* clamped_d, const int32_t* tile_start_d, const int32_t* sorted_ids_d,
+                 const float* final_T_d, const int32_t* n_contrib_d, const float* dL_dimage_d, float* dsplat_d,
+                 float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
+                 float* dcolors_d, float* dshs_d, void* stream) {
+  (void)opacities_d;
+  if (!view_ok(view) || n < 0 || !tile_start_d || !final_T_d || !n_contrib_d || !dL_dimage_d) return LGR_E_BADARG;
+  if (n == 0) return 0;
+  const bool use_sh = shs_d != nullptr;
+  if (use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
+  if (!means3D_d || !scales_d || !rotations_d || !splat_d || !radii_d || !dsplat_d || !dmeans3D_d || !dmeans2D_d ||
+      !dopacities_d || !dscales_d || !drotations_d)
+    return LGR_E_BADARG;
+  if (use_sh ? (!dshs_d || !clamped_d || !view->campos_d) : !dcolors_d) return LGR_E_BADARG;
+  if (num_instances > 0 && !sorted_ids_d) return LGR_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const View v = make_view(view);
+  int rc = 0;
+  if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, final_T_d, n_contrib_d, dL_dimage_d, dsplat_d, st);
+  if (rc) return rc;
+  return launch_project_bwd(v, n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
+                            dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, st);
+}
+
+/* ---- diagnostics: per-kernel CUDA-event timing (used by bench.py for the live roofline numbers) ---- */
+int lgr_profile_enable(int on) {
+  Profiler& p = Profiler::get();
+  p.enabled = on != 0;
+  p.used = 0;
+  for (int k = 0; k < K_COUNT; k++) p.launches[k] = 0;
+  return 0;
+}
+
+int lgr_profile_collect(double* ms_out, int32_t* launches_out, int32_t capacity) {
+  Profiler& p = Profiler::get();
+  if (!ms_out || !launches_out || capacity < K_COUNT) return LGR_E_BADARG;
+  for (int k = 0; k < K_COUNT; k++) { ms_out[k] = 0.0; launches_out[k] = p.launches[k]; }
+  for (int i = 0; i < p.used; i++) {
+    cudaError_t e = cudaEventSynchronize(p.stop[i]);
+    if (e != cudaSuccess) return (int)e;
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, p.start[i], p.stop[i]);
+    if (e != cudaSuccess) return (int)e;
+    ms_out[p.kid[i]] += ms;
+  }
+  p.used = 0;
+  for (int k = 0; k < K_COUNT; k++) p.launches[k] = 0;
+  return 0;
+}
+
+const char* lgr_profile_kernel_name(int k) {
+  static const char* names[K_COUNT] = {"project_fwd", "tile_scan", "bin_scatter", "tile_sort", "blend_fwd", "blend_bwd",
+                                       "project_bwd", "compute_radius"};
+  return (k >= 0 && k < K_COUNT) ? names[k] : "";
+}
+
+}  // extern "C"

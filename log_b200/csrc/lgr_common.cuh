@@ -1,0 +1,177 @@
+// Shared device helpers for the B200 (sm_100a) Gaussian-splatting rasteriser.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/log_b200_raster.h"
+
+namespace lgr {
+
+constexpr int TILE = LGR_TILE;          // 16x16 pixel tiles
+constexpr int TILE_PIX = TILE * TILE;   // 256 threads per blend CTA
+constexpr float NEAR_Z = 0.2f;
+constexpr float ALPHA_MAX = 0.99f;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float T_STOP = 1e-4f;
+constexpr float FILTER_VAR = 0.3f;      // LoG/cuda/compute_radius_kernel.cu:61
+constexpr float CLAMP_FOV = 1.3f;       // compute_radius_kernel.cu:71-72
+
+// Kernel-side copy of lgr_view with derived quantities.
+struct View {
+  int H, W, gx, gy;          // image size, tile grid
+  int row0, row1;            // tile rows rendered by this call [row0,row1)
+  float tanfovx, tanfovy, fx, fy, scale_mod;
+  int sh_degree, sh_K, filter_mode, want_aux;
+  const float* view;         // (4,4) transposed storage: t_j = sum_i p_i * view[i*4+j] + view[12+j]
+  const float* proj;
+  const float* campos;
+  const float* bg;
+};
+
+inline View make_view(const lgr_view* v) {
+  View o;
+  o.H = v->image_height; o.W = v->image_width;
+  o.gx = (o.W + TILE - 1) / TILE; o.gy = (o.H + TILE - 1) / TILE;
+  o.row0 = v->tile_row_begin; o.row1 = v->tile_row_end;
+  if (o.row0 == 0 && o.row1 == 0) o.row1 = o.gy;
+  o.tanfovx = v->tanfovx; o.tanfovy = v->tanfovy;
+  o.fx = o.W / (2.0f * v->tanfovx); o.fy = o.H / (2.0f * v->tanfovy);
+  o.scale_mod = v->scale_modifier;
+  o.sh_degree = v->sh_degree; o.sh_K = v->sh_coeffs; o.filter_mode = v->filter_mode; o.want_aux = v->want_aux;
+  o.view = v->viewmatrix_d; o.proj = v->projmatrix_d; o.campos = v->campos_d; o.bg = v->bg_d;
+  return o;
+}
+
+// ---- projected splat record: 3 x float4 per Gaussian ---------------------------------------------------
+//   r0 = (px, py, conic_x, conic_y)      r1 = (conic_z, opacity, hx, hy)      r2 = (r, g, b, depth)
+// (hx,hy) is a conservative half-extent of the region where alpha >= 1/255 can hold; it is only used to skip
+// work and never changes a result.
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+struct Cov2D {
+  float a, b, c;        // after the low-pass filter
+  float a_raw, c_raw;   // before it
+  float t[3];           // view-space mean
+  float T[6];           // 2x3  T = J W
+  bool inx, iny;        // t.x/t.z, t.y/t.z inside the 1.3*tanfov clamp
+};
+
+// Rotation matrix from a quaternion (r,x,y,z) WITHOUT normalisation (compute_radius_kernel.cu:36).
+__device__ __forceinline__ void quat_to_R(const float4 q, float R[9]) {
+  const float r = q.x, x = q.y, y = q.z, z = q.w;
+  R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
+  R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
+  R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+// Sigma = (R S)(R S)^T   (LoG/model/geometry.py:27-41); symmetric 3x3 stored full.
+__device__ __forceinline__ void cov3d(const float s[3], const float R[9], float Sg[9]) {
+  float M[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) M[i * 3 + k] = R[i * 3 + k] * s[k];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) Sg[i * 3 + j] = M[i * 3] * M[j * 3] + M[i * 3 + 1] * M[j * 3 + 1] + M[i * 3 + 2] * M[j * 3 + 2];
+}
+
+// EWA projection of the 3D covariance (geometry.py:91-130, compute_radius_kernel.cu:63-105).
+__device__ __forceinline__ void cov2d(const float* __restrict__ V, const float p[3], const float Sg[9], float fx, float fy,
+                                      float tanfovx, float tanfovy, int filter_mode, Cov2D& o) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) o.t[j] = p[0] * V[j] + p[1] * V[4 + j] + p[2] * V[8 + j] + V[12 + j];
+  const float limx = CLAMP_FOV * tanfovx, limy = CLAMP_FOV * tanfovy;
+  const float itz = 1.0f / o.t[2];
+  const float txtz = o.t[0] * itz, tytz = o.t[1] * itz;
+  o.inx = (txtz >= -limx) && (txtz <= limx);
+  o.iny = (tytz >= -limy) && (tytz <= limy);
+  const float txc = fminf(limx, fmaxf(-limx, txtz)) * o.t[2];
+  const float tyc = fminf(limy, fmaxf(-limy, tytz)) * o.t[2];
+  const float J00 = fx * itz, J02 = -(fx * txc) * itz * itz, J11 = fy * itz, J12 = -(fy * tyc) * itz * itz;
+  // T = J W with W = V[:3,:3]^T :  T[r][j] = sum_k J[r][k] V[j*4+k]
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    o.T[j] = J00 * V[j * 4 + 0] + J02 * V[j * 4 + 2];
+    o.T[3 + j] = J11 * V[j * 4 + 1] + J12 * V[j * 4 + 2];
+  }
+  float TS[6];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) TS[r * 3 + j] = o.T[r * 3] * Sg[j] + o.T[r * 3 + 1] * Sg[3 + j] + o.T[r * 3 + 2] * Sg[6 + j];
+  o.a_raw = TS[0] * o.T[0] + TS[1] * o.T[1] + TS[2] * o.T[2];
+  o.b = TS[0] * o.T[3] + TS[1] * o.T[4] + TS[2] * o.T[5];
+  o.c_raw = TS[3] * o.T[3] + TS[4] * o.T[4] + TS[5] * o.T[5];
+  o.a = o.a_raw; o.c = o.c_raw;
+  if (filter_mode == LGR_FILTER_ADD) { o.a += FILTER_VAR; o.c += FILTER_VAR; }
+  else if (filter_mode == LGR_FILTER_MAX) { o.a = fmaxf(o.a, FILTER_VAR); o.c = fmaxf(o.c, FILTER_VAR); }
+}
+
+// 3 sqrt(lambda_max)  (compute_radius_kernel.cu:139-152)
+__device__ __forceinline__ float radius_from_cov(float a, float b, float c, float& det) {
+  det = a * c - b * b;
+  const float mid = 0.5f * (a + c);
+  const float root = sqrtf(fmaxf(0.1f, mid * mid - det));
+  return 3.0f * sqrtf(fmaxf(mid + root, mid - root));
+}
+
+// Stock tile rectangle from the radius square, clamped to the tile grid.
+__device__ __forceinline__ void tile_rect(float px, float py, int rad, int gx, int gy, int& x0, int& y0, int& x1, int& y1) {
+  x0 = min(gx, max(0, (int)((px - rad) / TILE)));
+  x1 = min(gx, max(0, (int)((px + rad + TILE - 1) / TILE)));
+  y0 = min(gy, max(0, (int)((py - rad) / TILE)));
+  y1 = min(gy, max(0, (int)((py + rad + TILE - 1) / TILE)));
+}
+
+// Tightened rectangle: tiles of the stock rectangle that the conservative alpha>=1/255 box (hx,hy) can reach,
+// restricted to the tile rows [row0,row1) this call renders.
+__device__ __forceinline__ void tile_rect_tight(float px, float py, int rad, float hx, float hy, int gx, int gy, int row0,
+                                                int row1, int& x0, int& y0, int& x1, int& y1) {
+  tile_rect(px, py, rad, gx, gy, x0, y0, x1, y1);
+  // tile tx holds pixel centres 16tx .. 16tx+15 ; reachable iff px+hx >= 16tx and px-hx <= 16tx+15
+  const int tx0 = (int)ceilf((px - hx - (TILE - 1)) * (1.0f / TILE));
+  const int tx1 = (int)floorf((px + hx) * (1.0f / TILE)) + 1;
+  const int ty0 = (int)ceilf((py - hy - (TILE - 1)) * (1.0f / TILE));
+  const int ty1 = (int)floorf((py + hy) * (1.0f / TILE)) + 1;
+  x0 = max(x0, tx0); x1 = min(x1, tx1);
+  y0 = max(max(y0, ty0), row0); y1 = min(min(y1, ty1), row1);
+  if (x1 < x0) x1 = x0;
+  if (y1 < y0) y1 = y0;
+}
+
+// ---- SH basis (LoG/model/sh_utils.py:31-58, DC first) ---------------------------------------------------
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+__device__ __constant__ const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                                 -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                                 0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                                 -0.5900435899266435f};
+
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float B[16]) {
+  B[0] = SH_C0;
+  if (deg > 0) {
+    B[1] = -SH_C1 * y; B[2] = SH_C1 * z; B[3] = -SH_C1 * x;
+    if (deg > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      B[4] = SH_C2[0] * xy; B[5] = SH_C2[1] * yz; B[6] = SH_C2[2] * (2.f * zz - xx - yy);
+      B[7] = SH_C2[3] * xz; B[8] = SH_C2[4] * (xx - yy);
+      if (deg > 2) {
+        B[9] = SH_C3[0] * y * (3.f * xx - yy); B[10] = SH_C3[1] * xy * z; B[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
+        B[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); B[13] = SH_C3[4] * x * (4.f * zz - xx - yy);
+        B[14] = SH_C3[5] * z * (xx - yy); B[15] = SH_C3[6] * x * (xx - 3.f * yy);
+      }
+    }
+  }
+}
+
+}  // namespace lgr
+
+#define LGR_CHECK_LAUNCH()                     \
+  do {                                         \
+    cudaError_t e__ = cudaGetLastError();      \
+    if (e__ != cudaSuccess) return (int)e__;   \
+  } while (0)

@@ -1,0 +1,362 @@
+// Per-Gaussian stage of the rasteriser: 3D->2D projection, EWA covariance, colour, tile counting (forward);
+// chain rule from the 2D accumulators back to means/scales/rotations/opacities/colours|SH (backward);
+// and the stand-alone compute_radius that replaces LoG/cuda/compute_radius_kernel.cu.
+//
+// One thread per Gaussian, 256 threads per CTA; a warp reads 32 consecutive AoS rows of every input, so each
+// 128-byte line fetched is fully consumed by the warp (HBM-bound streaming kernel, no reuse to stage).
+#include "lgr_common.cuh"
+#include "lgr_prof.cuh"
+
+namespace lgr {
+
+constexpr int PROJ_THREADS = 256;
+
+__device__ __forceinline__ void load3(const float* __restrict__ p, int64_t i, float o[3]) {
+  o[0] = __ldg(p + 3 * i); o[1] = __ldg(p + 3 * i + 1); o[2] = __ldg(p + 3 * i + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// compute_radius  (reference: LoG/cuda/compute_radius_kernel.cu:107-156)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PROJ_THREADS)
+compute_radius_kernel(int64_t n, const float* __restrict__ means, const float* __restrict__ scales,
+                      const float* __restrict__ rots, const float* __restrict__ proj, const float* __restrict__ view,
+                      float fx, float fy, float tanfovx, float tanfovy, float* __restrict__ radii) {
+  __shared__ float sV[16], sP[16];
+  if (threadIdx.x < 16) { sV[threadIdx.x] = view[threadIdx.x]; sP[threadIdx.x] = proj[threadIdx.x]; }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
+  if (i >= n) return;
+  float p[3];
+  load3(means, i, p);
+  float hom[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) hom[k] = p[0] * sP[k] + p[1] * sP[4 + k] + p[2] * sP[8 + k] + sP[12 + k];
+  const float pw = 1.0f / (hom[3] + 0.0000001f);
+  const float nx = hom[0] * pw, ny = hom[1] * pw;
+  float out = 0.0f;
+  if (!(nx < -1.3f || nx > 1.3f || ny < -1.3f || ny > 1.3f)) {
+    float s[3], R[9], Sg[9];
+    load3(scales, i, s);
+    quat_to_R(ldg4(rots + 4 * i), R);
+    cov3d(s, R, Sg);
+    Cov2D cv;
+    cov2d(sV, p, Sg, fx, fy, tanfovx, tanfovy, LGR_FILTER_MAX, cv);
+    float det;
+    const float rad = radius_from_cov(cv.a, cv.b, cv.c, det);
+    if (det != 0.0f) out = rad;
+  }
+  radii[i] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward projection
+// ---------------------------------------------------------------------------------------------------------
+template <bool USE_SH>
+__global__ void __launch_bounds__(PROJ_THREADS)
+project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ opac,
+                   const float* __restrict__ scales, const float* __restrict__ rots,
+                   const float* __restrict__ colors, const float* __restrict__ shs, float* __restrict__ splat,
+                   int32_t* __restrict__ radii, uint8_t* __restrict__ clamped, int32_t* __restrict__ tile_count,
+                   int32_t* __restrict__ meta) {
+  __shared__ float sV[16], sP[16], sCam[3];
+  __shared__ unsigned long long sStock[PROJ_THREADS / 32];
+  __shared__ int sVis[PROJ_THREADS / 32];
+  if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sP[threadIdx.x] = v.proj[threadIdx.x]; }
+  if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
+  int rad_out = 0;
+  unsigned long long stock_tiles = 0;
+  if (i < n) {
+    float p[3], s[3], R[9], Sg[9];
+    load3(means, i, p);
+    load3(scales, i, s);
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[k] *= v.scale_mod;
+    quat_to_R(ldg4(rots + 4 * i), R);
+    cov3d(s, R, Sg);
+    Cov2D cv;
+    cov2d(sV, p, Sg, v.fx, v.fy, v.tanfovx, v.tanfovy, v.filter_mode, cv);
+    float det;
+    const float radf = radius_from_cov(cv.a, cv.b, cv.c, det);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    if (cv.t[2] > NEAR_Z && det > 0.0f) {
+      float hom[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) hom[k] = p[0] * sP[k] + p[1] * sP[4 + k] + p[2] * sP[8 + k] + sP[12 + k];
+      const float pw = 1.0f / (hom[3] + 0.0000001f);
+      const float px = ((hom[0] * pw + 1.0f) * v.W - 1.0f) * 0.5f;
+      const float py = ((hom[1] * pw + 1.0f) * v.H - 1.0f) * 0.5f;
+      const int rad = (int)ceilf(radf);
+      int x0, y0, x1, y1;
+      tile_rect(px, py, rad, v.gx, v.gy, x0, y0, x1, y1);
+      if ((x1 - x0) * (y1 - y0) > 0) {
+        rad_out = rad;
+        stock_tiles = (unsigned long long)((x1 - x0) * (max(0, min(y1, v.row1) - max(y0, v.row0))));
+        const float idet = 1.0f / det;
+        const float o = __ldg(opac + i);
+        // conservative half extents of {alpha >= 1/255}:  d^T Conic d <= 2 ln(255 o)  =>  |dx| <= sqrt(q a)
+        float hx = 0.f, hy = 0.f;
+        bool reach = o * 255.0f >= 1.0f;
+        if (reach) {
+          const float q = 2.0f * logf(o * 255.0f) * 1.004f + 1e-3f;
+          hx = sqrtf(q * cv.a) * 1.001f + 1e-3f;
+          hy = sqrtf(q * cv.c) * 1.001f + 1e-3f;
+        }
+        float rgb[3];
+        if (USE_SH) {
+          float d[3] = {p[0] - sCam[0], p[1] - sCam[1], p[2] - sCam[2]};
+          const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+          float B[16];
+          sh_basis(v.sh_degree, d[0] * inv, d[1] * inv, d[2] * inv, B);
+          const int nb = (v.sh_degree + 1) * (v.sh_degree + 1);
+          const float* sh = shs + (int64_t)i * v.sh_K * 3;
+          rgb[0] = rgb[1] = rgb[2] = 0.5f;
+          for (int k = 0; k < nb; k++) {
+            rgb[0] += B[k] * __ldg(sh + 3 * k); rgb[1] += B[k] * __ldg(sh + 3 * k + 1); rgb[2] += B[k] * __ldg(sh + 3 * k + 2);
+          }
+          uint8_t cl = 0;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) if (rgb[ch] < 0.0f) { cl |= (uint8_t)(1u << ch); rgb[ch] = 0.0f; }
+          clamped[i] = cl;
+        } else {
+          load3(colors, i, rgb);
+        }
+        r0 = make_float4(px, py, cv.c * idet, -cv.b * idet);
+        r1 = make_float4(cv.a * idet, o, hx, hy);
+        r2 = make_float4(rgb[0], rgb[1], rgb[2], cv.t[2]);
+        if (reach) {
+          tile_rect_tight(px, py, rad, hx, hy, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
+          for (int ty = y0; ty < y1; ty++)
+            for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + (ty - v.row0) * v.gx + tx, 1);
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(splat + i * LGR_SPLAT_FLOATS);
+    dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    radii[i] = rad_out;
+    if (USE_SH && rad_out == 0) clamped[i] = 0;
+  }
+  // block statistics: D by the stock rule, number of visible Gaussians (one atomic pair per CTA)
+  int vis = rad_out > 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    stock_tiles += __shfl_xor_sync(0xffffffffu, stock_tiles, o);
+    vis += __shfl_xor_sync(0xffffffffu, vis, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sStock[threadIdx.x >> 5] = stock_tiles; sVis[threadIdx.x >> 5] = vis; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0; int b = 0;
+#pragma unroll
+    for (int w = 0; w < PROJ_THREADS / 32; w++) { a += sStock[w]; b += sVis[w]; }
+    if (a) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 2), a);
+    if (b) atomicAdd(meta + 4, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward projection: dsplat (d/dpx, d/dpy, d/dconic xyz, d/dopacity, d/drgb) -> input gradients
+// ---------------------------------------------------------------------------------------------------------
+template <bool USE_SH>
+__global__ void __launch_bounds__(PROJ_THREADS)
+project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ scales,
+                   const float* __restrict__ rots, const float* __restrict__ shs, const int32_t* __restrict__ radii,
+                   const uint8_t* __restrict__ clamped, const float* __restrict__ dsplat, float* __restrict__ dmeans,
+                   float* __restrict__ dmeans2D, float* __restrict__ dopac, float* __restrict__ dscales,
+                   float* __restrict__ drots, float* __restrict__ dcolors, float* __restrict__ dshs) {
+  __shared__ float sV[16], sP[16], sCam[3];
+  if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sP[threadIdx.x] = v.proj[threadIdx.x]; }
+  if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
+  if (i >= n) return;
+  float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dop = 0.f, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+  float drgb[3] = {0.f, 0.f, 0.f};
+  const bool live = radii[i] > 0;
+  const int K = v.sh_K;
+  if (live) {
+    const float4 g0 = ldg4(dsplat + i * LGR_GRAD_FLOATS);       // d/dpx d/dpy d/dconx d/dcony
+    const float4 g1 = ldg4(dsplat + i * LGR_GRAD_FLOATS + 4);   // d/dconz d/dop d/dr d/dg
+    const float4 g2 = ldg4(dsplat + i * LGR_GRAD_FLOATS + 8);   // d/db
+    float p[3], s0[3], s[3], R[9], Sg[9];
+    load3(means, i, p);
+    load3(scales, i, s0);
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[k] = s0[k] * v.scale_mod;
+    const float4 q = ldg4(rots + 4 * i);
+    quat_to_R(q, R);
+    cov3d(s, R, Sg);
+    Cov2D cv;
+    cov2d(sV, p, Sg, v.fx, v.fy, v.tanfovx, v.tanfovy, v.filter_mode, cv);
+    dop = g1.y;
+    drgb[0] = g1.z; drgb[1] = g1.w; drgb[2] = g2.x;
+    // conic -> cov2D (true derivatives; d/dconic_y is w.r.t. the single off-diagonal parameter)
+    const float a = cv.a, b = cv.b, c = cv.c;
+    const float det = a * c - b * b, idet2 = 1.0f / (det * det);
+    float da = idet2 * (-c * c * g0.z + b * c * g0.w + (det - a * c) * g1.x);
+    float dc = idet2 * (-a * a * g1.x + a * b * g0.w + (det - a * c) * g0.z);
+    const float db = idet2 * (2.f * b * c * g0.z - (det + 2.f * b * b) * g0.w + 2.f * a * b * g1.x);
+    if (v.filter_mode == LGR_FILTER_MAX) {
+      if (!(cv.a_raw >= FILTER_VAR)) da = 0.f;
+      if (!(cv.c_raw >= FILTER_VAR)) dc = 0.f;
+    }
+    const float G00 = da, G01 = 0.5f * db, G11 = dc;
+    // dSigma = T^T G T
+    float GT[6];
+#pragma unroll
+    for (int j = 0; j < 3; j++) { GT[j] = G00 * cv.T[j] + G01 * cv.T[3 + j]; GT[3 + j] = G01 * cv.T[j] + G11 * cv.T[3 + j]; }
+    float dS[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) dS[r * 3 + j] = cv.T[r] * GT[j] + cv.T[3 + r] * GT[3 + j];
+    // Sigma = M M^T, M = R diag(s): dM = 2 dS M
+    float dR[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const float dMrk = 2.f * (dS[r * 3] * R[k] * s[k] + dS[r * 3 + 1] * R[3 + k] * s[k] + dS[r * 3 + 2] * R[6 + k] * s[k]);
+        acc += dMrk * R[r * 3 + k];
+        dR[r * 3 + k] = dMrk * s[k];
+      }
+      dsc[k] = acc * v.scale_mod;
+    }
+    {
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+      dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+      dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+      dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+    }
+    // dT = 2 G T Sigma ; dJ = dT W^T  (only J00,J02,J11,J12 depend on t)
+    float TS[6], dT[6];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) TS[r * 3 + j] = cv.T[r * 3] * Sg[j] + cv.T[r * 3 + 1] * Sg[3 + j] + cv.T[r * 3 + 2] * Sg[6 + j];
+#pragma unroll
+    for (int j = 0; j < 3; j++) { dT[j] = 2.f * (G00 * TS[j] + G01 * TS[3 + j]); dT[3 + j] = 2.f * (G01 * TS[j] + G11 * TS[3 + j]); }
+    const float dJ00 = dT[0] * sV[0] + dT[1] * sV[4] + dT[2] * sV[8];
+    const float dJ02 = dT[0] * sV[2] + dT[1] * sV[6] + dT[2] * sV[10];
+    const float dJ11 = dT[3] * sV[1] + dT[4] * sV[5] + dT[5] * sV[9];
+    const float dJ12 = dT[3] * sV[2] + dT[4] * sV[6] + dT[5] * sV[10];
+    const float tz = cv.t[2], itz = 1.0f / tz, itz2 = itz * itz, itz3 = itz2 * itz;
+    const float limx = CLAMP_FOV * v.tanfovx, limy = CLAMP_FOV * v.tanfovy;
+    const float txc = fminf(limx, fmaxf(-limx, cv.t[0] * itz)) * tz, tyc = fminf(limy, fmaxf(-limy, cv.t[1] * itz)) * tz;
+    float dt[3];
+    dt[0] = cv.inx ? -v.fx * itz2 * dJ02 : 0.f;
+    dt[1] = cv.iny ? -v.fy * itz2 * dJ12 : 0.f;
+    dt[2] = -v.fx * itz2 * dJ00 - v.fy * itz2 * dJ11 + 2.f * v.fx * txc * itz3 * dJ02 + 2.f * v.fy * tyc * itz3 * dJ12;
+#pragma unroll
+    for (int r = 0; r < 3; r++) dm[r] = sV[r * 4] * dt[0] + sV[r * 4 + 1] * dt[1] + sV[r * 4 + 2] * dt[2];
+    // screen-space mean: pixel -> ndc -> homogeneous
+    float hom[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) hom[k] = p[0] * sP[k] + p[1] * sP[4 + k] + p[2] * sP[8 + k] + sP[12 + k];
+    const float pw = 1.0f / (hom[3] + 0.0000001f);
+    dm2[0] = g0.x * 0.5f * v.W; dm2[1] = g0.y * 0.5f * v.H;
+    const float dh0 = dm2[0] * pw, dh1 = dm2[1] * pw, dh3 = -(dm2[0] * hom[0] + dm2[1] * hom[1]) * pw * pw;
+#pragma unroll
+    for (int r = 0; r < 3; r++) dm[r] += sP[r * 4] * dh0 + sP[r * 4 + 1] * dh1 + sP[r * 4 + 3] * dh3;
+    if (USE_SH) {
+      float d[3] = {p[0] - sCam[0], p[1] - sCam[1], p[2] - sCam[2]};
+      const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      const float x = d[0] * inv, y = d[1] * inv, z = d[2] * inv;
+      const uint8_t cl = clamped[i];
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) if (cl & (1u << ch)) drgb[ch] = 0.f;
+      float B[16];
+      sh_basis(v.sh_degree, x, y, z, B);
+      const int nb = (v.sh_degree + 1) * (v.sh_degree + 1);
+      const float* sh = shs + (int64_t)i * K * 3;
+      float* dsh = dshs + (int64_t)i * K * 3;
+      // c_k = sum_ch shs[k][ch] * drgb[ch]
+      float ck[16];
+      for (int k = 0; k < nb; k++) {
+        ck[k] = __ldg(sh + 3 * k) * drgb[0] + __ldg(sh + 3 * k + 1) * drgb[1] + __ldg(sh + 3 * k + 2) * drgb[2];
+        dsh[3 * k] = B[k] * drgb[0]; dsh[3 * k + 1] = B[k] * drgb[1]; dsh[3 * k + 2] = B[k] * drgb[2];
+      }
+      for (int k = nb; k < K; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+      float dd[3] = {0.f, 0.f, 0.f};
+      if (v.sh_degree > 0) {
+        dd[1] += -SH_C1 * ck[1]; dd[2] += SH_C1 * ck[2]; dd[0] += -SH_C1 * ck[3];
+        if (v.sh_degree > 1) {
+          const float xx = x * x, yy = y * y, zz = z * z;
+          dd[0] += SH_C2[0] * y * ck[4] + SH_C2[2] * -2.f * x * ck[6] + SH_C2[3] * z * ck[7] + SH_C2[4] * 2.f * x * ck[8];
+          dd[1] += SH_C2[0] * x * ck[4] + SH_C2[1] * z * ck[5] + SH_C2[2] * -2.f * y * ck[6] + SH_C2[4] * -2.f * y * ck[8];
+          dd[2] += SH_C2[1] * y * ck[5] + SH_C2[2] * 4.f * z * ck[6] + SH_C2[3] * x * ck[7];
+          if (v.sh_degree > 2) {
+            dd[0] += SH_C3[0] * 6.f * x * y * ck[9] + SH_C3[1] * y * z * ck[10] + SH_C3[2] * -2.f * x * y * ck[11] +
+                     SH_C3[3] * -6.f * x * z * ck[12] + SH_C3[4] * (4.f * zz - 3.f * xx - yy) * ck[13] +
+                     SH_C3[5] * 2.f * x * z * ck[14] + SH_C3[6] * (3.f * xx - 3.f * yy) * ck[15];
+            dd[1] += SH_C3[0] * (3.f * xx - 3.f * yy) * ck[9] + SH_C3[1] * x * z * ck[10] +
+                     SH_C3[2] * (4.f * zz - xx - 3.f * yy) * ck[11] + SH_C3[3] * -6.f * y * z * ck[12] +
+                     SH_C3[4] * -2.f * x * y * ck[13] + SH_C3[5] * -2.f * y * z * ck[14] + SH_C3[6] * -6.f * x * y * ck[15];
+            dd[2] += SH_C3[1] * x * y * ck[10] + SH_C3[2] * 8.f * y * z * ck[11] +
+                     SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy) * ck[12] + SH_C3[4] * 8.f * x * z * ck[13] +
+                     SH_C3[5] * (xx - yy) * ck[14];
+          }
+        }
+      }
+      const float dot = x * dd[0] + y * dd[1] + z * dd[2];
+      dm[0] += (dd[0] - x * dot) * inv; dm[1] += (dd[1] - y * dot) * inv; dm[2] += (dd[2] - z * dot) * inv;
+    }
+  } else if (USE_SH) {
+    float* dsh = dshs + (int64_t)i * K * 3;
+    for (int k = 0; k < K * 3; k++) dsh[k] = 0.f;
+  }
+  dmeans[3 * i] = dm[0]; dmeans[3 * i + 1] = dm[1]; dmeans[3 * i + 2] = dm[2];
+  dmeans2D[3 * i] = dm2[0]; dmeans2D[3 * i + 1] = dm2[1]; dmeans2D[3 * i + 2] = 0.f;
+  dopac[i] = dop;
+  dscales[3 * i] = dsc[0]; dscales[3 * i + 1] = dsc[1]; dscales[3 * i + 2] = dsc[2];
+  reinterpret_cast<float4*>(drots)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+  if (!USE_SH) { dcolors[3 * i] = drgb[0]; dcolors[3 * i + 1] = drgb[1]; dcolors[3 * i + 2] = drgb[2]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host launchers (called from lgr_capi.cu)
+// ---------------------------------------------------------------------------------------------------------
+int launch_compute_radius(int64_t n, const float* means, const float* scales, const float* rots, const float* proj,
+                          const float* view, float fx, float fy, float tx, float ty, float* radii, cudaStream_t st) {
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
+  ProfScope ps(K_COMPUTE_RADIUS, st);
+  compute_radius_kernel<<<blocks, PROJ_THREADS, 0, st>>>(n, means, scales, rots, proj, view, fx, fy, tx, ty, radii);
+  LGR_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_project_fwd(const View& v, int64_t n, const float* means, const float* opac, const float* scales,
+                       const float* rots, const float* colors, const float* shs, float* splat, int32_t* radii,
+                       uint8_t* clamped, int32_t* tile_count, int32_t* meta, cudaStream_t st) {
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
+  ProfScope ps(K_PROJECT_FWD, st);
+  if (colors)
+    project_fwd_kernel<false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
+  else
+    project_fwd_kernel<true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
+  LGR_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_project_bwd(const View& v, int64_t n, const float* means, const float* scales, const float* rots,
+                       const float* shs, bool use_sh, const int32_t* radii, const uint8_t* clamped, const float* dsplat,
+                       float* dmeans, float* dmeans2D, float* dopac, float* dscales, float* drots, float* dcolors,
+                       float* dshs, cudaStream_t st) {
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
+  ProfScope ps(K_PROJECT_BWD, st);
+  if (!use_sh)
+    project_bwd_kernel<false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs);
+  else
+    project_bwd_kernel<true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs);
+  LGR_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace lgr

@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's rasteriser interface, over the C ABI (include/log_b200_raster.h).
+
+Reference surface reproduced here (all call sites are in /root/reference):
+  * ``GaussianRasterizationSettings(image_height, image_width, tanfovx, tanfovy, bg, scale_modifier, viewmatrix,
+    projmatrix, sh_degree, campos, prefiltered, debug)``            -- kwargs at LoG/render/renderer.py:63-76
+  * ``GaussianRasterizer(raster_settings=...)`` ; ``.raster_settings`` read back at
+    LoG/model/level_of_gaussian.py:73-78
+  * ``rasterizer(means3D=, means2D=, shs=, colors_precomp=, opacities=, scales=, rotations=, cov3D_precomp=
+    [, use_filter=])``                                              -- LoG/render/renderer.py:141-153, :190
+  * stock flavour returns ``(image, radii)`` (renderer.py:160-161); the fork flavour returns
+    ``(image, radii, point_id_pixel, point_weight_pixel, point_weight)`` (renderer.py:154-155)
+  * ``rasterizer.compute_radius(xyz, scaling, rotation)`` (fork only) -- LoG/model/level_of_gaussian.py:59
+  * ``means2D.grad`` is populated with d loss / d (NDC x, y)        -- read at LoG/model/counter.py:40
+
+PyTorch is used for device memory, the current stream and autograd plumbing only; every computation is a
+hand-written sm_100a kernel behind the C ABI.  There is no CPU path: CPU tensors raise.
+"""
+import ctypes
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _capi
+from ._capi import LGR_FILTER_ADD, LGR_FILTER_MAX, LGR_FILTER_NONE, LgrView
+
+FLAVOUR_STOCK = 'stock'   # diff_gaussian_rasterization            (graphdeco-inria)   -> 2-tuple, cov += 0.3
+FLAVOUR_FORK = 'fork'     # diff_gaussian_rasterization_wodilate   (chingswy antialias) -> 5-tuple, cov = max(cov, 0.3)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None or t.numel() == 0 else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32c(t: Optional[torch.Tensor], name: str, device=None):
+    """float32, contiguous, 16-byte aligned CUDA tensor (what the C ABI requires)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _capi.LgrError(f'{name} is on {t.device}: log_b200 rasterises on CUDA only (no CPU fallback)')
+    if device is not None and t.device != device:
+        raise _capi.LgrError(f'{name} is on {t.device}, expected {device}')
+    if t.dtype != torch.float32:
+        raise TypeError(f'{name} must be float32, got {t.dtype}')
+    t = t.detach()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep):
+    dev = s.viewmatrix.device
+    vm, pm = _f32c(s.viewmatrix, 'viewmatrix'), _f32c(s.projmatrix, 'projmatrix', dev)
+    bg = _f32c(s.bg, 'bg', dev)
+    cp = _f32c(s.campos, 'campos', dev) if s.campos is not None else None
+    keep.extend([vm, pm, bg, cp])
+    v = LgrView()
+    v.image_height, v.image_width = int(s.image_height), int(s.image_width)
+    v.tanfovx, v.tanfovy = float(s.tanfovx), float(s.tanfovy)
+    v.scale_modifier = float(s.scale_modifier)
+    v.sh_degree, v.sh_coeffs = int(s.sh_degree), int(sh_coeffs)
+    v.filter_mode, v.want_aux = int(filter_mode), int(bool(want_aux))
+    v.tile_row_begin, v.tile_row_end = (0, 0) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+    v.viewmatrix_d, v.projmatrix_d = vm.data_ptr(), pm.data_ptr()
+    v.campos_d = cp.data_ptr() if cp is not None else None
+    v.bg_d = bg.data_ptr()
+    return v
+
+
+class RasterState:
+    """Buffers produced by the forward and consumed by the backward (kept alive by autograd)."""
+    __slots__ = ('view', 'keep', 'n', 'num_instances', 'max_tile_len', 'stock_instances', 'num_visible', 'splat',
+                 'radii', 'clamped', 'tile_start', 'sorted_ids', 'final_T', 'n_contrib', 'sh')
+
+
+def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_precomp, shs, filter_mode, want_aux,
+                      tile_rows=None):
+    """Run the forward through the C ABI.  Returns (image, radii, pid, pwp, point_weight, state)."""
+    lib = _capi.load()
+    dev = means3D.device
+    n = int(means3D.shape[0])
+    keep = []
+    K = 0 if shs is None else int(shs.shape[1])
+    view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep)
+    H, W = view.image_height, view.image_width
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    rows = gy if tile_rows is None else int(tile_rows[1]) - int(tile_rows[0])
+    ntiles = gx * rows
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    splat = torch.empty((n, _capi.LGR_SPLAT_FLOATS), **f32)
+    radii = torch.empty((n,), **i32)
+    clamped = torch.empty((n,), dtype=torch.uint8, device=dev) if shs is not None else None
+    tile_start = torch.empty((ntiles + 1,), **i32)
+    tile_cursor = torch.empty((max(ntiles, 1),), **i32)
+    meta = torch.empty((_capi.LGR_META_INTS,), **i32)
+    st = _stream()
+    _capi.check(lib.lgr_forward_project(ctypes.byref(view), n, _ptr(means3D), _ptr(opacities), _ptr(scales),
+                                        _ptr(rotations), _ptr(colors_precomp), _ptr(shs), _ptr(splat), _ptr(radii),
+                                        _ptr(clamped), _ptr(tile_start), _ptr(tile_cursor), _ptr(meta), st),
+                'lgr_forward_project')
+    m = meta.tolist()                                   # the one host sync of the forward (8 ints)
+    D, max_len = int(m[0]), int(m[1])
+    stock_D = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
+    u32 = dict(dtype=torch.int32, device=dev)
+    inst_key = torch.empty((D,), **u32)
+    inst_val = torch.empty((D,), **u32)
+    inst_tmp = torch.empty((2 * D,), **u32) if max_len > lib.lgr_sort_smem_capacity() else None
+    sorted_ids = torch.empty((D,), **i32)
+    # a sharded call owns only its rows; untouched rows stay zero so that ranks can be summed
+    image = torch.empty((3, H, W), **f32) if tile_rows is None else torch.zeros((3, H, W), **f32)
+    final_T = torch.empty((H, W), **f32) if tile_rows is None else torch.ones((H, W), **f32)
+    n_contrib = torch.empty((H, W), **i32) if tile_rows is None else torch.zeros((H, W), **i32)
+    pid = pwp = pw = None
+    if want_aux:
+        pid = torch.empty((H, W), **i32) if tile_rows is None else torch.full((H, W), -1, **i32)
+        pwp = torch.empty((H, W), **f32) if tile_rows is None else torch.zeros((H, W), **f32)
+        pw = torch.zeros((n,), **f32)
+    _capi.check(lib.lgr_forward_render(ctypes.byref(view), n, D, max_len, _ptr(splat), _ptr(radii), _ptr(tile_start),
+                                       _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
+                                       _ptr(sorted_ids), _ptr(image), _ptr(final_T), _ptr(n_contrib), _ptr(pid),
+                                       _ptr(pwp), _ptr(pw), st), 'lgr_forward_render')
+    s = RasterState()
+    s.view, s.keep, s.n, s.num_instances, s.max_tile_len = view, keep, n, D, max_len
+    s.stock_instances, s.num_visible = stock_D, int(m[4])
+    s.splat, s.radii, s.clamped, s.tile_start, s.sorted_ids = splat, radii, clamped, tile_start, sorted_ids
+    s.final_T, s.n_contrib, s.sh = final_T, n_contrib, shs is not None
+    return image, radii, pid, pwp, pw, s
+
+
+def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scales, rotations, colors_precomp, shs):
+    """Run the backward through the C ABI.  Returns (dmeans3D, dmeans2D, dopacities, dscales, drotations, dcolors, dshs)."""
+    lib = _capi.load()
+    dev = means3D.device
+    n = state.n
+    f32 = dict(dtype=torch.float32, device=dev)
+    g = _f32c(grad_image, 'grad_image', dev)
+    dsplat = torch.zeros((n, _capi.LGR_GRAD_FLOATS), **f32)
+    dmeans3D = torch.empty((n, 3), **f32)
+    dmeans2D = torch.empty((n, 3), **f32)
+    dopac = torch.empty((n,), **f32)
+    dscales = torch.empty((n, 3), **f32)
+    drot = torch.empty((n, 4), **f32)
+    dcolors = torch.empty((n, 3), **f32) if colors_precomp is not None else None
+    dshs = torch.empty_like(shs) if shs is not None else None
+    _capi.check(lib.lgr_backward(ctypes.byref(state.view), n, state.num_instances, _ptr(means3D), _ptr(opacities),
+                                 _ptr(scales), _ptr(rotations), _ptr(colors_precomp), _ptr(shs), _ptr(state.splat),
+                                 _ptr(state.radii), _ptr(state.clamped), _ptr(state.tile_start), _ptr(state.sorted_ids),
+                                 _ptr(state.final_T), _ptr(state.n_contrib), _ptr(g), _ptr(dsplat), _ptr(dmeans3D),
+                                 _ptr(dmeans2D), _ptr(dopac), _ptr(dscales), _ptr(drot), _ptr(dcolors), _ptr(dshs),
+                                 _stream()), 'lgr_backward')
+    return dmeans3D, dmeans2D, dopac, dscales, drot, dcolors, dshs
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, opacities, colors_precomp, shs, scales, rotations, settings, filter_mode, want_aux,
+                tile_rows):
+        dev = means3D.device
+        m = _f32c(means3D, 'means3D')
+        o = _f32c(opacities, 'opacities', dev)
+        sc = _f32c(scales, 'scales', dev)
+        r = _f32c(rotations, 'rotations', dev)
+        c = _f32c(colors_precomp, 'colors_precomp', dev)
+        sh = _f32c(shs, 'shs', dev)
+        image, radii, pid, pwp, pw, state = rasterize_forward(settings, m, o, sc, r, c, sh, filter_mode, want_aux, tile_rows)
+        ctx.state = state
+        ctx.opacity_shape = opacities.shape
+        ctx.save_for_backward(m, o, sc, r, c if c is not None else torch.empty(0, device=dev),
+                              sh if sh is not None else torch.empty(0, device=dev))
+        ctx.has_color, ctx.has_sh = c is not None, sh is not None
+        if want_aux:
+            ctx.mark_non_differentiable(radii, pid, pwp, pw)
+            return image, radii, pid, pwp, pw
+        ctx.mark_non_differentiable(radii)
+        return image, radii
+
+    @staticmethod
+    def backward(ctx, grad_image, *unused):
+        m, o, sc, r, c, sh = ctx.saved_tensors
+        c = c if ctx.has_color else None
+        sh = sh if ctx.has_sh else None
+        dm3, dm2, dop, dsc, drot, dcol, dsh = rasterize_backward(ctx.state, grad_image, m, o, sc, r, c, sh)
+        return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None
+
+
+class GaussianRasterizer(nn.Module):
+    """Drop-in for ``diff_gaussian_rasterization[_wodilate].GaussianRasterizer``."""
+    flavour = FLAVOUR_FORK
+
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+        self.tile_rows = None      # set by log_b200.sharded for tile-sharded multi-GPU rendering
+
+    def markVisible(self, positions):
+        """Stock API: boolean mask of points in front of the near plane (view z > 0.2)."""
+        with torch.no_grad():
+            V = self.raster_settings.viewmatrix
+            z = positions @ V[:3, 2] + V[3, 2]
+            return z > 0.2
+
+    def compute_radius(self, xyz, scaling, rotation):
+        """Fork API (level_of_gaussian.py:59): projected 3-sigma radius in pixels, 0 when culled."""
+        s = self.raster_settings
+        return compute_radius(xyz, scaling, rotation, s.projmatrix, s.viewmatrix,
+                              s.image_width / (2.0 * s.tanfovx), s.image_height / (2.0 * s.tanfovy), s.tanfovx, s.tanfovy)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, use_filter=True):
+        if (shs is None) == (colors_precomp is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if cov3D_precomp is not None:
+            raise NotImplementedError('cov3D_precomp is not supported: LoG always passes None (renderer.py:134,149)')
+        if scales is None or rotations is None:
+            raise Exception('Please provide scales and rotations')
+        fork = self.flavour == FLAVOUR_FORK
+        if fork:
+            filter_mode = LGR_FILTER_MAX if use_filter else LGR_FILTER_NONE
+        else:
+            filter_mode = LGR_FILTER_ADD
+        return _RasterizeGaussians.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
+                                         self.raster_settings, filter_mode, fork, self.tile_rows)
+
+
+class StockGaussianRasterizer(GaussianRasterizer):
+    """``diff_gaussian_rasterization.GaussianRasterizer``: (image, radii), +0.3 dilation."""
+    flavour = FLAVOUR_STOCK
+
+
+def compute_radius(means3D, scales, rotations, projmatrix, viewmatrix, focal_x, focal_y, tan_fovx, tan_fovy):
+    """Drop-in for ``compute_radius_module.compute_radius`` (LoG/cuda/compute_radius.py:3,
+    compute_radius_kernel.cu:158-183): same positional arguments, returns a float32 (N,) tensor."""
+    lib = _capi.load()
+    m = _f32c(means3D, 'means3D')
+    dev = m.device
+    s, r = _f32c(scales, 'scales', dev), _f32c(rotations, 'rotations', dev)
+    P, V = _f32c(projmatrix, 'projmatrix', dev), _f32c(viewmatrix, 'viewmatrix', dev)
+    n = int(m.shape[0])
+    out = torch.empty((n,), dtype=torch.float32, device=dev)
+    _capi.check(lib.lgr_compute_radius(n, _ptr(m), _ptr(s), _ptr(r), _ptr(P), _ptr(V), float(focal_x), float(focal_y),
+                                       float(tan_fovx), float(tan_fovy), _ptr(out), _stream()), 'lgr_compute_radius')
+    return out

@@ -1,0 +1,56 @@
+"""CPU: the C-ABI shared library builds for sm_100a, loads, and exports every symbol include/*.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'log_b200_raster.h')
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(lgr_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_declares_the_path():
+    names = declared_functions()
+    for want in ('lgr_compute_radius', 'lgr_forward_project', 'lgr_forward_render', 'lgr_backward', 'lgr_abi_version'):
+        assert want in names
+
+
+def test_library_loads_and_exports_every_declared_symbol(built):
+    from log_b200 import _capi
+    from log_b200.build import LIB_PATH
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    assert set(declared_functions()) == set(_capi.EXPORTS)
+    lib.lgr_abi_version.restype = ctypes.c_int
+    assert lib.lgr_abi_version() == _capi.LGR_ABI_VERSION          # pure host call, no GPU needed
+    assert _capi.load().lgr_sort_smem_capacity() > 1024
+
+
+def test_library_is_sm_100a_only(built):
+    from log_b200.build import LIB_PATH
+    out = subprocess.run(['cuobjdump', '-lelf', LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_(\d+a?)', out))
+    assert archs == {'100a'}, archs
+
+
+def test_view_struct_layout_matches_header():
+    from log_b200._capi import LgrView
+    src = open(HEADER).read()
+    body = re.search(r'typedef struct lgr_view \{(.*?)\} lgr_view;', src, flags=re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1] if not decl.startswith('const') else decl.split('*', 1)[1]
+        fields += [n.strip(' *') for n in names.split(',')]
+    assert fields == [f[0] for f in LgrView._fields_]

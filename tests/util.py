@@ -1,0 +1,62 @@
+"""Shared helpers for the parity tests (oracle-side only utilities live in oracle/)."""
+import numpy as np
+import torch
+
+from oracle import torch_dense as O
+
+
+def rel(a, b):
+    """Norm-wise relative error ||a-b|| / ||b||."""
+    a = np.asarray(a.detach().cpu().numpy() if hasattr(a, 'detach') else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if hasattr(b, 'detach') else b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def settings_from_camera(cam, device, sh_degree=None):
+    from log_b200 import GaussianRasterizationSettings
+    f = lambda t: t.to(device=device, dtype=torch.float32)
+    return GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=f(cam.bg), scale_modifier=cam.scale_modifier, viewmatrix=f(cam.viewmatrix), projmatrix=f(cam.projmatrix),
+        sh_degree=cam.sh_degree if sh_degree is None else sh_degree, campos=f(cam.campos), prefiltered=False, debug=False)
+
+
+def f32_camera(cam):
+    """Round every camera tensor to float32 (what the GPU path sees) but keep them as float64 for the fp64 oracle."""
+    r = lambda t: t.to(torch.float32).to(torch.float64)
+    return cam._replace(viewmatrix=r(cam.viewmatrix), projmatrix=r(cam.projmatrix), campos=r(cam.campos), bg=r(cam.bg),
+                        tanfovx=float(np.float32(cam.tanfovx)), tanfovy=float(np.float32(cam.tanfovy)))
+
+
+def run_gpu(cam, scene, G=None, flavour='fork', use_filter=True, sh_degree=0, device='cuda:0', tile_rows=None):
+    """Forward (+backward if G) through the public GaussianRasterizer API.  scene: dict of float tensors."""
+    from log_b200 import GaussianRasterizer, StockGaussianRasterizer
+    dev = torch.device(device)
+    s = settings_from_camera(cam, dev, sh_degree)
+    rast = (GaussianRasterizer if flavour == 'fork' else StockGaussianRasterizer)(s)
+    rast.tile_rows = tile_rows
+    t = {k: v.to(device=dev, dtype=torch.float32).requires_grad_(G is not None) for k, v in scene.items()}
+    n = t['means3D'].shape[0]
+    m2d = torch.zeros(n, 3, device=dev, requires_grad=G is not None)
+    kw = dict(means3D=t['means3D'], means2D=m2d, opacities=t['opacities'], scales=t['scales'], rotations=t['rotations'],
+              cov3D_precomp=None)
+    if sh_degree > 0 or 'colors' not in t:
+        kw.update(shs=t['shs'], colors_precomp=None)
+    else:
+        kw.update(shs=None, colors_precomp=t['colors'])
+    if flavour == 'fork' and not use_filter:
+        kw['use_filter'] = False
+    out = rast(**kw)
+    res = dict(image=out[0], radii=out[1])
+    if flavour == 'fork':
+        res.update(point_id_pixel=out[2], point_weight_pixel=out[3], point_weight=out[4])
+    if G is not None:
+        (out[0] * G.to(device=dev, dtype=torch.float32)).sum().backward()
+        res.update(dmeans3D=t['means3D'].grad, dmeans2D=m2d.grad, dopacities=t['opacities'].grad.reshape(-1),
+                   dscales=t['scales'].grad, drotations=t['rotations'].grad)
+        if kw['shs'] is not None:
+            res['dshs'] = t['shs'].grad
+        else:
+            res['dcolors'] = t['colors'].grad
+    torch.cuda.synchronize()
+    return res
