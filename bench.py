@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the hot path (BASELINE.json):
+forward + backward of the differentiable Gaussian-splatting rasteriser on synthetic Gaussians at 1080p.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 10m|100k|1k] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one view: project -> bin/sort -> blend -> backward sweep -> per-Gaussian
+backward.  `value` = Gaussians processed per second by the whole job with inputs resident in HBM; `e2e` = the same
+through the public GaussianRasterizer autograd API with HOST (pinned) inputs copied in and the loss read back every
+step.  N > 1: tile rows are sharded over ranks (strong scaling of ONE view), per-Gaussian gradients are reduced to
+owner ranks with NCCL; time = max over ranks.
+
+`--impl reference` times the CPU implementation of the same path (the oracle port: the reference's rasteriser is an
+un-vendored CUDA package that cannot be built or run on a CPU) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, W, H, median sigma px, sh_degree)   -- SURVEY.md 8(d) / BASELINE.json configs
+    '10m': (10_000_000, 1920, 1080, 1.5, 0),     # config 3 (the metric's configuration): precomputed colour, as LoG feeds
+    '100k': (100_000, 1920, 1080, 8.0, 3),       # config 1: SH degree 3 in-kernel
+    '1k': (1_000, 256, 256, 3.0, 0),             # config 0 (plumbing)
+}
+CPU_SAMPLE = {'10m': 1_000_000, '100k': 100_000, '1k': 1_000}   # Gaussians in the bounded CPU sample
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def algorithmic_bytes(n, H, W, D, sh_degree):
+    """per-kernel split of B_model = B_min + 112 D  (fp32)."""
+    b_in = 56 if sh_degree == 0 else 56 - 12 + 4 * 3 * (sh_degree + 1) ** 2
+    b_grad = 68 if sh_degree == 0 else 68 - 12 + 4 * 3 * (sh_degree + 1) ** 2
+    HW = H * W
+    k = {'project_fwd': n * b_in + n * 8, 'bin_sort': D * 32, 'blend_fwd': D * 40 + HW * 20,
+         'blend_bwd': D * 40 + HW * 12, 'project_bwd': n * b_in + n * b_grad}
+    b_min = n * b_in + n * 8 + HW * 20 + n * b_in + HW * 12 + n * b_grad
+    return k, b_min, b_min + 112 * D
+
+
+def make_inputs(workload, dtype=torch.float32):
+    from log_b200.synthetic import make_camera, make_cotangent, make_scene
+    n, W, H, r, deg = WORKLOADS[workload]
+    cam = make_camera(W, H, dtype=dtype, sh_degree=deg)
+    sc = make_scene(n, W, H, r, seed=0, sh_degree=deg, dtype=dtype)
+    G = make_cotangent(3, H, W, seed=1, dtype=dtype)
+    return cam, sc, G
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port (C, OpenMP, all host threads) on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    n, W, H, r, deg = WORKLOADS[args.workload]
+    ns = min(n, CPU_SAMPLE[args.workload])
+    cam, sc, G = make_inputs(args.workload)
+    sub = {k: v[:ns].numpy() for k, v in sc.items()}
+    kw = dict(colors_precomp=sub['colors']) if deg == 0 else dict(shs=sub['shs'])
+    cores = c_oracle.num_threads()
+
+    def step():
+        c_oracle.render(cam, sub['means3D'], sub['opacities'], sub['scales'], sub['rotations'],
+                        filter_mode=c_oracle.FILTER_MAX, dL_dimage=G.numpy(), dtype=np.float32, want_aux=True, **kw)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = ns / dt
+    sample = f'first {ns} of {n} Gaussians, {W}x{H}, fwd+bwd, fp32, {cores} OpenMP threads'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'gaussians_per_s_fwd_bwd', 'value': val, 'unit': 'Gaussians/s', 'n_gpus': 0,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / dt / 1e6,
+        'config': {'workload': f'{args.workload}: {n} Gaussians, {W}x{H}, sh_degree {deg}', 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': 'Gaussians/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'Gaussians/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='10m', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from log_b200 import GaussianRasterizationSettings, GaussianRasterizer, _capi, rasterize_backward, rasterize_forward
+    from log_b200 import sharded
+    from log_b200._capi import LGR_FILTER_MAX
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; log_b200 has no CPU fallback (use --impl reference for the CPU arm)')
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    n, W, H, r, deg = WORKLOADS[args.workload]
+    cam, sc, G = make_inputs(args.workload)
+    host = {k: v.pin_memory() for k, v in sc.items()}
+    host_G = G.pin_memory()
+    settings = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=cam.bg.to(dev), scale_modifier=1.0,
+        viewmatrix=cam.viewmatrix.to(dev), projmatrix=cam.projmatrix.to(dev), sh_degree=deg, campos=cam.campos.to(dev),
+        prefiltered=False, debug=False)
+    tile_rows = sharded.tile_row_partition(H, world)[rank] if world > 1 else None
+    d = {k: v.to(dev) for k, v in host.items()}
+    dG = host_G.to(dev)
+    col = d['colors'] if deg == 0 else None
+    shs = d['shs'] if deg > 0 else None
+    opac = d['opacities'].reshape(-1)
+    stats = {}
+
+    def step_resident():
+        img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
+                                                         LGR_FILTER_MAX, True, tile_rows)
+        g = rasterize_backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
+        stats['D'], stats['D_stock'], stats['maxlen'], stats['visible'] = st.num_instances, st.stock_instances, st.max_tile_len, st.num_visible
+        if world > 1:
+            packed = sharded.pack_grads((g[0], g[1], g[2], g[3], g[4], g[5] if deg == 0 else g[6].reshape(n, -1)))
+            return sharded.reduce_to_owners(packed)
+        return g
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _capi.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    prof = _capi.profile_collect()
+    _capi.profile_enable(False)
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # ---- end to end through the public API: pinned host inputs in, loss out, every step ----
+    e2e = None
+    if not args.no_e2e:
+        rast = GaussianRasterizer(settings)
+        rast.tile_rows = tile_rows
+        h2d = sum(v.numel() * 4 for k, v in host.items() if not (k == 'colors' and deg > 0)) + host_G.numel() * 4
+
+        def step_e2e():
+            t_ = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in host.items() if not (k == 'colors' and deg > 0)}
+            Gd = host_G.to(dev, non_blocking=True)
+            m2d = torch.zeros(n, 3, device=dev, requires_grad=True)
+            out = rast(means3D=t_['means3D'], means2D=m2d, shs=t_.get('shs') if deg > 0 else None,
+                       colors_precomp=t_['colors'] if deg == 0 else None, opacities=t_['opacities'], scales=t_['scales'],
+                       rotations=t_['rotations'], cov3D_precomp=None)
+            loss = (out[0] * Gd).sum()
+            loss.backward()
+            if world > 1:
+                sharded.reduce_to_owners(sharded.pack_grads((t_['means3D'].grad, m2d.grad, t_['opacities'].grad, t_['scales'].grad,
+                                                             t_['rotations'].grad, t_['colors'].grad if deg == 0 else t_['shs'].grad.reshape(n, -1))))
+            return float(loss.item())           # D2H read of the step's result
+        ne = max(3, min(args.steps, 10))
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ne):
+            step_e2e()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / ne], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': n / float(te.item()), 'unit': 'Gaussians/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+               'ms_per_step': float(te.item()) * 1e3, 'steps': ne}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    D_stock, D_bin = stats['D_stock'], stats['D']
+    kb, b_min, b_model = algorithmic_bytes(n, H, W, D_stock, deg)
+    kms = {'project_fwd': prof['project_fwd'][0], 'bin_sort': prof['tile_scan'][0] + prof['bin_scatter'][0] + prof['tile_sort'][0],
+           'blend_fwd': prof['blend_fwd'][0], 'blend_bwd': prof['blend_bwd'][0], 'project_bwd': prof['project_bwd'][0]}
+    kms = {k: v / args.steps for k, v in kms.items()}
+    dom = max(kms, key=kms.get)
+    ach = kb[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+    launches = sum(v[1] for v in prof.values())
+    line = {
+        'metric': 'gaussians_per_s_fwd_bwd', 'value': n / (ms_step * 1e-3), 'unit': 'Gaussians/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / (ms_step * 1e-3) / 1e6,
+        'config': {'workload': f'{args.workload}: {n} Gaussians, {W}x{H}, sh_degree {deg}, fork flavour (5-tuple aux outputs)',
+                   'parallelism': f'tile-row shard x{world}' if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
+                   'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible']},
+        'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                     'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes': kb[dom], 'kernel_ms': kms[dom]},
+        'roofline_step': {'b_model_bytes': b_model, 'b_min_bytes': b_min, 'achieved': b_model / (ms_step * 1e-3) / 1e9,
+                          'frac': b_model / (ms_step * 1e-3) / 1e9 / peak, 'b_min_frac': b_min / (ms_step * 1e-3) / 1e9 / peak},
+        'kernel_ms': kms, 'gpu_launches': launches, 'clocks': clk, 'e2e': e2e,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle          # the checker, timed as the CPU baseline (bounded sample)
+        ns = min(n, CPU_SAMPLE[args.workload])
+        sub = {k: v[:ns].numpy() for k, v in sc.items()}
+        kw = dict(colors_precomp=sub['colors']) if deg == 0 else dict(shs=sub['shs'])
+        t0 = time.perf_counter()
+        c_oracle.render(cam, sub['means3D'], sub['opacities'], sub['scales'], sub['rotations'], filter_mode=c_oracle.FILTER_MAX,
+                        dL_dimage=G.numpy(), dtype=np.float32, want_aux=True, **kw)
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = {'value': ns / dt, 'unit': 'Gaussians/s', 'cores': c_oracle.num_threads(), 'kind': 'port',
+                                'sample': f'first {ns} of {n} Gaussians, {W}x{H}, fwd+bwd, fp32 C oracle, 1 repetition', 'seconds': dt}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,60 @@
+"""Tile-sharded multi-GPU rendering (BASELINE config 4): one process per GPU, Gaussians replicated,
+each rank renders a contiguous band of 16-pixel tile rows, and the per-Gaussian gradients -- the only exchange step
+of the path -- are reduced to their owner rank (Gaussian index blocks) over NCCL.
+
+The reference has no multi-GPU path at all (`cfg.gpus` only sets CUDA_VISIBLE_DEVICES, apps/train.py:136-137).
+"""
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+GRAD_FLOATS_PRECOMP = 17   # means3D 3 + means2D 3 + opacity 1 + scales 3 + rotations 4 + colors 3
+
+
+def tile_row_partition(image_height: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous, near-equal bands of tile rows; band r belongs to rank r.  Bands can be empty when there are more
+    ranks than tile rows."""
+    gy = (image_height + 15) // 16
+    base, extra = divmod(gy, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append((start, start + n))
+        start += n
+    return out
+
+
+def owner_partition(num_gaussians: int, world_size: int) -> List[Tuple[int, int]]:
+    """Gaussian index blocks [lo,hi) owning the reduced gradient rows (equal chunk, last ranks may be short)."""
+    chunk = (num_gaussians + world_size - 1) // world_size
+    return [(min(num_gaussians, r * chunk), min(num_gaussians, (r + 1) * chunk)) for r in range(world_size)]
+
+
+def pack_grads(grads) -> torch.Tensor:
+    """(dmeans3D, dmeans2D, dopacities, dscales, drotations, dcolors) -> one (N, 17) row-major buffer."""
+    dm3, dm2, dop, dsc, drot, dcol = grads
+    return torch.cat([dm3, dm2, dop.reshape(-1, 1), dsc, drot, dcol], dim=1)
+
+
+def unpack_grads(buf: torch.Tensor):
+    return buf[:, 0:3], buf[:, 3:6], buf[:, 6], buf[:, 7:10], buf[:, 10:14], buf[:, 14:17]
+
+
+def reduce_to_owners(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the per-rank partial gradients; rank r receives rows owner_partition(N)[r] (zero padded to the chunk).
+    NCCL: one reduce_scatter over NVLink.  gloo (CPU tests): all_reduce + slice, same result."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n, f = packed.shape
+    chunk = (n + world - 1) // world
+    if n != chunk * world:
+        pad = torch.zeros((chunk * world - n, f), dtype=packed.dtype, device=packed.device)
+        packed = torch.cat([packed, pad], dim=0)
+    if dist.get_backend(group) == 'nccl':
+        out = torch.empty((chunk, f), dtype=packed.dtype, device=packed.device)
+        dist.reduce_scatter_tensor(out, packed.contiguous(), op=dist.ReduceOp.SUM, group=group)
+        return out
+    full = packed.clone()
+    dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full[rank * chunk:(rank + 1) * chunk].clone()

@@ -41,6 +41,9 @@ def lib():
     global _lib
     if _lib is None:
         build()
+        # two OpenMP runtimes live in one process (torch's bundled libgomp and the system one this .so links):
+        # spinning waiters of both oversubscribe the cores, so make ours sleep between parallel regions.
+        os.environ.setdefault('OMP_WAIT_POLICY', 'passive')
         _lib = ctypes.CDLL(LIB)
         for pfx in ('lgo64_', 'lgo32_'):
             getattr(_lib, pfx + 'render').restype = ctypes.c_int64
