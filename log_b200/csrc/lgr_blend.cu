@@ -37,6 +37,15 @@ __device__ __forceinline__ bool box_hits(const float4 r0, const float4 r1, const
   return (r0.x + r1.z >= s.x0) && (r0.x - r1.z <= s.x1) && (r0.y + r1.w >= s.y0) && (r0.y - r1.w <= s.y1);
 }
 
+// The skip decisions (power > 0, alpha < 1/255, T < 1e-4) must come out IDENTICAL in the forward and the backward
+// kernel, otherwise the transmittance the backward recovers by division drifts from the forward's.  Explicitly
+// rounded intrinsics are never contracted or re-associated, so both kernels execute the same arithmetic.
+__device__ __forceinline__ float eval_power(const float4 r0, const float4 r1, float dx, float dy) {
+  const float q = __fmaf_rn(r0.z, __fmul_rn(dx, dx), __fmul_rn(r1.x, __fmul_rn(dy, dy)));   // cx dx^2 + cz dy^2
+  return __fmaf_rn(-0.5f, q, -__fmul_rn(r0.w, __fmul_rn(dx, dy)));
+}
+__device__ __forceinline__ float eval_alpha(float opacity, float G) { return fminf(ALPHA_MAX, __fmul_rn(opacity, G)); }
+
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
@@ -80,13 +89,13 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           mask &= mask - 1;
           const int e = c0 + j;
           const float4 r0 = s_r0[e], r1 = s_r1[e];
-          const float dx = r0.x - pxf, dy = r0.y - pyf;
-          const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
-          const float alpha = fminf(ALPHA_MAX, r1.y * __expf(power));
+          const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
+          const float power = eval_power(r0, r1, dx, dy);
+          const float alpha = eval_alpha(r1.y, __expf(power));
           bool contrib = !done && power <= 0.0f && alpha >= ALPHA_MIN;
           float w = 0.f;
           if (contrib) {
-            const float test_T = T * (1.0f - alpha);
+            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
             if (test_T < T_STOP) { done = true; contrib = false; }
             else {
               w = alpha * T;
@@ -200,10 +209,10 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           mask &= ~(1u << j);
           const int e = c0 + j;
           const float4 r0 = s_r0[e], r1 = s_r1[e];
-          const float dx = r0.x - pxf, dy = r0.y - pyf;
-          const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
+          const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
+          const float power = eval_power(r0, r1, dx, dy);
           const float G = __expf(power);
-          const float alpha = fminf(ALPHA_MAX, r1.y * G);
+          const float alpha = eval_alpha(r1.y, G);
           const bool contrib = (base + e < ncon) && power <= 0.0f && alpha >= ALPHA_MIN;
           if (!__any_sync(FULL, contrib)) continue;
           float g[9];
@@ -211,7 +220,7 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           for (int k = 0; k < 9; k++) g[k] = 0.f;
           if (contrib) {
             const float4 r2 = s_r2[e];
-            T = T / (1.0f - alpha);
+            T = __fdiv_rn(T, __fsub_rn(1.0f, alpha));
             const float dch = alpha * T;
             acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
             acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
