@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 1
+#define LGR_ABI_VERSION 2
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -56,7 +56,8 @@ typedef struct lgr_view {
 #define LGR_SPLAT_FLOATS 12 /* per-Gaussian projected record: 3 x float4 */
 #define LGR_GRAD_FLOATS 12  /* per-Gaussian 2D-gradient accumulator: 3 x float4 */
 #define LGR_META_INTS 8     /* meta_d: [0]=D binned instances [1]=longest tile list [2..3]=D by the stock
-                               radius-square rule (lo,hi 32 bits) [4]=#Gaussians with radius>0 */
+                               radius-square rule (lo,hi 32 bits) [4]=#Gaussians with radius>0
+                               [5]=#tiles whose list exceeds the small shared-memory sort */
 
 int lgr_abi_version(void);
 
@@ -70,36 +71,37 @@ int lgr_compute_radius(int64_t n, const float* means3D_d, const float* scales_d,
  *   in : means3D (N,3) opacities (N) scales (N,3) rotations (N,4); colors_precomp (N,3) XOR shs (N,K,3)
  *   out: splat_d (N,12) radii_d (N) int32; clamped_d (N) uint8 (SH only, may be NULL with colors_precomp);
  *        tile_start_d (tiles+1) int32 exclusive scan of per-tile counts (tiles = gx * rows rendered);
- *        tile_cursor_d (tiles) int32 scratch; meta_d (LGR_META_INTS) int32.
- * The caller reads meta_d[0..1] (one 8-byte D2H) to size the instance buffers for lgr_forward_render. */
+ *        tile_cursor_d (2*tiles) int32 scratch; meta_d (LGR_META_INTS) int32.
+ * The caller reads meta_d (one 32-byte D2H) to size the instance buffers for lgr_forward_render. */
 int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d, const float* opacities_d,
                         const float* scales_d, const float* rotations_d, const float* colors_precomp_d,
                         const float* shs_d, float* splat_d, int32_t* radii_d, uint8_t* clamped_d,
                         int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, void* stream);
 
 /* Stage 2 of the forward: bin (Gaussian,tile) instances, per-tile (depth,index) radix sort, front-to-back blend.
- *   num_instances / max_tile_len : the values read from meta_d[0], meta_d[1]
+ *   num_instances / max_tile_len / num_long_tiles : the values read from meta_d[0], meta_d[1], meta_d[5]
  *   scratch: inst_key_d, inst_val_d (num_instances) uint32; inst_tmp_d (2*num_instances) uint32, only needed when
  *            max_tile_len exceeds the shared-memory sort capacity (lgr_sort_smem_capacity()), else may be NULL
  *   out: sorted_ids_d (num_instances) int32 (kept for backward); image_d (3,H,W); final_T_d (H,W);
  *        n_contrib_d (H,W) int32; when view->want_aux: point_id_pixel_d (H,W) int32, point_weight_pixel_d (H,W),
  *        point_weight_d (N) -- must be zero-filled by the caller. */
 int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, int32_t max_tile_len,
-                       const float* splat_d, const int32_t* radii_d, const int32_t* tile_start_d,
+                       int32_t num_long_tiles, const float* splat_d, const int32_t* radii_d, const int32_t* tile_start_d,
                        int32_t* tile_cursor_d, uint32_t* inst_key_d, uint32_t* inst_val_d, uint32_t* inst_tmp_d,
                        int32_t* sorted_ids_d, float* image_d, float* final_T_d, int32_t* n_contrib_d,
                        int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d, void* stream);
 int32_t lgr_sort_smem_capacity(void);
 
-/* Backward: per-tile back-to-front gradient sweep, then per-Gaussian projection backward.
- *   dsplat_d (N,12) scratch, zero-filled by the caller.
+/* Backward: per-tile gradient sweep (front to back, re-using the rendered image_d of the forward for the colour
+ * behind each splat), then per-Gaussian projection backward.
+ *   image_d (3,H,W): the forward's output, unmodified.  dsplat_d (N,12) scratch, zero-filled by the caller.
  *   out (each written for every Gaussian; culled ones get 0): dmeans3D (N,3) dmeans2D (N,3; d/d(ndc x,y), z = 0)
  *        dopacities (N) dscales (N,3) drotations (N,4) and dcolors (N,3) XOR dshs (N,K,3). */
 int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const float* means3D_d,
                  const float* opacities_d, const float* scales_d, const float* rotations_d,
                  const float* colors_precomp_d, const float* shs_d, const float* splat_d, const int32_t* radii_d,
                  const uint8_t* clamped_d, const int32_t* tile_start_d, const int32_t* sorted_ids_d,
-                 const float* final_T_d, const int32_t* n_contrib_d, const float* dL_dimage_d, float* dsplat_d,
+                 const float* image_d, const float* dL_dimage_d, float* dsplat_d,
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
                  float* dcolors_d, float* dshs_d, void* stream);
 

@@ -11,7 +11,7 @@ LGR_FILTER_ADD, LGR_FILTER_MAX, LGR_FILTER_NONE = 0, 1, 2
 LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
-LGR_ABI_VERSION = 1
+LGR_ABI_VERSION = 2
 
 EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
            'lgr_forward_render', 'lgr_backward', 'lgr_profile_enable', 'lgr_profile_collect',
@@ -50,9 +50,9 @@ def load():
     lib.lgr_forward_project.restype = ctypes.c_int
     lib.lgr_forward_project.argtypes = [ctypes.POINTER(LgrView), _i64] + [_vp] * 13
     lib.lgr_forward_render.restype = ctypes.c_int
-    lib.lgr_forward_render.argtypes = [ctypes.POINTER(LgrView), _i64, _i64, _i32] + [_vp] * 15
+    lib.lgr_forward_render.argtypes = [ctypes.POINTER(LgrView), _i64, _i64, _i32, _i32] + [_vp] * 15
     lib.lgr_backward.restype = ctypes.c_int
-    lib.lgr_backward.argtypes = [ctypes.POINTER(LgrView), _i64, _i64] + [_vp] * 23
+    lib.lgr_backward.argtypes = [ctypes.POINTER(LgrView), _i64, _i64] + [_vp] * 22
     lib.lgr_profile_enable.restype = ctypes.c_int
     lib.lgr_profile_enable.argtypes = [ctypes.c_int]
     lib.lgr_profile_collect.restype = ctypes.c_int

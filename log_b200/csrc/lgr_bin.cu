@@ -14,14 +14,16 @@ namespace lgr {
 // exclusive scan of tile counts (a few thousand tiles: one CTA)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 1024;
+constexpr int SORT_CAP_SMALL_FWD = 2560;
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* in: counts[0..ntiles) ; out: starts[0..ntiles] */,
-                 int32_t* __restrict__ cursor, int32_t* __restrict__ meta) {
+                 int32_t* __restrict__ cursor /* [0,ntiles): zeroed cursors ; [ntiles,2*ntiles): ids of long tiles */,
+                 int32_t* __restrict__ meta, int small_cap) {
   __shared__ int warp_sum[SCAN_THREADS / 32];
-  __shared__ int carry_s, maxl_s;
+  __shared__ int carry_s, maxl_s, nbig_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) { carry_s = 0; maxl_s = 0; }
+  if (tid == 0) { carry_s = 0; maxl_s = 0; nbig_s = 0; }
   __syncthreads();
   int local_max = 0;
   for (int base = 0; base < ntiles; base += SCAN_THREADS) {
@@ -42,7 +44,10 @@ tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* in: counts[0..n
     __syncthreads();
     const int carry = carry_s;
     const int excl = carry + (wid ? warp_sum[wid - 1] : 0) + x - c;
-    if (i < ntiles) { tile_start[i] = excl; cursor[i] = 0; }
+    if (i < ntiles) {
+      tile_start[i] = excl; cursor[i] = 0;
+      if (c > small_cap) cursor[ntiles + atomicAdd(&nbig_s, 1)] = i;   // tiles the small-smem sort cannot hold
+    }
     __syncthreads();
     if (tid == SCAN_THREADS - 1) carry_s = carry + warp_sum[31];
     __syncthreads();
@@ -51,7 +56,7 @@ tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* in: counts[0..n
   for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
   if (lane == 0) atomicMax(&maxl_s, local_max);
   __syncthreads();
-  if (tid == 0) { tile_start[ntiles] = carry_s; meta[0] = carry_s; meta[1] = maxl_s; }
+  if (tid == 0) { tile_start[ntiles] = carry_s; meta[0] = carry_s; meta[1] = maxl_s; meta[5] = nbig_s; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -90,6 +95,8 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_CAP_SMALL = SORT_CAP_SMALL_FWD;    // 40 KB dynamic smem: 4 CTAs / SM
+constexpr int SORT_CAP_LARGE = 13312;   // 208 KB dynamic smem: 1 CTA / SM
 
 // One pass over `len` items on digit (src[sel][i] >> shift) & 255, stable.  Warp w owns the contiguous segment
 // [w*seg, (w+1)*seg): it histograms it, then re-walks it 32 items at a time ranking equal digits with match.any.
@@ -177,12 +184,13 @@ __device__ __forceinline__ void sort_tile(uint32_t* kA, uint32_t* vA, uint32_t* 
 // mode 1: lists with lo < len are sorted in global memory (inst_* in place, tmp_* scratch).
 template <int MODE>
 __global__ void __launch_bounds__(SORT_THREADS)
-tile_sort_kernel(int ntiles, const int32_t* __restrict__ tile_start, uint32_t* __restrict__ inst_key,
+tile_sort_kernel(const int32_t* __restrict__ tile_list /* nullptr: tile = blockIdx.x */,
+                 const int32_t* __restrict__ tile_start, uint32_t* __restrict__ inst_key,
                  uint32_t* __restrict__ inst_val, uint32_t* __restrict__ tmp, int32_t* __restrict__ sorted_ids, int lo,
                  int cap, int id_bits) {
   extern __shared__ uint32_t smem_u32[];
   __shared__ int whist[SORT_WARPS * RADIX];
-  const int t = blockIdx.x;
+  const int t = tile_list ? tile_list[blockIdx.x] : (int)blockIdx.x;
   const int beg = tile_start[t], len = tile_start[t + 1] - beg;
   if (len <= lo || (MODE == 0 && len > cap)) return;
   if (MODE == 0) {
@@ -200,19 +208,17 @@ tile_sort_kernel(int ntiles, const int32_t* __restrict__ tile_start, uint32_t* _
   }
 }
 
-constexpr int SORT_CAP_SMALL = 2560;    // 40 KB dynamic smem: 4 CTAs / SM
-constexpr int SORT_CAP_LARGE = 13312;   // 208 KB dynamic smem: 1 CTA / SM
 
 int sort_smem_capacity() { return SORT_CAP_LARGE; }
 
 int launch_tile_scan(int ntiles, int32_t* tile_start, int32_t* cursor, int32_t* meta, cudaStream_t st) {
   ProfScope ps(K_TILE_SCAN, st);
-  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(ntiles, tile_start, cursor, meta);
+  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(ntiles, tile_start, cursor, meta, SORT_CAP_SMALL_FWD);
   LGR_CHECK_LAUNCH();
   return 0;
 }
 
-int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len, const float* splat,
+int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len, int num_long, const float* splat,
                         const int32_t* radii, const int32_t* tile_start, int32_t* cursor, uint32_t* inst_key,
                         uint32_t* inst_val, uint32_t* inst_tmp, int32_t* sorted_ids, cudaStream_t st) {
   if (n == 0 || num_inst == 0) return 0;
@@ -231,17 +237,19 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  ProfScope ps(K_TILE_SORT, st, 1 + (max_len > SORT_CAP_SMALL) + (max_len > SORT_CAP_LARGE));
-  tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * SORT_CAP_SMALL, st>>>(ntiles, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, SORT_CAP_SMALL, id_bits);
+  ProfScope ps(K_TILE_SORT, st, 1 + (num_long > 0) + (max_len > SORT_CAP_LARGE));
+  tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * SORT_CAP_SMALL, st>>>(nullptr, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, SORT_CAP_SMALL, id_bits);
   LGR_CHECK_LAUNCH();
-  if (max_len > SORT_CAP_SMALL) {
-    tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * SORT_CAP_LARGE, st>>>(ntiles, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_SMALL, SORT_CAP_LARGE, id_bits);
+  if (num_long > 0) {   // only the long tiles (listed by the scan kernel behind the cursors), smem sized to the longest
+    const int32_t* long_list = cursor + ntiles;
+    const int cap = min(max_len, SORT_CAP_LARGE);
+    tile_sort_kernel<0><<<num_long, SORT_THREADS, 16 * cap, st>>>(long_list, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_SMALL, cap, id_bits);
     LGR_CHECK_LAUNCH();
-  }
-  if (max_len > SORT_CAP_LARGE) {
-    if (!inst_tmp) return LGR_E_CAPACITY;
-    tile_sort_kernel<1><<<ntiles, SORT_THREADS, 0, st>>>(ntiles, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_LARGE, 0, id_bits);
-    LGR_CHECK_LAUNCH();
+    if (max_len > SORT_CAP_LARGE) {
+      if (!inst_tmp) return LGR_E_CAPACITY;
+      tile_sort_kernel<1><<<num_long, SORT_THREADS, 0, st>>>(long_list, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_LARGE, 0, id_bits);
+      LGR_CHECK_LAUNCH();
+    }
   }
   return 0;
 }

@@ -5,8 +5,8 @@
 // 3 x 16-byte gather per splat).  Each warp then tests 32 staged splats at once against its sub-tile
 // (lane = splat, conservative alpha>=1/255 box), ballots, and only walks the hits (lane = pixel, broadcast LDS).
 // With small splats this skips ~3/4 of the (pixel, splat) pairs the classic per-thread loop evaluates.
-// Backward: per hit the 9 partial gradients are reduced across the warp with a transposed butterfly (16 SHFL
-// instead of 45), accumulated per staged splat in shared memory, and flushed with 3 vector atomics per splat.
+// Backward: same front-to-back walk; per hit the 9 partial gradients are reduced across the warp through a
+// shared-memory transpose, accumulated per staged splat in shared memory, and flushed with 3 vector atomics per splat.
 #include "lgr_common.cuh"
 #include "lgr_prof.cuh"
 
@@ -38,13 +38,27 @@ __device__ __forceinline__ bool box_hits(const float4 r0, const float4 r1, const
 }
 
 // The skip decisions (power > 0, alpha < 1/255, T < 1e-4) must come out IDENTICAL in the forward and the backward
-// kernel, otherwise the transmittance the backward recovers by division drifts from the forward's.  Explicitly
-// rounded intrinsics are never contracted or re-associated, so both kernels execute the same arithmetic.
-__device__ __forceinline__ float eval_power(const float4 r0, const float4 r1, float dx, float dy) {
-  const float q = __fmaf_rn(r0.z, __fmul_rn(dx, dx), __fmul_rn(r1.x, __fmul_rn(dy, dy)));   // cx dx^2 + cz dy^2
+// kernel (the backward re-walks the list front to back and must stop where the forward stopped).  Explicitly rounded
+// intrinsics are never contracted or re-associated, so both kernels execute the same arithmetic.
+// The conic in the splat record is pre-multiplied by log2(e): alpha = o * 2^(power2).
+__device__ __forceinline__ float eval_power2(const float4 r0, const float con_z, float dx, float dy) {
+  const float q = __fmaf_rn(r0.z, __fmul_rn(dx, dx), __fmul_rn(con_z, __fmul_rn(dy, dy)));   // cx dx^2 + cz dy^2
   return __fmaf_rn(-0.5f, q, -__fmul_rn(r0.w, __fmul_rn(dx, dy)));
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float eval_alpha(float opacity, float G) { return fminf(ALPHA_MAX, __fmul_rn(opacity, G)); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void red_shared_max_u32(uint32_t addr, unsigned v) {
+  asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_shared_add_f32(uint32_t addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // forward
@@ -62,6 +76,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   const SubTile st = make_subtile(v, tile, lane, warp);
   const float pxf = (float)st.x, pyf = (float)st.y;
   const int beg = tile_start[tile], len = tile_start[tile + 1] - beg;
+  const uint32_t s_w_addr = smem_u32(s_w);
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, wmax = 0.f;
   int last = 0, wid = -1;
@@ -84,19 +99,20 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
         bool hit = false;
         if (e_l < cnt) hit = box_hits(s_r0[e_l], s_r1[e_l], st);
         unsigned mask = __ballot_sync(FULL, hit);
+        unsigned own_w = 0u;                 // max weight of the splat this lane tested, over this warp's pixels
         while (mask) {
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
           const int e = c0 + j;
-          const float4 r0 = s_r0[e], r1 = s_r1[e];
+          const float4 r0 = s_r0[e];
+          const float2 r1 = *reinterpret_cast<const float2*>(&s_r1[e]);    // (conic_z, opacity)
           const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
-          const float power = eval_power(r0, r1, dx, dy);
-          const float alpha = eval_alpha(r1.y, __expf(power));
-          bool contrib = !done && power <= 0.0f && alpha >= ALPHA_MIN;
+          const float power = eval_power2(r0, r1.x, dx, dy);
+          const float alpha = eval_alpha(r1.y, ex2_approx(power));
           float w = 0.f;
-          if (contrib) {
+          if (!done && power <= 0.0f && alpha >= ALPHA_MIN) {
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            if (test_T < T_STOP) { done = true; contrib = false; }
+            if (test_T < T_STOP) done = true;
             else {
               w = alpha * T;
               const float4 r2 = s_r2[e];
@@ -108,9 +124,10 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           }
           if (AUX) {
             const unsigned m = __reduce_max_sync(FULL, __float_as_uint(w));   // w >= 0: uint order == float order
-            if (lane == 0 && m > s_w[e]) atomicMax(&s_w[e], m);
+            if (lane == j) own_w = m;
           }
         }
+        if (AUX && own_w) red_shared_max_u32(s_w_addr + 4u * e_l, own_w);
         if (__all_sync(FULL, done)) break;
       }
     }
@@ -133,62 +150,45 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
 // ---------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------
-// Reduce 9 per-lane values over the warp.  On return lanes 2k and 2k+1 hold the warp total of slot k (k<16).
-__device__ __forceinline__ float warp_reduce9_transposed(const float in[9], int lane) {
-  float v[16];
-#pragma unroll
-  for (int i = 0; i < 9; i++) v[i] = in[i];
-#pragma unroll
-  for (int i = 9; i < 16; i++) v[i] = 0.f;
-#pragma unroll
-  for (int half = 8; half >= 1; half >>= 1) {
-    const bool hi = (lane & (half * 2)) != 0;
-#pragma unroll
-    for (int i = 0; i < half; i++) {
-      const float a = v[i], b = v[i + half];
-      const float send = hi ? a : b, keep = hi ? b : a;
-      v[i] = keep + __shfl_xor_sync(FULL, send, half * 2);
-    }
-  }
-  return v[0] + __shfl_xor_sync(FULL, v[0], 1);
-}
+// The sweep runs FRONT TO BACK, exactly like the forward: T_j comes from the same multiplications (no division
+// chain), the colour in front of j is the running prefix P_j, and the colour behind j follows from the rendered
+// pixel:  S_j = image - P_j - c_j a_j T_j  (= sum_{k>j} c_k a_k T_k + bg T_final).  Then
+//   dL/da_j = sum_c dL/dC_c * ( c_j T_j - S_j / (1 - a_j) )
+// which is the published back-to-front recurrence written in closed form.
+//
+// Per hit the 9 partial gradients of the 32 lanes are transposed through a per-warp shared-memory scratch
+// (3 STS per lane), 27 lanes each add up a third of one column (11 LDS), 3 partials are combined with 2 shuffles
+// and 9 lanes issue one red.shared.add each.  ~33 instructions instead of a 45-shuffle butterfly (~90).
+constexpr int GSTRIDE = 12;   // floats per scratch row (16-byte aligned rows, conflict-free 128-bit stores)
 
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
-                 const float* __restrict__ splat, const float* __restrict__ final_T,
-                 const int32_t* __restrict__ n_contrib, const float* __restrict__ dL_dimage, float* __restrict__ dsplat) {
+                 const float* __restrict__ splat, const float* __restrict__ image,
+                 const float* __restrict__ dL_dimage, float* __restrict__ dsplat) {
   __shared__ float4 s_r0[BATCH], s_r1[BATCH], s_r2[BATCH];
   __shared__ int s_id[BATCH];
   __shared__ float s_g[BATCH * 9];
-  __shared__ int s_max;
+  __shared__ __align__(16) float s_x[(BLEND_THREADS / 32) * 32 * GSTRIDE];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SubTile st = make_subtile(v, tile, lane, warp);
   const float pxf = (float)st.x, pyf = (float)st.y;
-  const int beg = tile_start[tile];
+  const int beg = tile_start[tile], len = tile_start[tile + 1] - beg;
+  float* xw = s_x + warp * 32 * GSTRIDE;                 // this warp's transpose scratch
+  const uint32_t s_g_addr = smem_u32(s_g);
+  const int red_k = lane % 9, red_s = lane / 9;          // lanes 0..26: column red_k, rows red_s, red_s+3, ...
 
-  float T_final = 1.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
-  int ncon = 0;
+  float I0 = 0.f, I1 = 0.f, I2 = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
   if (st.inside) {
     const int64_t pix = (int64_t)st.y * v.W + st.x, HW = (int64_t)v.H * v.W;
-    T_final = final_T[pix]; ncon = n_contrib[pix];
+    I0 = image[pix]; I1 = image[HW + pix]; I2 = image[2 * HW + pix];
     dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix];
   }
-  const float bgdot = __ldg(v.bg) * dp0 + __ldg(v.bg + 1) * dp1 + __ldg(v.bg + 2) * dp2;
-  if (tid == 0) s_max = 0;
-  __syncthreads();
-  {
-    const int m = __reduce_max_sync(FULL, ncon);
-    if (lane == 0 && m > 0) atomicMax(&s_max, m);
-  }
-  __syncthreads();
-  const int maxc = s_max;
-  const int wmaxc = __reduce_max_sync(FULL, ncon);   // this warp's deepest contributor
+  float T = 1.0f, P0 = 0.f, P1 = 0.f, P2 = 0.f;
+  bool done = !st.inside;
 
-  float T = T_final, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
-
-  for (int base = ((maxc - 1) / BATCH) * BATCH; base >= 0 && maxc > 0; base -= BATCH) {
-    const int cnt = min(BATCH, maxc - base);
-    __syncthreads();
+  for (int base = 0; base < len; base += BATCH) {
+    if (__syncthreads_and(done)) break;
+    const int cnt = min(BATCH, len - base);
     if (tid < cnt) {
       const int id = sorted_ids[beg + base + tid];
       const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
@@ -197,52 +197,67 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
     }
     for (int k = tid; k < cnt * 9; k += BLEND_THREADS) s_g[k] = 0.f;
     __syncthreads();
-    if (base < wmaxc) {
-      const int wcnt = min(cnt, wmaxc - base);
-      for (int c0 = ((wcnt - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+    if (!__all_sync(FULL, done)) {
+      for (int c0 = 0; c0 < cnt; c0 += 32) {
         const int e_l = c0 + lane;
         bool hit = false;
-        if (e_l < wcnt) hit = box_hits(s_r0[e_l], s_r1[e_l], st);
+        if (e_l < cnt) hit = box_hits(s_r0[e_l], s_r1[e_l], st);
         unsigned mask = __ballot_sync(FULL, hit);
         while (mask) {
-          const int j = 31 - __clz(mask);
-          mask &= ~(1u << j);
+          const int j = __ffs(mask) - 1;
+          mask &= mask - 1;
           const int e = c0 + j;
-          const float4 r0 = s_r0[e], r1 = s_r1[e];
+          const float4 r0 = s_r0[e];
+          const float2 r1 = *reinterpret_cast<const float2*>(&s_r1[e]);    // (conic_z, opacity)
           const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
-          const float power = eval_power(r0, r1, dx, dy);
-          const float G = __expf(power);
+          const float power = eval_power2(r0, r1.x, dx, dy);
+          const float G = ex2_approx(power);
           const float alpha = eval_alpha(r1.y, G);
-          const bool contrib = (base + e < ncon) && power <= 0.0f && alpha >= ALPHA_MIN;
+          bool contrib = !done && power <= 0.0f && alpha >= ALPHA_MIN;
+          float test_T = 0.f;
+          if (contrib) {
+            test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+            if (test_T < T_STOP) { done = true; contrib = false; }
+          }
           if (!__any_sync(FULL, contrib)) continue;
-          float g[9];
-#pragma unroll
-          for (int k = 0; k < 9; k++) g[k] = 0.f;
+          float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+          float gc = 0.f;
           if (contrib) {
             const float4 r2 = s_r2[e];
-            T = __fdiv_rn(T, __fsub_rn(1.0f, alpha));
-            const float dch = alpha * T;
-            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-            lc0 = r2.x; lc1 = r2.y; lc2 = r2.z;
-            float dL_dalpha = (r2.x - acc0) * dp0 + (r2.y - acc1) * dp1 + (r2.z - acc2) * dp2;
-            dL_dalpha *= T;
-            last_alpha = alpha;
-            dL_dalpha += (-T_final / (1.f - alpha)) * bgdot;
-            const float dL_dG = r1.y * dL_dalpha;      // 0.99 clamp is straight-through
-            const float gdx = G * dx, gdy = G * dy;
-            g[0] = dL_dG * (-gdx * r0.z - gdy * r0.w);
-            g[1] = dL_dG * (-gdy * r1.x - gdx * r0.w);
-            g[2] = -0.5f * gdx * dx * dL_dG;
-            g[3] = -gdx * dy * dL_dG;
-            g[4] = -0.5f * gdy * dy * dL_dG;
-            g[5] = G * dL_dalpha;
-            g[6] = dch * dp0; g[7] = dch * dp1; g[8] = dch * dp2;
+            const float w = alpha * T;
+            const float cw0 = r2.x * w, cw1 = r2.y * w, cw2 = r2.z * w;
+            const float S0 = I0 - P0 - cw0, S1 = I1 - P1 - cw1, S2 = I2 - P2 - cw2;   // colour behind j (+ bg T_final)
+            P0 += cw0; P1 += cw1; P2 += cw2;
+            const float inv = __frcp_rn(1.0f - alpha);
+            const float dL_dalpha = (r2.x * dp0 + r2.y * dp1 + r2.z * dp2) * T - (S0 * dp0 + S1 * dp1 + S2 * dp2) * inv;
+            T = test_T;
+            const float wG = r1.y * dL_dalpha * G;          // dL/dG * G ; the 0.99 clamp is straight-through
+            const float gdx = wG * dx, gdy = wG * dy;
+            ga.x = -(gdx * r0.z + gdy * r0.w);              // d/dpx   (x log2e, undone in project_bwd)
+            ga.y = -(gdy * r1.x + gdx * r0.w);              // d/dpy   (x log2e)
+            ga.z = -0.5f * gdx * dx;                        // d/dconic_x
+            ga.w = -gdx * dy;                               // d/dconic_y
+            gb.x = -0.5f * gdy * dy;                        // d/dconic_z
+            gb.y = G * dL_dalpha;                           // d/dopacity
+            gb.z = w * dp0; gb.w = w * dp1; gc = w * dp2;   // d/drgb
           }
-          const float tot = warp_reduce9_transposed(g, lane);
-          if (!(lane & 1) && lane < 18) atomicAdd(&s_g[e * 9 + (lane >> 1)], tot);
+          // transpose-reduce the 9 values over the warp
+          float4* row = reinterpret_cast<float4*>(xw + lane * GSTRIDE);
+          row[0] = ga; row[1] = gb; xw[lane * GSTRIDE + 8] = gc;
+          __syncwarp();
+          float sum = 0.f;
+          if (lane < 27) {
+#pragma unroll
+            for (int i = 0; i < 11; i++) {
+              const int r = red_s + 3 * i;
+              if (r < 32) sum += xw[r * GSTRIDE + red_k];
+            }
+          }
+          sum += __shfl_down_sync(FULL, sum, 9) + __shfl_down_sync(FULL, sum, 18);
+          if (lane < 9) red_shared_add_f32(s_g_addr + 4u * (e * 9 + lane), sum);
+          __syncwarp();
         }
+        if (__all_sync(FULL, done)) break;
       }
     }
     __syncthreads();
@@ -279,12 +294,11 @@ int launch_blend_fwd(const View& v, const int32_t* tile_start, const int32_t* so
 }
 
 int launch_blend_bwd(const View& v, const int32_t* tile_start, const int32_t* sorted_ids, const float* splat,
-                     const float* final_T, const int32_t* n_contrib, const float* dL_dimage, float* dsplat,
-                     cudaStream_t st) {
+                     const float* image, const float* dL_dimage, float* dsplat, cudaStream_t st) {
   const int ntiles = v.gx * (v.row1 - v.row0);
   if (ntiles <= 0) return 0;
   ProfScope ps(K_BLEND_BWD, st);
-  blend_bwd_kernel<<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, final_T, n_contrib, dL_dimage, dsplat);
+  blend_bwd_kernel<<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, dL_dimage, dsplat);
   LGR_CHECK_LAUNCH();
   return 0;
 }

@@ -12,13 +12,13 @@ int launch_project_bwd(const View&, int64_t, const float*, const float*, const f
                        const int32_t*, const uint8_t*, const float*, float*, float*, float*, float*, float*, float*,
                        float*, cudaStream_t);
 int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, cudaStream_t);
-int launch_bin_and_sort(const View&, int64_t, int64_t, int, const float*, const int32_t*, const int32_t*, int32_t*,
+int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, const int32_t*, int32_t*,
                         uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
 int sort_smem_capacity();
 int launch_blend_fwd(const View&, const int32_t*, const int32_t*, const float*, float*, float*, int32_t*, int32_t*,
                      float*, float*, cudaStream_t);
-int launch_blend_bwd(const View&, const int32_t*, const int32_t*, const float*, const float*, const int32_t*,
-                     const float*, float*, cudaStream_t);
+int launch_blend_bwd(const View&, const int32_t*, const int32_t*, const float*, const float*, const float*, float*,
+                     cudaStream_t);
 }  // namespace lgr
 
 using namespace lgr;
@@ -75,11 +75,11 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
 }
 
 int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, int32_t max_tile_len,
-                       const float* splat_d, const int32_t* radii_d, const int32_t* tile_start_d,
+                       int32_t num_long_tiles, const float* splat_d, const int32_t* radii_d, const int32_t* tile_start_d,
                        int32_t* tile_cursor_d, uint32_t* inst_key_d, uint32_t* inst_val_d, uint32_t* inst_tmp_d,
                        int32_t* sorted_ids_d, float* image_d, float* final_T_d, int32_t* n_contrib_d,
                        int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d, void* stream) {
-  if (!view_ok(view) || n < 0 || num_instances < 0 || !tile_start_d || !tile_cursor_d || !image_d || !final_T_d ||
+  if (!view_ok(view) || n < 0 || num_instances < 0 || num_long_tiles < 0 || !tile_start_d || !tile_cursor_d || !image_d || !final_T_d ||
       !n_contrib_d)
     return LGR_E_BADARG;
   if (num_instances > 0 && (!inst_key_d || !inst_val_d || !sorted_ids_d || !splat_d || !radii_d)) return LGR_E_BADARG;
@@ -87,7 +87,7 @@ int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, i
   if (num_instances > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const View v = make_view(view);
-  int rc = launch_bin_and_sort(v, n, num_instances, max_tile_len, splat_d, radii_d, tile_start_d, tile_cursor_d,
+  int rc = launch_bin_and_sort(v, n, num_instances, max_tile_len, num_long_tiles, splat_d, radii_d, tile_start_d, tile_cursor_d,
                                inst_key_d, inst_val_d, inst_tmp_d, sorted_ids_d, st);
   if (rc) return rc;
   return launch_blend_fwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, final_T_d, n_contrib_d, point_id_pixel_d,
@@ -98,11 +98,11 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  const float* opacities_d, const float* scales_d, const float* rotations_d,
                  const float* colors_precomp_d, const float* shs_d, const float* splat_d, const int32_t* radii_d,
                  const uint8_t* clamped_d, const int32_t* tile_start_d, const int32_t* sorted_ids_d,
-                 const float* final_T_d, const int32_t* n_contrib_d, const float* dL_dimage_d, float* dsplat_d,
+                 const float* image_d, const float* dL_dimage_d, float* dsplat_d,
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
                  float* dcolors_d, float* dshs_d, void* stream) {
   (void)opacities_d;
-  if (!view_ok(view) || n < 0 || !tile_start_d || !final_T_d || !n_contrib_d || !dL_dimage_d) return LGR_E_BADARG;
+  if (!view_ok(view) || n < 0 || !tile_start_d || !image_d || !dL_dimage_d) return LGR_E_BADARG;
   if (n == 0) return 0;
   const bool use_sh = shs_d != nullptr;
   if (use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
@@ -114,7 +114,7 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   cudaStream_t st = (cudaStream_t)stream;
   const View v = make_view(view);
   int rc = 0;
-  if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, final_T_d, n_contrib_d, dL_dimage_d, dsplat_d, st);
+  if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, dL_dimage_d, dsplat_d, st);
   if (rc) return rc;
   return launch_project_bwd(v, n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
                             dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, st);

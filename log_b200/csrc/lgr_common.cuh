@@ -15,6 +15,8 @@ constexpr float ALPHA_MIN = 1.0f / 255.0f;
 constexpr float T_STOP = 1e-4f;
 constexpr float FILTER_VAR = 0.3f;      // LoG/cuda/compute_radius_kernel.cu:61
 constexpr float CLAMP_FOV = 1.3f;       // compute_radius_kernel.cu:71-72
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 // Kernel-side copy of lgr_view with derived quantities.
 struct View {
@@ -44,6 +46,7 @@ inline View make_view(const lgr_view* v) {
 
 // ---- projected splat record: 3 x float4 per Gaussian ---------------------------------------------------
 //   r0 = (px, py, conic_x, conic_y)      r1 = (conic_z, opacity, hx, hy)      r2 = (r, g, b, depth)
+// The conic is stored pre-multiplied by log2(e) so that the blend can use ex2.approx directly.
 // (hx,hy) is a conservative half-extent of the region where alpha >= 1/255 can hold; it is only used to skip
 // work and never changes a result.
 

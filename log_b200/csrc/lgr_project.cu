@@ -123,8 +123,10 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
         } else {
           load3(colors, i, rgb);
         }
-        r0 = make_float4(px, py, cv.c * idet, -cv.b * idet);
-        r1 = make_float4(cv.a * idet, o, hx, hy);
+        // conic pre-multiplied by log2(e): the blend evaluates alpha = o * 2^(-0.5 d^T C' d)
+        const float kdet = LOG2E * idet;
+        r0 = make_float4(px, py, cv.c * kdet, -cv.b * kdet);
+        r1 = make_float4(cv.a * kdet, o, hx, hy);
         r2 = make_float4(rgb[0], rgb[1], rgb[2], cv.t[2]);
         if (reach) {
           tile_rect_tight(px, py, rad, hx, hy, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
@@ -258,7 +260,8 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
 #pragma unroll
     for (int k = 0; k < 4; k++) hom[k] = p[0] * sP[k] + p[1] * sP[4 + k] + p[2] * sP[8 + k] + sP[12 + k];
     const float pw = 1.0f / (hom[3] + 0.0000001f);
-    dm2[0] = g0.x * 0.5f * v.W; dm2[1] = g0.y * 0.5f * v.H;
+    // d/dpx, d/dpy were accumulated with the log2(e)-scaled conic: undo with ln 2
+    dm2[0] = g0.x * (LN2 * 0.5f) * v.W; dm2[1] = g0.y * (LN2 * 0.5f) * v.H;
     const float dh0 = dm2[0] * pw, dh1 = dm2[1] * pw, dh3 = -(dm2[0] * hom[0] + dm2[1] * hom[1]) * pw * pw;
 #pragma unroll
     for (int r = 0; r < 3; r++) dm[r] += sP[r * 4] * dh0 + sP[r * 4 + 1] * dh1 + sP[r * 4 + 3] * dh3;

@@ -91,7 +91,7 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
 class RasterState:
     """Buffers produced by the forward and consumed by the backward (kept alive by autograd)."""
     __slots__ = ('view', 'keep', 'n', 'num_instances', 'max_tile_len', 'stock_instances', 'num_visible', 'splat',
-                 'radii', 'clamped', 'tile_start', 'sorted_ids', 'final_T', 'n_contrib', 'sh')
+                 'radii', 'clamped', 'tile_start', 'sorted_ids', 'final_T', 'n_contrib', 'image', 'sh')
 
 
 def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_precomp, shs, filter_mode, want_aux,
@@ -113,7 +113,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     radii = torch.empty((n,), **i32)
     clamped = torch.empty((n,), dtype=torch.uint8, device=dev) if shs is not None else None
     tile_start = torch.empty((ntiles + 1,), **i32)
-    tile_cursor = torch.empty((max(ntiles, 1),), **i32)
+    tile_cursor = torch.empty((2 * max(ntiles, 1),), **i32)
     meta = torch.empty((_capi.LGR_META_INTS,), **i32)
     st = _stream()
     _capi.check(lib.lgr_forward_project(ctypes.byref(view), n, _ptr(means3D), _ptr(opacities), _ptr(scales),
@@ -121,7 +121,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
                                         _ptr(clamped), _ptr(tile_start), _ptr(tile_cursor), _ptr(meta), st),
                 'lgr_forward_project')
     m = meta.tolist()                                   # the one host sync of the forward (8 ints)
-    D, max_len = int(m[0]), int(m[1])
+    D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
     stock_D = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
     u32 = dict(dtype=torch.int32, device=dev)
     inst_key = torch.empty((D,), **u32)
@@ -137,7 +137,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         pid = torch.empty((H, W), **i32) if tile_rows is None else torch.full((H, W), -1, **i32)
         pwp = torch.empty((H, W), **f32) if tile_rows is None else torch.zeros((H, W), **f32)
         pw = torch.zeros((n,), **f32)
-    _capi.check(lib.lgr_forward_render(ctypes.byref(view), n, D, max_len, _ptr(splat), _ptr(radii), _ptr(tile_start),
+    _capi.check(lib.lgr_forward_render(ctypes.byref(view), n, D, max_len, num_long, _ptr(splat), _ptr(radii), _ptr(tile_start),
                                        _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
                                        _ptr(sorted_ids), _ptr(image), _ptr(final_T), _ptr(n_contrib), _ptr(pid),
                                        _ptr(pwp), _ptr(pw), st), 'lgr_forward_render')
@@ -145,7 +145,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     s.view, s.keep, s.n, s.num_instances, s.max_tile_len = view, keep, n, D, max_len
     s.stock_instances, s.num_visible = stock_D, int(m[4])
     s.splat, s.radii, s.clamped, s.tile_start, s.sorted_ids = splat, radii, clamped, tile_start, sorted_ids
-    s.final_T, s.n_contrib, s.sh = final_T, n_contrib, shs is not None
+    s.final_T, s.n_contrib, s.image, s.sh = final_T, n_contrib, image, shs is not None
     return image, radii, pid, pwp, pw, s
 
 
@@ -167,7 +167,7 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
     _capi.check(lib.lgr_backward(ctypes.byref(state.view), n, state.num_instances, _ptr(means3D), _ptr(opacities),
                                  _ptr(scales), _ptr(rotations), _ptr(colors_precomp), _ptr(shs), _ptr(state.splat),
                                  _ptr(state.radii), _ptr(state.clamped), _ptr(state.tile_start), _ptr(state.sorted_ids),
-                                 _ptr(state.final_T), _ptr(state.n_contrib), _ptr(g), _ptr(dsplat), _ptr(dmeans3D),
+                                 _ptr(state.image), _ptr(g), _ptr(dsplat), _ptr(dmeans3D),
                                  _ptr(dmeans2D), _ptr(dopac), _ptr(dscales), _ptr(drot), _ptr(dcolors), _ptr(dshs),
                                  _stream()), 'lgr_backward')
     return dmeans3D, dmeans2D, dopac, dscales, drot, dcolors, dshs
@@ -185,10 +185,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         c = _f32c(colors_precomp, 'colors_precomp', dev)
         sh = _f32c(shs, 'shs', dev)
         image, radii, pid, pwp, pw, state = rasterize_forward(settings, m, o, sc, r, c, sh, filter_mode, want_aux, tile_rows)
+        state.image = None          # the backward re-reads the rendered image: saved below so autograd guards it
         ctx.state = state
         ctx.opacity_shape = opacities.shape
         ctx.save_for_backward(m, o, sc, r, c if c is not None else torch.empty(0, device=dev),
-                              sh if sh is not None else torch.empty(0, device=dev))
+                              sh if sh is not None else torch.empty(0, device=dev), image)
         ctx.has_color, ctx.has_sh = c is not None, sh is not None
         if want_aux:
             ctx.mark_non_differentiable(radii, pid, pwp, pw)
@@ -198,9 +199,10 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_image, *unused):
-        m, o, sc, r, c, sh = ctx.saved_tensors
+        m, o, sc, r, c, sh, image = ctx.saved_tensors
         c = c if ctx.has_color else None
         sh = sh if ctx.has_sh else None
+        ctx.state.image = image
         dm3, dm2, dop, dsc, drot, dcol, dsh = rasterize_backward(ctx.state, grad_image, m, o, sc, r, c, sh)
         return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None
 

@@ -41,7 +41,7 @@ def check_all(got, ref, deg, fork, n_pix, ref32=None):
     def tol(k):
         return TOL if ref32 is None else max(TOL, 4.0 * rel(ref32[k], ref[k]))
     assert rel(got['image'], ref['image']) < tol('image')
-    rg, rr = got['radii'].cpu().numpy(), ref['radii']
+    rg, rr = np.asarray(got['radii'].cpu().numpy() if hasattr(got['radii'], 'cpu') else got['radii']), ref['radii']
     assert (rg != rr).sum() <= max(2, int(2e-4 * rr.size)), ((rg != rr).sum(), rr.size)
     assert np.abs(rg - rr).max() <= 1
     for k in ['dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations'] + (['dcolors'] if deg == 0 else ['dshs']):
@@ -50,10 +50,52 @@ def check_all(got, ref, deg, fork, n_pix, ref32=None):
     if fork:
         assert rel(got['point_weight'], ref['point_weight']) < tol('point_weight')
         assert rel(got['point_weight_pixel'], ref['point_weight_pixel']) < tol('point_weight_pixel')
-        pg, pr = got['point_id_pixel'].cpu().numpy(), ref['point_id_pixel']
+        pg = got['point_id_pixel']
+        pg, pr = (pg.cpu().numpy() if hasattr(pg, 'cpu') else pg), ref['point_id_pixel']
         bad = pg != pr
         assert bad.sum() <= max(3, int(1e-3 * n_pix)), bad.sum()
         assert ((pg == -1) == (pr == -1)).mean() > 0.999
+
+
+def borderline_decisions(cam, sc, fm, thr=1e-6):
+    """(Gaussian ids, pixel ids) of the pairs with |alpha * 255 - 1| < thr in float64.  The rule
+    `alpha < 1/255 -> skip` is a discontinuity: a pair sitting within fp32 round-off of it can legitimately be decided
+    either way by two fp32 implementations, which moves that Gaussian's gradient by O(1%) and that pixel by O(0.004).
+    Scenes with millions of low-opacity pairs always contain a few; they are excluded from the comparison by name."""
+    pr = O.project(sc['means3D'], sc['scales'], sc['rotations'], cam, fm)
+    H, W = cam.image_height, cam.image_width
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing='ij')
+    xy, con, op = pr['xy'].numpy(), pr['conic'].numpy(), sc['opacities'].numpy().reshape(-1)
+    gs, ps = [], []
+    for i in np.nonzero(pr['valid'].numpy())[0]:
+        dx, dy = xy[i, 0] - xs, xy[i, 1] - ys
+        power = -0.5 * (con[i, 0] * dx * dx + con[i, 2] * dy * dy) - con[i, 1] * dx * dy
+        near = np.abs(op[i] * np.exp(np.minimum(power, 0)) * 255 - 1) < thr
+        if near.any():
+            gs.append(int(i))
+            ps.extend(np.nonzero(near.reshape(-1))[0].tolist())
+    return np.array(gs, dtype=np.int64), np.array(sorted(set(ps)), dtype=np.int64)
+
+
+def drop(d, gs, ps):
+    """Copy of a result dict with the named Gaussian rows / pixels zeroed (numpy)."""
+    out = {}
+    for k, v in d.items():
+        if v is None or np.isscalar(v):
+            out[k] = v
+            continue
+        a = np.array(v.detach().cpu().numpy() if hasattr(v, 'detach') else v, copy=True)
+        if k == 'image':
+            a.reshape(3, -1)[:, ps] = 0
+        elif k in ('point_weight_pixel', 'point_id_pixel', 'final_T'):
+            a.reshape(-1)[ps] = 0
+        elif a.ndim >= 1 and a.shape[0] == sc_n[0]:
+            a[gs] = 0
+        out[k] = a
+    return out
+
+
+sc_n = [0]
 
 
 CASES = [
@@ -146,13 +188,19 @@ def test_long_tile_lists(built, n):
     """Tile lists longer than the small (2560) and the large (13312) shared-memory sort capacity."""
     W, H = 32, 32
     cam = f32_camera(O.make_camera(W, H, bg=(0.5, 0.5, 0.5)))
-    sc = f32_scene(O.make_scene(n, W, H, 8.0, seed=13))
+    sc = O.make_scene(n, W, H, 8.0, seed=13)
     sc['opacities'][:] *= 0.05        # keep the transmittance alive through thousands of splats
     sc['opacities'][:] += 0.004
+    sc = f32_scene(sc)
     G = O.make_cotangent(3, H, W)
     ref = oracle(cam, sc, G, O.FILTER_MAX, 0)
+    ref32 = oracle(cam, sc, G, O.FILTER_MAX, 0, dtype=np.float32)
     got = run_gpu(cam, sc, G)
-    check_all(got, ref, 0, True, H * W, oracle(cam, sc, G, O.FILTER_MAX, 0, dtype=np.float32))
+    # millions of pairs hover around alpha = 1/255 here (seed 13 has one at 1.3e-7): exclude the borderline ones
+    gs, ps = borderline_decisions(cam, sc, O.FILTER_MAX)
+    assert len(gs) <= 40
+    sc_n[0] = n
+    check_all(drop(got, gs, ps), drop(ref, gs, ps), 0, True, H * W, drop(ref32, gs, ps))
 
 
 def test_tile_row_shards_sum_to_full(built):
