@@ -156,11 +156,15 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
 //   dL/da_j = sum_c dL/dC_c * ( c_j T_j - S_j / (1 - a_j) )
 // which is the published back-to-front recurrence written in closed form.
 //
-// Per hit the 9 partial gradients of the 32 lanes are transposed through a per-warp shared-memory scratch
-// (3 STS per lane), 27 lanes each add up a third of one column (11 LDS), 3 partials are combined with 2 shuffles
-// and 9 lanes issue one red.shared.add each.  ~33 instructions instead of a 45-shuffle butterfly (~90).
-constexpr int GSTRIDE = 12;   // floats per scratch row (16-byte aligned rows, conflict-free 128-bit stores)
-
+// Reduction over the warp's pixels.  Every one of the 9 per-splat outputs is a FIXED-weight linear functional of two
+// per-lane scalars of the hit, wG = dL/dG * G and w = alpha * T:
+//     M00, M10, M01, M20, M11, M02 = sum_l wG_l * {1, u, v, u^2, uv, v^2}_l      (u, v: tile-centred pixel coordinates)
+//     C0, C1, C2                   = sum_l w_l * dL/dC_{0,1,2; l}
+// so each lane publishes just (wG, w) to a per-warp shared scratch (one 8-byte store), 27 lanes -- 9 outputs x 3
+// row groups -- each accumulate 11 rows against weights they keep in registers, the 3 partials are combined with two
+// shuffles and 9 lanes issue one red.shared.add each.  The moments are turned into d/dmean2D, d/dconic, d/dopacity
+// once per staged splat when the batch is flushed (with X = splat centre in the same tile-centred coordinates):
+//     sum wG dx = X M00 - M10,   sum wG dx^2 = X^2 M00 - 2 X M10 + M20,   sum wG dx dy = XY M00 - X M01 - Y M10 + M11 ...
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
                  const float* __restrict__ splat, const float* __restrict__ image,
@@ -168,14 +172,14 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   __shared__ float4 s_r0[BATCH], s_r1[BATCH], s_r2[BATCH];
   __shared__ int s_id[BATCH];
   __shared__ float s_g[BATCH * 9];
-  __shared__ __align__(16) float s_x[(BLEND_THREADS / 32) * 32 * GSTRIDE];
+  __shared__ __align__(8) float2 s_x[BLEND_THREADS];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SubTile st = make_subtile(v, tile, lane, warp);
   const float pxf = (float)st.x, pyf = (float)st.y;
   const int beg = tile_start[tile], len = tile_start[tile + 1] - beg;
-  float* xw = s_x + warp * 32 * GSTRIDE;                 // this warp's transpose scratch
+  float2* xw = s_x + warp * 32;                           // this warp's (wG, w) scratch
   const uint32_t s_g_addr = smem_u32(s_g);
-  const int red_k = lane % 9, red_s = lane / 9;          // lanes 0..26: column red_k, rows red_s, red_s+3, ...
+  const float tcx = (float)((tile % v.gx) * TILE) + 7.5f, tcy = (float)((v.row0 + tile / v.gx) * TILE) + 7.5f;
 
   float I0 = 0.f, I1 = 0.f, I2 = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
   if (st.inside) {
@@ -183,6 +187,33 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
     I0 = image[pix]; I1 = image[HW + pix]; I2 = image[2 * HW + pix];
     dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix];
   }
+  // fixed reduction weights of this lane: output red_k, rows red_s + 3 i
+  const int red_k = lane % 9, red_s = lane / 9;
+  float wt[11];
+  {
+    const float u = pxf - tcx, w_ = pyf - tcy;
+#pragma unroll
+    for (int i = 0; i < 11; i++) {
+      const int r = min(red_s + 3 * i, 31);
+      const float ur = __shfl_sync(FULL, u, r), vr = __shfl_sync(FULL, w_, r);
+      const float d0 = __shfl_sync(FULL, dp0, r), d1 = __shfl_sync(FULL, dp1, r), d2 = __shfl_sync(FULL, dp2, r);
+      float t;
+      switch (red_k) {
+        case 0: t = 1.f; break;
+        case 1: t = ur; break;
+        case 2: t = vr; break;
+        case 3: t = ur * ur; break;
+        case 4: t = ur * vr; break;
+        case 5: t = vr * vr; break;
+        case 6: t = d0; break;
+        case 7: t = d1; break;
+        default: t = d2; break;
+      }
+      wt[i] = (lane < 27 && red_s + 3 * i < 32) ? t : 0.f;
+    }
+  }
+  const bool red_second = red_k >= 6;                     // outputs 6..8 weight w, outputs 0..5 weight wG
+
   float T = 1.0f, P0 = 0.f, P1 = 0.f, P2 = 0.f;
   bool done = !st.inside;
 
@@ -220,8 +251,7 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
             if (test_T < T_STOP) { done = true; contrib = false; }
           }
           if (!__any_sync(FULL, contrib)) continue;
-          float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
-          float gc = 0.f;
+          float2 pub = make_float2(0.f, 0.f);
           if (contrib) {
             const float4 r2 = s_r2[e];
             const float w = alpha * T;
@@ -231,27 +261,16 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
             const float inv = __frcp_rn(1.0f - alpha);
             const float dL_dalpha = (r2.x * dp0 + r2.y * dp1 + r2.z * dp2) * T - (S0 * dp0 + S1 * dp1 + S2 * dp2) * inv;
             T = test_T;
-            const float wG = r1.y * dL_dalpha * G;          // dL/dG * G ; the 0.99 clamp is straight-through
-            const float gdx = wG * dx, gdy = wG * dy;
-            ga.x = -(gdx * r0.z + gdy * r0.w);              // d/dpx   (x log2e, undone in project_bwd)
-            ga.y = -(gdy * r1.x + gdx * r0.w);              // d/dpy   (x log2e)
-            ga.z = -0.5f * gdx * dx;                        // d/dconic_x
-            ga.w = -gdx * dy;                               // d/dconic_y
-            gb.x = -0.5f * gdy * dy;                        // d/dconic_z
-            gb.y = G * dL_dalpha;                           // d/dopacity
-            gb.z = w * dp0; gb.w = w * dp1; gc = w * dp2;   // d/drgb
+            pub.x = r1.y * dL_dalpha * G;                   // wG = dL/dG * G   (the 0.99 clamp is straight-through)
+            pub.y = w;
           }
-          // transpose-reduce the 9 values over the warp
-          float4* row = reinterpret_cast<float4*>(xw + lane * GSTRIDE);
-          row[0] = ga; row[1] = gb; xw[lane * GSTRIDE + 8] = gc;
+          xw[lane] = pub;
           __syncwarp();
           float sum = 0.f;
-          if (lane < 27) {
 #pragma unroll
-            for (int i = 0; i < 11; i++) {
-              const int r = red_s + 3 * i;
-              if (r < 32) sum += xw[r * GSTRIDE + red_k];
-            }
+          for (int i = 0; i < 11; i++) {
+            const float2 q = xw[min(red_s + 3 * i, 31)];
+            sum = fmaf(wt[i], red_second ? q.y : q.x, sum);
           }
           sum += __shfl_down_sync(FULL, sum, 9) + __shfl_down_sync(FULL, sum, 18);
           if (lane < 9) red_shared_add_f32(s_g_addr + 4u * (e * 9 + lane), sum);
@@ -262,17 +281,30 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
     }
     __syncthreads();
     if (tid < cnt) {
-      const float* gs = s_g + tid * 9;
-      const float4 a = make_float4(gs[0], gs[1], gs[2], gs[3]);
-      const float4 b = make_float4(gs[4], gs[5], gs[6], gs[7]);
-      const float c = gs[8];
-      const bool nz = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
-                      (b.z != 0.f) | (b.w != 0.f) | (c != 0.f);
+      const float* m = s_g + tid * 9;
+      const float M00 = m[0], M10 = m[1], M01 = m[2], M20 = m[3], M11 = m[4], M02 = m[5];
+      const bool nz = (M00 != 0.f) | (M10 != 0.f) | (M01 != 0.f) | (M20 != 0.f) | (M11 != 0.f) | (M02 != 0.f) |
+                      (m[6] != 0.f) | (m[7] != 0.f) | (m[8] != 0.f);
       if (nz) {
+        const float4 r0 = s_r0[tid];
+        const float2 r1 = *reinterpret_cast<const float2*>(&s_r1[tid]);
+        const float X = r0.x - tcx, Y = r0.y - tcy;
+        const float Sx = fmaf(X, M00, -M10), Sy = fmaf(Y, M00, -M01);                       // sum wG dx, sum wG dy
+        const float Sxx = fmaf(X, fmaf(X, M00, -2.f * M10), M20);                           // sum wG dx^2
+        const float Syy = fmaf(Y, fmaf(Y, M00, -2.f * M01), M02);
+        const float Sxy = fmaf(X, fmaf(Y, M00, -M01), fmaf(-Y, M10, M11));                  // sum wG dx dy
+        float4 a, b;
+        a.x = -(r0.z * Sx + r0.w * Sy);          // d/dpx  (x log2e: the conic in the record is pre-scaled)
+        a.y = -(r1.x * Sy + r0.w * Sx);          // d/dpy  (x log2e)
+        a.z = -0.5f * Sxx;                       // d/dconic_x
+        a.w = -Sxy;                              // d/dconic_y
+        b.x = -0.5f * Syy;                       // d/dconic_z
+        b.y = M00 / r1.y;                        // d/dopacity = sum G dL/dalpha = sum wG / o
+        b.z = m[6]; b.w = m[7];                  // d/drgb
         float4* dst = reinterpret_cast<float4*>(dsplat + (int64_t)s_id[tid] * LGR_GRAD_FLOATS);
         atomicAdd(dst, a);
         atomicAdd(dst + 1, b);
-        atomicAdd(reinterpret_cast<float*>(dst + 2), c);
+        atomicAdd(reinterpret_cast<float*>(dst + 2), m[8]);
       }
     }
   }
