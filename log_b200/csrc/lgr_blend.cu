@@ -60,6 +60,20 @@ __device__ __forceinline__ void red_shared_add_f32(uint32_t addr, float v) {
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+// Staged splat: three consecutive float4 per list entry (48-byte stride: conflict-free for 128-bit accesses),
+//   [0] = (px, py, conic_x', conic_y')   [1] = (conic_z', opacity, hx, hy)   [2] = (r, g, b, id as int bits)
+__device__ __forceinline__ void stage_splat(float4* s_rec, int slot, const float* __restrict__ splat, int id) {
+  const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
+  float4 r2 = ldg4(rec + 8);
+  r2.w = __int_as_float(id);
+  s_rec[3 * slot] = ldg4(rec); s_rec[3 * slot + 1] = ldg4(rec + 4); s_rec[3 * slot + 2] = r2;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
@@ -69,8 +83,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
                  const float* __restrict__ splat, float* __restrict__ image, float* __restrict__ final_T,
                  int32_t* __restrict__ n_contrib, int32_t* __restrict__ pid_pixel, float* __restrict__ pw_pixel,
                  unsigned* __restrict__ point_weight_bits) {
-  __shared__ float4 s_r0[BATCH], s_r1[BATCH], s_r2[BATCH];
-  __shared__ int s_id[BATCH];
+  __shared__ float4 s_rec[BATCH * 3];
   __shared__ unsigned s_w[AUX ? BATCH : 1];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SubTile st = make_subtile(v, tile, lane, warp);
@@ -80,16 +93,13 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, wmax = 0.f;
   int last = 0, wid = -1;
-  bool done = !st.inside;
+  int done = st.inside ? 0 : 1;
 
   for (int base = 0; base < len; base += BATCH) {
     if (__syncthreads_and(done)) break;      // also orders smem reuse between batches
     const int cnt = min(BATCH, len - base);
     if (tid < cnt) {
-      const int id = sorted_ids[beg + base + tid];
-      const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
-      s_r0[tid] = ldg4(rec); s_r1[tid] = ldg4(rec + 4); s_r2[tid] = ldg4(rec + 8);
-      s_id[tid] = id;
+      stage_splat(s_rec, tid, splat, sorted_ids[beg + base + tid]);
       if (AUX) s_w[tid] = 0u;
     }
     __syncthreads();
@@ -97,29 +107,29 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
       for (int c0 = 0; c0 < cnt; c0 += 32) {
         const int e_l = c0 + lane;
         bool hit = false;
-        if (e_l < cnt) hit = box_hits(s_r0[e_l], s_r1[e_l], st);
+        if (e_l < cnt) hit = box_hits(s_rec[3 * e_l], s_rec[3 * e_l + 1], st);
         unsigned mask = __ballot_sync(FULL, hit);
         unsigned own_w = 0u;                 // max weight of the splat this lane tested, over this warp's pixels
         while (mask) {
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
-          const int e = c0 + j;
-          const float4 r0 = s_r0[e];
-          const float2 r1 = *reinterpret_cast<const float2*>(&s_r1[e]);    // (conic_z, opacity)
+          const float4* rec = s_rec + 3 * (c0 + j);
+          const float4 r0 = rec[0];
+          const float2 r1 = *reinterpret_cast<const float2*>(rec + 1);    // (conic_z, opacity)
           const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
           const float power = eval_power2(r0, r1.x, dx, dy);
           const float alpha = eval_alpha(r1.y, ex2_approx(power));
           float w = 0.f;
           if (!done && power <= 0.0f && alpha >= ALPHA_MIN) {
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            if (test_T < T_STOP) done = true;
+            if (test_T < T_STOP) done = 1;
             else {
               w = alpha * T;
-              const float4 r2 = s_r2[e];
-              C0 += r2.x * w; C1 += r2.y * w; C2 += r2.z * w;
+              const float4 r2 = rec[2];
+              C0 = fmaf(r2.x, w, C0); C1 = fmaf(r2.y, w, C1); C2 = fmaf(r2.z, w, C2);
               T = test_T;
-              last = base + e + 1;
-              if (AUX && w > wmax) { wmax = w; wid = s_id[e]; }
+              last = base + c0 + j + 1;
+              if (AUX && w > wmax) { wmax = w; wid = __float_as_int(r2.w); }
             }
           }
           if (AUX) {
@@ -133,7 +143,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
     }
     if (AUX) {
       __syncthreads();
-      if (tid < cnt && s_w[tid]) atomicMax(point_weight_bits + s_id[tid], s_w[tid]);
+      if (tid < cnt && s_w[tid]) atomicMax(point_weight_bits + __float_as_int(s_rec[3 * tid + 2].w), s_w[tid]);
     }
   }
   if (st.inside) {
@@ -160,24 +170,23 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
 // per-lane scalars of the hit, wG = dL/dG * G and w = alpha * T:
 //     M00, M10, M01, M20, M11, M02 = sum_l wG_l * {1, u, v, u^2, uv, v^2}_l      (u, v: tile-centred pixel coordinates)
 //     C0, C1, C2                   = sum_l w_l * dL/dC_{0,1,2; l}
-// so each lane publishes just (wG, w) to a per-warp shared scratch (one 8-byte store), 27 lanes -- 9 outputs x 3
-// row groups -- each accumulate 11 rows against weights they keep in registers, the 3 partials are combined with two
-// shuffles and 9 lanes issue one red.shared.add each.  The moments are turned into d/dmean2D, d/dconic, d/dopacity
-// once per staged splat when the batch is flushed (with X = splat centre in the same tile-centred coordinates):
+// so each lane publishes just (wG, w) to a per-warp shared scratch (two 4-byte stores, SoA), 27 lanes -- 9 outputs
+// x 3 row groups -- each accumulate 12 rows (3 x LDS.128) against weights they keep in registers, the 3 partials are
+// combined with two shuffles and 9 lanes add into the per-splat accumulators.  The moments are turned into
+// d/dmean2D, d/dconic, d/dopacity once per staged splat when the batch is flushed (X = splat centre, same coordinates):
 //     sum wG dx = X M00 - M10,   sum wG dx^2 = X^2 M00 - 2 X M10 + M20,   sum wG dx dy = XY M00 - X M01 - Y M10 + M11 ...
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
                  const float* __restrict__ splat, const float* __restrict__ image,
                  const float* __restrict__ dL_dimage, float* __restrict__ dsplat) {
-  __shared__ float4 s_r0[BATCH], s_r1[BATCH], s_r2[BATCH];
-  __shared__ int s_id[BATCH];
+  __shared__ float4 s_rec[BATCH * 3];
   __shared__ float s_g[BATCH * 9];
-  __shared__ __align__(8) float2 s_x[BLEND_THREADS];
+  __shared__ __align__(16) float s_x[(BLEND_THREADS / 32) * 64];     // per warp: wG[32] | w[32]
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SubTile st = make_subtile(v, tile, lane, warp);
   const float pxf = (float)st.x, pyf = (float)st.y;
   const int beg = tile_start[tile], len = tile_start[tile + 1] - beg;
-  float2* xw = s_x + warp * 32;                           // this warp's (wG, w) scratch
+  float* xg = s_x + warp * 64;
   const uint32_t s_g_addr = smem_u32(s_g);
   const float tcx = (float)((tile % v.gx) * TILE) + 7.5f, tcy = (float)((v.row0 + tile / v.gx) * TILE) + 7.5f;
 
@@ -187,14 +196,14 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
     I0 = image[pix]; I1 = image[HW + pix]; I2 = image[2 * HW + pix];
     dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix];
   }
-  // fixed reduction weights of this lane: output red_k, rows red_s + 3 i
-  const int red_k = lane % 9, red_s = lane / 9;
-  float wt[11];
+  // fixed reduction weights of this lane: output red_k, rows 12 red_s .. 12 red_s + 11 (clipped to 32)
+  const int red_k = lane % 9, red_s = min(lane / 9, 2);
+  float wt[12];
   {
     const float u = pxf - tcx, w_ = pyf - tcy;
 #pragma unroll
-    for (int i = 0; i < 11; i++) {
-      const int r = min(red_s + 3 * i, 31);
+    for (int i = 0; i < 12; i++) {
+      const int r = min(12 * red_s + i, 31);
       const float ur = __shfl_sync(FULL, u, r), vr = __shfl_sync(FULL, w_, r);
       const float d0 = __shfl_sync(FULL, dp0, r), d1 = __shfl_sync(FULL, dp1, r), d2 = __shfl_sync(FULL, dp2, r);
       float t;
@@ -209,69 +218,65 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
         case 7: t = d1; break;
         default: t = d2; break;
       }
-      wt[i] = (lane < 27 && red_s + 3 * i < 32) ? t : 0.f;
+      wt[i] = (lane < 27 && 12 * red_s + i < 32) ? t : 0.f;
     }
   }
-  const bool red_second = red_k >= 6;                     // outputs 6..8 weight w, outputs 0..5 weight wG
+  // where this lane reads: the wG half for outputs 0..5, the w half for 6..8; group 2 re-reads quad 7 with weight 0
+  const float4* red_src = reinterpret_cast<const float4*>(xg + (red_k >= 6 ? 32 : 0)) + 3 * red_s;
+  const int q2 = red_s == 2 ? 1 : 2;
 
   float T = 1.0f, P0 = 0.f, P1 = 0.f, P2 = 0.f;
-  bool done = !st.inside;
+  int done = st.inside ? 0 : 1;
 
   for (int base = 0; base < len; base += BATCH) {
     if (__syncthreads_and(done)) break;
     const int cnt = min(BATCH, len - base);
-    if (tid < cnt) {
-      const int id = sorted_ids[beg + base + tid];
-      const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
-      s_r0[tid] = ldg4(rec); s_r1[tid] = ldg4(rec + 4); s_r2[tid] = ldg4(rec + 8);
-      s_id[tid] = id;
-    }
+    if (tid < cnt) stage_splat(s_rec, tid, splat, sorted_ids[beg + base + tid]);
     for (int k = tid; k < cnt * 9; k += BLEND_THREADS) s_g[k] = 0.f;
     __syncthreads();
     if (!__all_sync(FULL, done)) {
       for (int c0 = 0; c0 < cnt; c0 += 32) {
         const int e_l = c0 + lane;
         bool hit = false;
-        if (e_l < cnt) hit = box_hits(s_r0[e_l], s_r1[e_l], st);
+        if (e_l < cnt) hit = box_hits(s_rec[3 * e_l], s_rec[3 * e_l + 1], st);
         unsigned mask = __ballot_sync(FULL, hit);
         while (mask) {
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
           const int e = c0 + j;
-          const float4 r0 = s_r0[e];
-          const float2 r1 = *reinterpret_cast<const float2*>(&s_r1[e]);    // (conic_z, opacity)
+          const float4* rec = s_rec + 3 * e;
+          const float4 r0 = rec[0];
+          const float2 r1 = *reinterpret_cast<const float2*>(rec + 1);    // (conic_z, opacity)
           const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
           const float power = eval_power2(r0, r1.x, dx, dy);
           const float G = ex2_approx(power);
           const float alpha = eval_alpha(r1.y, G);
-          bool contrib = !done && power <= 0.0f && alpha >= ALPHA_MIN;
+          int contrib = 0;
           float test_T = 0.f;
-          if (contrib) {
+          if (!done && power <= 0.0f && alpha >= ALPHA_MIN) {
             test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            if (test_T < T_STOP) { done = true; contrib = false; }
+            if (test_T < T_STOP) done = 1; else contrib = 1;
           }
           if (!__any_sync(FULL, contrib)) continue;
-          float2 pub = make_float2(0.f, 0.f);
+          float wG = 0.f, w = 0.f;
           if (contrib) {
-            const float4 r2 = s_r2[e];
-            const float w = alpha * T;
-            const float cw0 = r2.x * w, cw1 = r2.y * w, cw2 = r2.z * w;
-            const float S0 = I0 - P0 - cw0, S1 = I1 - P1 - cw1, S2 = I2 - P2 - cw2;   // colour behind j (+ bg T_final)
-            P0 += cw0; P1 += cw1; P2 += cw2;
-            const float inv = __frcp_rn(1.0f - alpha);
-            const float dL_dalpha = (r2.x * dp0 + r2.y * dp1 + r2.z * dp2) * T - (S0 * dp0 + S1 * dp1 + S2 * dp2) * inv;
+            const float4 r2 = rec[2];
+            w = alpha * T;
+            const float cdot = r2.x * dp0 + r2.y * dp1 + r2.z * dp2;
+            // colour behind j (+ bg T_final):  S = I - P - c w
+            const float Sdot = (I0 - P0) * dp0 + (I1 - P1) * dp1 + (I2 - P2) * dp2 - cdot * w;
+            P0 = fmaf(r2.x, w, P0); P1 = fmaf(r2.y, w, P1); P2 = fmaf(r2.z, w, P2);
+            const float dL_dalpha = cdot * T - Sdot * rcp_approx(1.0f - alpha);
             T = test_T;
-            pub.x = r1.y * dL_dalpha * G;                   // wG = dL/dG * G   (the 0.99 clamp is straight-through)
-            pub.y = w;
+            wG = r1.y * dL_dalpha * G;                      // dL/dG * G   (the 0.99 clamp is straight-through)
           }
-          xw[lane] = pub;
+          xg[lane] = wG; xg[32 + lane] = w;
           __syncwarp();
-          float sum = 0.f;
-#pragma unroll
-          for (int i = 0; i < 11; i++) {
-            const float2 q = xw[min(red_s + 3 * i, 31)];
-            sum = fmaf(wt[i], red_second ? q.y : q.x, sum);
-          }
+          const float4 a0 = red_src[0], a1 = red_src[1], a2 = red_src[q2];
+          float sum = wt[0] * a0.x;
+          sum = fmaf(wt[1], a0.y, sum); sum = fmaf(wt[2], a0.z, sum); sum = fmaf(wt[3], a0.w, sum);
+          sum = fmaf(wt[4], a1.x, sum); sum = fmaf(wt[5], a1.y, sum); sum = fmaf(wt[6], a1.z, sum); sum = fmaf(wt[7], a1.w, sum);
+          sum = fmaf(wt[8], a2.x, sum); sum = fmaf(wt[9], a2.y, sum); sum = fmaf(wt[10], a2.z, sum); sum = fmaf(wt[11], a2.w, sum);
           sum += __shfl_down_sync(FULL, sum, 9) + __shfl_down_sync(FULL, sum, 18);
           if (lane < 9) red_shared_add_f32(s_g_addr + 4u * (e * 9 + lane), sum);
           __syncwarp();
@@ -286,8 +291,9 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
       const bool nz = (M00 != 0.f) | (M10 != 0.f) | (M01 != 0.f) | (M20 != 0.f) | (M11 != 0.f) | (M02 != 0.f) |
                       (m[6] != 0.f) | (m[7] != 0.f) | (m[8] != 0.f);
       if (nz) {
-        const float4 r0 = s_r0[tid];
-        const float2 r1 = *reinterpret_cast<const float2*>(&s_r1[tid]);
+        const float4 r0 = s_rec[3 * tid];
+        const float2 r1 = *reinterpret_cast<const float2*>(&s_rec[3 * tid + 1]);
+        const int id = __float_as_int(s_rec[3 * tid + 2].w);
         const float X = r0.x - tcx, Y = r0.y - tcy;
         const float Sx = fmaf(X, M00, -M10), Sy = fmaf(Y, M00, -M01);                       // sum wG dx, sum wG dy
         const float Sxx = fmaf(X, fmaf(X, M00, -2.f * M10), M20);                           // sum wG dx^2
@@ -301,7 +307,7 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
         b.x = -0.5f * Syy;                       // d/dconic_z
         b.y = M00 / r1.y;                        // d/dopacity = sum G dL/dalpha = sum wG / o
         b.z = m[6]; b.w = m[7];                  // d/drgb
-        float4* dst = reinterpret_cast<float4*>(dsplat + (int64_t)s_id[tid] * LGR_GRAD_FLOATS);
+        float4* dst = reinterpret_cast<float4*>(dsplat + (int64_t)id * LGR_GRAD_FLOATS);
         atomicAdd(dst, a);
         atomicAdd(dst + 1, b);
         atomicAdd(reinterpret_cast<float*>(dst + 2), m[8]);
