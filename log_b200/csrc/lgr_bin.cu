@@ -14,7 +14,7 @@ namespace lgr {
 // exclusive scan of tile counts (a few thousand tiles: one CTA)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 1024;
-constexpr int SORT_CAP_SMALL_FWD = 2560;
+constexpr int SORT_CAP_SMALL_FWD = 4096;   // lists up to this length are sorted by the main launch
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* in: counts[0..ntiles) ; out: starts[0..ntiles] */,
@@ -95,7 +95,7 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int SORT_CAP_SMALL = SORT_CAP_SMALL_FWD;    // 40 KB dynamic smem: 4 CTAs / SM
+constexpr int SORT_CAP_SMALL = SORT_CAP_SMALL_FWD;    // main launch: dynamic smem = 16 B x min(longest list, 4096)
 constexpr int SORT_CAP_LARGE = 13312;   // 208 KB dynamic smem: 1 CTA / SM
 
 // One pass over `len` items on digit (src[sel][i] >> shift) & 255, stable.  Warp w owns the contiguous segment
@@ -238,7 +238,8 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
     attr_set = true;
   }
   ProfScope ps(K_TILE_SORT, st, 1 + (num_long > 0) + (max_len > SORT_CAP_LARGE));
-  tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * SORT_CAP_SMALL, st>>>(nullptr, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, SORT_CAP_SMALL, id_bits);
+  const int cap_main = max(256, min(max_len, SORT_CAP_SMALL));
+  tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * cap_main, st>>>(nullptr, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, cap_main, id_bits);
   LGR_CHECK_LAUNCH();
   if (num_long > 0) {   // only the long tiles (listed by the scan kernel behind the cursors), smem sized to the longest
     const int32_t* long_list = cursor + ntiles;
