@@ -244,7 +244,7 @@ def main():
                                                              t_['rotations'].grad, t_['colors'].grad if deg == 0 else t_['shs'].grad.reshape(n, -1))))
             return float(loss.item())           # D2H read of the step's result
         ne = max(3, min(args.steps, 10))
-        for _ in range(2):
+        for _ in range(6):          # allocator growth settles after ~5 iterations
             step_e2e()
         barrier()
         t0 = time.perf_counter()

@@ -55,6 +55,7 @@ typedef struct lgr_view {
 /* Sizes of the buffers the caller must provide. */
 #define LGR_SPLAT_FLOATS 12 /* per-Gaussian projected record: 3 x float4 */
 #define LGR_GRAD_FLOATS 12  /* per-Gaussian 2D-gradient accumulator: 3 x float4 */
+#define LGR_TILE_SCRATCH_INTS 33 /* per tile: one counter per 128-byte line (32 ints) + one slot of the long-tile list */
 #define LGR_META_INTS 8     /* meta_d: [0]=D binned instances [1]=longest tile list [2..3]=D by the stock
                                radius-square rule (lo,hi 32 bits) [4]=#Gaussians with radius>0
                                [5]=#tiles whose list exceeds the small shared-memory sort */
@@ -71,7 +72,7 @@ int lgr_compute_radius(int64_t n, const float* means3D_d, const float* scales_d,
  *   in : means3D (N,3) opacities (N) scales (N,3) rotations (N,4); colors_precomp (N,3) XOR shs (N,K,3)
  *   out: splat_d (N,12) radii_d (N) int32; clamped_d (N) uint8 (SH only, may be NULL with colors_precomp);
  *        tile_start_d (tiles+1) int32 exclusive scan of per-tile counts (tiles = gx * rows rendered);
- *        tile_cursor_d (2*tiles) int32 scratch; meta_d (LGR_META_INTS) int32.
+ *        tile_cursor_d (LGR_TILE_SCRATCH_INTS*tiles) int32 scratch; meta_d (LGR_META_INTS) int32.
  * The caller reads meta_d (one 32-byte D2H) to size the instance buffers for lgr_forward_render. */
 int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d, const float* opacities_d,
                         const float* scales_d, const float* rotations_d, const float* colors_precomp_d,

@@ -17,8 +17,9 @@ constexpr int SCAN_THREADS = 1024;
 constexpr int SORT_CAP_SMALL_FWD = 4096;   // lists up to this length are sorted by the main launch
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* in: counts[0..ntiles) ; out: starts[0..ntiles] */,
-                 int32_t* __restrict__ cursor /* [0,ntiles): zeroed cursors ; [ntiles,2*ntiles): ids of long tiles */,
+tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* out: starts[0..ntiles] */,
+                 int32_t* __restrict__ cursor /* [0,CSTRIDE*ntiles): padded counts in, zeroed cursors out ;
+                                                 then ntiles ints: ids of long tiles */,
                  int32_t* __restrict__ meta, int small_cap) {
   __shared__ int warp_sum[SCAN_THREADS / 32];
   __shared__ int carry_s, maxl_s, nbig_s;
@@ -28,7 +29,7 @@ tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* in: counts[0..n
   int local_max = 0;
   for (int base = 0; base < ntiles; base += SCAN_THREADS) {
     const int i = base + tid;
-    const int c = (i < ntiles) ? tile_start[i] : 0;
+    const int c = (i < ntiles) ? cursor[i * CSTRIDE] : 0;
     local_max = max(local_max, c);
     int x = c;
 #pragma unroll
@@ -45,8 +46,8 @@ tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* in: counts[0..n
     const int carry = carry_s;
     const int excl = carry + (wid ? warp_sum[wid - 1] : 0) + x - c;
     if (i < ntiles) {
-      tile_start[i] = excl; cursor[i] = 0;
-      if (c > small_cap) cursor[ntiles + atomicAdd(&nbig_s, 1)] = i;   // tiles the small-smem sort cannot hold
+      tile_start[i] = excl; cursor[i * CSTRIDE] = 0;
+      if (c > small_cap) cursor[CSTRIDE * ntiles + atomicAdd(&nbig_s, 1)] = i;   // tiles the main sort launch cannot hold
     }
     __syncthreads();
     if (tid == SCAN_THREADS - 1) carry_s = carry + warp_sum[31];
@@ -82,7 +83,7 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
   for (int ty = y0; ty < y1; ty++)
     for (int tx = x0; tx < x1; tx++) {
       const int t = (ty - v.row0) * v.gx + tx;
-      const int pos = tile_start[t] + atomicAdd(cursor + t, 1);
+      const int pos = tile_start[t] + atomicAdd(cursor + t * CSTRIDE, 1);
       inst_key[pos] = key;
       inst_val[pos] = (uint32_t)i;
     }
@@ -242,7 +243,7 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
   tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * cap_main, st>>>(nullptr, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, cap_main, id_bits);
   LGR_CHECK_LAUNCH();
   if (num_long > 0) {   // only the long tiles (listed by the scan kernel behind the cursors), smem sized to the longest
-    const int32_t* long_list = cursor + ntiles;
+    const int32_t* long_list = cursor + CSTRIDE * ntiles;
     const int cap = min(max_len, SORT_CAP_LARGE);
     tile_sort_kernel<0><<<num_long, SORT_THREADS, 16 * cap, st>>>(long_list, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_SMALL, cap, id_bits);
     LGR_CHECK_LAUNCH();

@@ -64,12 +64,12 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
   cudaStream_t st = (cudaStream_t)stream;
   const View v = make_view(view);
   const int ntiles = v.gx * (v.row1 - v.row0);
-  cudaError_t e = cudaMemsetAsync(tile_start_d, 0, sizeof(int32_t) * (size_t)(ntiles + 1), st);
+  cudaError_t e = cudaMemsetAsync(tile_cursor_d, 0, sizeof(int32_t) * (size_t)ntiles * CSTRIDE, st);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(meta_d, 0, sizeof(int32_t) * LGR_META_INTS, st);
   if (e != cudaSuccess) return (int)e;
   int rc = launch_project_fwd(v, n, means3D_d, opacities_d, scales_d, rotations_d, colors_precomp_d, shs_d, splat_d,
-                              radii_d, clamped_d, tile_start_d, meta_d, st);
+                              radii_d, clamped_d, tile_cursor_d, meta_d, st);
   if (rc) return rc;
   return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, st);
 }

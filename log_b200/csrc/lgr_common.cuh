@@ -15,6 +15,7 @@ constexpr float ALPHA_MIN = 1.0f / 255.0f;
 constexpr float T_STOP = 1e-4f;
 constexpr float FILTER_VAR = 0.3f;      // LoG/cuda/compute_radius_kernel.cu:61
 constexpr float CLAMP_FOV = 1.3f;       // compute_radius_kernel.cu:71-72
+constexpr int CSTRIDE = 32;              // per-tile counters live one per 128-byte line (spreads L2 atomics over slices)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 

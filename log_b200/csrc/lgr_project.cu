@@ -131,7 +131,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
         if (reach) {
           tile_rect_tight(px, py, rad, hx, hy, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
           for (int ty = y0; ty < y1; ty++)
-            for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + (ty - v.row0) * v.gx + tx, 1);
+            for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE, 1);
         }
       }
     }

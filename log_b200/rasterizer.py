@@ -113,7 +113,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     radii = torch.empty((n,), **i32)
     clamped = torch.empty((n,), dtype=torch.uint8, device=dev) if shs is not None else None
     tile_start = torch.empty((ntiles + 1,), **i32)
-    tile_cursor = torch.empty((2 * max(ntiles, 1),), **i32)
+    tile_cursor = torch.empty((_capi.LGR_TILE_SCRATCH_INTS * max(ntiles, 1),), **i32)
     meta = torch.empty((_capi.LGR_META_INTS,), **i32)
     st = _stream()
     _capi.check(lib.lgr_forward_project(ctypes.byref(view), n, _ptr(means3D), _ptr(opacities), _ptr(scales),
