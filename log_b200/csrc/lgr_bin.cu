@@ -181,6 +181,121 @@ __device__ __forceinline__ void sort_tile(uint32_t* kA, uint32_t* vA, uint32_t* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// MSD bucket sort in shared memory (the default path)
+// ---------------------------------------------------------------------------------------------------------
+// The order is by the 64-bit composite (depth bits << 32 | id), which is unique, so no pass has to be stable:
+//   1. block min / max of the composite over the range  ->  the highest differing bit picks an 8-bit digit that
+//      splits the range as evenly as the data allows (adapts to the depth range of THIS tile);
+//   2. histogram (ATOMS), exclusive scan, scatter with slots handed out by returning ATOMS.ADD, copy back;
+//   3. every bin of <= MSD_SMALL entries is finished by ONE thread with an insertion sort on the composite
+//      (256 bins <-> 256 threads); larger bins are pushed on a block-level work stack and partitioned again.
+// Uniformly distributed depths finish after one partition (bins of ~L/256 entries).  No match.any / warp ranking:
+// the stable LSD sort kept below for huge lists spends its time in the ADU pipe on exactly those.
+constexpr int MSD_SMALL = 32;
+constexpr int MSD_STACK = 512;
+
+struct MsdShared {
+  int hist[RADIX];
+  int bstart[RADIX + 1];
+  int wsum[SORT_WARPS];
+  unsigned long long wmin[SORT_WARPS], wmax[SORT_WARPS];
+  int stack_beg[MSD_STACK], stack_len[MSD_STACK];
+  int top, shift, overflow;
+};
+
+__device__ __forceinline__ unsigned long long composite(uint32_t k, uint32_t v) { return ((unsigned long long)k << 32) | v; }
+
+__device__ __forceinline__ void insertion_sort(uint32_t* __restrict__ k, uint32_t* __restrict__ v, int n) {
+  for (int i = 1; i < n; i++) {
+    const uint32_t ki = k[i], vi = v[i];
+    const unsigned long long ci = composite(ki, vi);
+    int j = i - 1;
+    while (j >= 0 && composite(k[j], v[j]) > ci) { k[j + 1] = k[j]; v[j + 1] = v[j]; j--; }
+    k[j + 1] = ki; v[j + 1] = vi;
+  }
+}
+
+// Sorts (kA, vA)[0, len) in place; (kB, vB) is scratch of the same size.  Returns false if the work stack overflowed
+// (the caller then falls back to the LSD sort, which is always correct).
+__device__ __forceinline__ bool sort_tile_msd(uint32_t* kA, uint32_t* vA, uint32_t* kB, uint32_t* vB, int len, MsdShared& sh) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { sh.stack_beg[0] = 0; sh.stack_len[0] = len; sh.top = 1; sh.overflow = 0; }
+  __syncthreads();
+  while (true) {
+    const int top = sh.top;
+    if (top == 0 || sh.overflow) break;
+    const int beg = sh.stack_beg[top - 1], n = sh.stack_len[top - 1];
+    __syncthreads();
+    if (tid == 0) sh.top = top - 1;
+    // 1. range of the composite
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (int i = tid; i < n; i += SORT_THREADS) {
+      const unsigned long long c = composite(kA[beg + i], vA[beg + i]);
+      mn = min(mn, c); mx = max(mx, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { sh.wmin[wid] = mn; sh.wmax[wid] = mx; }
+    sh.hist[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long a = sh.wmin[0], b = sh.wmax[0];
+#pragma unroll
+      for (int w = 1; w < SORT_WARPS; w++) { a = min(a, sh.wmin[w]); b = max(b, sh.wmax[w]); }
+      const int hb = 63 - __clzll((long long)(a ^ b));      // a != b: composites are unique and n >= 2
+      sh.shift = max(0, hb - (RADIX_BITS - 1));
+    }
+    __syncthreads();
+    const int shift = sh.shift;
+    // 2. histogram -> scan -> scatter -> copy back
+    for (int i = tid; i < n; i += SORT_THREADS)
+      atomicAdd(&sh.hist[(int)((composite(kA[beg + i], vA[beg + i]) >> shift) & (RADIX - 1))], 1);
+    __syncthreads();
+    {
+      const int c = sh.hist[tid];
+      int x = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      if (lane == 31) sh.wsum[wid] = x;
+      __syncthreads();
+      int base = x - c;
+#pragma unroll
+      for (int w = 0; w < SORT_WARPS; w++) if (w < wid) base += sh.wsum[w];
+      sh.bstart[tid] = base;
+      sh.hist[tid] = base;                     // becomes the scatter cursor
+      if (tid == RADIX - 1) sh.bstart[RADIX] = base + c;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += SORT_THREADS) {
+      const uint32_t k = kA[beg + i], v = vA[beg + i];
+      const int slot = atomicAdd(&sh.hist[(int)((composite(k, v) >> shift) & (RADIX - 1))], 1);
+      kB[beg + slot] = k; vB[beg + slot] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += SORT_THREADS) { kA[beg + i] = kB[beg + i]; vA[beg + i] = vB[beg + i]; }
+    __syncthreads();
+    // 3. finish small bins, queue large ones
+    {
+      const int b0 = sh.bstart[tid], bn = sh.bstart[tid + 1] - b0;
+      if (bn > MSD_SMALL) {
+        const int slot = atomicAdd(&sh.top, 1);
+        if (slot < MSD_STACK) { sh.stack_beg[slot] = beg + b0; sh.stack_len[slot] = bn; }
+        else sh.overflow = 1;
+      } else if (bn > 1) {
+        insertion_sort(kA + beg + b0, vA + beg + b0, bn);
+      }
+    }
+    __syncthreads();
+  }
+  const bool ok = sh.overflow == 0;
+  __syncthreads();
+  return ok;
+}
+
 // mode 0: lists with len <= cap live in shared memory (dynamic smem = 16*cap bytes); longer lists are skipped.
 // mode 1: lists with lo < len are sorted in global memory (inst_* in place, tmp_* scratch).
 template <int MODE>
@@ -190,7 +305,8 @@ tile_sort_kernel(const int32_t* __restrict__ tile_list /* nullptr: tile = blockI
                  uint32_t* __restrict__ inst_val, uint32_t* __restrict__ tmp, int32_t* __restrict__ sorted_ids, int lo,
                  int cap, int id_bits) {
   extern __shared__ uint32_t smem_u32[];
-  __shared__ int whist[SORT_WARPS * RADIX];
+  __shared__ int whist[MODE == 1 ? SORT_WARPS * RADIX : 1];
+  __shared__ MsdShared msd;
   const int t = tile_list ? tile_list[blockIdx.x] : (int)blockIdx.x;
   const int beg = tile_start[t], len = tile_start[t + 1] - beg;
   if (len <= lo || (MODE == 0 && len > cap)) return;
@@ -198,7 +314,8 @@ tile_sort_kernel(const int32_t* __restrict__ tile_list /* nullptr: tile = blockI
     uint32_t* kA = smem_u32; uint32_t* vA = kA + cap; uint32_t* kB = vA + cap; uint32_t* vB = kB + cap;
     for (int i = threadIdx.x; i < len; i += SORT_THREADS) { kA[i] = inst_key[beg + i]; vA[i] = inst_val[beg + i]; }
     __syncthreads();
-    if (len > 1) sort_tile(kA, vA, kB, vB, len, id_bits, whist);
+    // the work stack holds at most cap / (MSD_SMALL + 1) <= 403 ranges: overflow is unreachable; fail loudly if it is hit
+    if (len > 1 && !sort_tile_msd(kA, vA, kB, vB, len, msd)) __trap();
     for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
   } else {
     uint32_t* kA = inst_key + beg; uint32_t* vA = inst_val + beg;
