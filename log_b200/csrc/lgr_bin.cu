@@ -188,8 +188,8 @@ __device__ __forceinline__ void sort_tile(uint32_t* kA, uint32_t* vA, uint32_t* 
 //   1. block min / max of the composite over the range  ->  the highest differing bit picks an 8-bit digit that
 //      splits the range as evenly as the data allows (adapts to the depth range of THIS tile);
 //   2. histogram (ATOMS), exclusive scan, scatter with slots handed out by returning ATOMS.ADD, copy back;
-//   3. every bin of <= MSD_SMALL entries is finished by ONE thread with an insertion sort on the composite
-//      (256 bins <-> 256 threads); larger bins are pushed on a block-level work stack and partitioned again.
+//   3. every bin of <= MSD_SMALL entries is finished by counting ranks inside the bin (one thread per element writes it
+//      to its final slot); larger bins are pushed on a block-level work stack and partitioned again.
 // Uniformly distributed depths finish after one partition (bins of ~L/256 entries).  No match.any / warp ranking:
 // the stable LSD sort kept below for huge lists spends its time in the ADU pipe on exactly those.
 constexpr int MSD_SMALL = 32;
@@ -205,16 +205,6 @@ struct MsdShared {
 };
 
 __device__ __forceinline__ unsigned long long composite(uint32_t k, uint32_t v) { return ((unsigned long long)k << 32) | v; }
-
-__device__ __forceinline__ void insertion_sort(uint32_t* __restrict__ k, uint32_t* __restrict__ v, int n) {
-  for (int i = 1; i < n; i++) {
-    const uint32_t ki = k[i], vi = v[i];
-    const unsigned long long ci = composite(ki, vi);
-    int j = i - 1;
-    while (j >= 0 && composite(k[j], v[j]) > ci) { k[j + 1] = k[j]; v[j + 1] = v[j]; j--; }
-    k[j + 1] = ki; v[j + 1] = vi;
-  }
-}
 
 // Sorts (kA, vA)[0, len) in place; (kB, vB) is scratch of the same size.  Returns false if the work stack overflowed
 // (the caller then falls back to the LSD sort, which is always correct).
@@ -276,17 +266,31 @@ __device__ __forceinline__ bool sort_tile_msd(uint32_t* kA, uint32_t* vA, uint32
       kB[beg + slot] = k; vB[beg + slot] = v;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += SORT_THREADS) { kA[beg + i] = kB[beg + i]; vA[beg + i] = vB[beg + i]; }
-    __syncthreads();
-    // 3. finish small bins, queue large ones
+    // 3. finish small bins by counting ranks (one thread per ELEMENT: lanes of a warp share a bin, so the bin scan
+    //    broadcasts and the loop lengths agree), copy large bins back unsorted and queue them for another partition
+    for (int i = tid; i < n; i += SORT_THREADS) {
+      const uint32_t k = kB[beg + i], v = vB[beg + i];
+      const int d = (int)((composite(k, v) >> shift) & (RADIX - 1));
+      const int b0 = sh.bstart[d], bn = sh.bstart[d + 1] - b0;
+      int dst = i;
+      if (bn <= MSD_SMALL) {
+        const uint32_t* kb = kB + beg + b0;
+        const uint32_t* vb = vB + beg + b0;
+        int rank = 0;
+        for (int j = 0; j < bn; j++) {
+          const uint32_t kj = kb[j];
+          rank += (kj < k) || (kj == k && vb[j] < v);
+        }
+        dst = b0 + rank;
+      }
+      kA[beg + dst] = k; vA[beg + dst] = v;
+    }
     {
       const int b0 = sh.bstart[tid], bn = sh.bstart[tid + 1] - b0;
       if (bn > MSD_SMALL) {
         const int slot = atomicAdd(&sh.top, 1);
         if (slot < MSD_STACK) { sh.stack_beg[slot] = beg + b0; sh.stack_len[slot] = bn; }
         else sh.overflow = 1;
-      } else if (bn > 1) {
-        insertion_sort(kA + beg + b0, vA + beg + b0, bn);
       }
     }
     __syncthreads();
