@@ -192,7 +192,7 @@ __device__ __forceinline__ void sort_tile(uint32_t* kA, uint32_t* vA, uint32_t* 
 //      to its final slot); larger bins are pushed on a block-level work stack and partitioned again.
 // Uniformly distributed depths finish after one partition (bins of ~L/256 entries).  No match.any / warp ranking:
 // the stable LSD sort kept below for huge lists spends its time in the ADU pipe on exactly those.
-constexpr int MSD_SMALL = 32;
+constexpr int MSD_SMALL = 96;     // rank counting is O(bin) per element with uniform SIMT control flow: cheap up to ~100
 constexpr int MSD_STACK = 512;
 
 struct MsdShared {
