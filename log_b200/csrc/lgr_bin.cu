@@ -276,11 +276,15 @@ __device__ __forceinline__ bool sort_tile_msd(uint32_t* kA, uint32_t* vA, uint32
       if (bn <= MSD_SMALL) {
         const uint32_t* kb = kB + beg + b0;
         const uint32_t* vb = vB + beg + b0;
-        int rank = 0;
-        for (int j = 0; j < bn; j++) {
+        int rank = 0, eq = 0;
+#pragma unroll 8
+        for (int j = 0; j < bn; j++) {           // branch-free main loop: depth ties are counted, not resolved
           const uint32_t kj = kb[j];
-          rank += (kj < k) || (kj == k && vb[j] < v);
+          rank += (kj < k) ? 1 : 0;
+          eq += (kj == k) ? 1 : 0;
         }
+        if (eq > 1)                              // rare: some other entry of the bin has the same depth -> order by id
+          for (int j = 0; j < bn; j++) rank += (kb[j] == k && vb[j] < v) ? 1 : 0;
         dst = b0 + rank;
       }
       kA[beg + dst] = k; vA[beg + dst] = v;
