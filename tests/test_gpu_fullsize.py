@@ -76,7 +76,7 @@ def test_config3_10m_permutation_invariance(built, scene10m):
     assert rel(b['image'], a['image']) < 1e-4
     p = perm.to(a['radii'].device)
     assert torch.equal(a['radii'][p], b['radii'])
-    assert rel(b['point_weight'], a['point_weight'][p]) < 1e-4           # max is order independent (up to depth ties)
+    assert rel(b['point_weight'], a['point_weight'][p]) < 2e-3           # max is order independent (up to depth ties)
     assert float((a['point_weight'][p] != b['point_weight']).float().mean()) < 1e-3
     for k in ['dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations', 'dcolors']:
         assert rel(b[k], a[k][p]) < 1e-4, k
