@@ -185,13 +185,16 @@ def main():
     stats = {}
 
     def step_resident():
-        img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
-                                                         LGR_FILTER_MAX, True, tile_rows)
-        g = rasterize_backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
+        if world > 1:      # band mode: owner-grouped id lists, packed gradient rows, one all-to-all to the owner ranks
+            img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
+                                                             LGR_FILTER_MAX, True, tile_rows, num_owners=world)
+            rows = rasterize_backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
+            g = sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
+        else:
+            img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
+                                                             LGR_FILTER_MAX, True, tile_rows)
+            g = rasterize_backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
         stats['D'], stats['D_stock'], stats['maxlen'], stats['visible'] = st.num_instances, st.stock_instances, st.max_tile_len, st.num_visible
-        if world > 1:
-            packed = sharded.pack_grads((g[0], g[1], g[2], g[3], g[4], g[5] if deg == 0 else g[6].reshape(n, -1)))
-            return sharded.reduce_to_owners(packed)
         return g
 
     def barrier():
@@ -231,17 +234,24 @@ def main():
         h2d = sum(v.numel() * 4 for k, v in host.items() if not (k == 'colors' and deg > 0)) + host_G.numel() * 4
 
         def step_e2e():
-            t_ = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in host.items() if not (k == 'colors' and deg > 0)}
+            t_ = {k: v.to(dev, non_blocking=True) for k, v in host.items() if not (k == 'colors' and deg > 0)}
             Gd = host_G.to(dev, non_blocking=True)
+            if world > 1:
+                o_ = t_['opacities'].reshape(-1)
+                img, radii, pid, pwp, pw, st = rasterize_forward(settings, t_['means3D'], o_, t_['scales'], t_['rotations'],
+                                                                 t_['colors'], None, LGR_FILTER_MAX, True, tile_rows, num_owners=world)
+                loss = (img * Gd).sum()
+                rows = rasterize_backward(st, Gd, t_['means3D'], o_, t_['scales'], t_['rotations'], t_['colors'], None)
+                sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
+                return float(loss.item())
+            for v_ in t_.values():
+                v_.requires_grad_(True)
             m2d = torch.zeros(n, 3, device=dev, requires_grad=True)
             out = rast(means3D=t_['means3D'], means2D=m2d, shs=t_.get('shs') if deg > 0 else None,
                        colors_precomp=t_['colors'] if deg == 0 else None, opacities=t_['opacities'], scales=t_['scales'],
                        rotations=t_['rotations'], cov3D_precomp=None)
             loss = (out[0] * Gd).sum()
             loss.backward()
-            if world > 1:
-                sharded.reduce_to_owners(sharded.pack_grads((t_['means3D'].grad, m2d.grad, t_['opacities'].grad, t_['scales'].grad,
-                                                             t_['rotations'].grad, t_['colors'].grad if deg == 0 else t_['shs'].grad.reshape(n, -1))))
             return float(loss.item())           # D2H read of the step's result
         ne = max(3, min(args.steps, 10))
         for _ in range(6):          # allocator growth settles after ~5 iterations
@@ -280,7 +290,7 @@ def main():
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / (ms_step * 1e-3) / 1e6,
         'config': {'workload': f'{args.workload}: {n} Gaussians, {W}x{H}, sh_degree {deg}, fork flavour (5-tuple aux outputs)',
-                   'parallelism': f'tile-row shard x{world}' if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
+                   'parallelism': f'tile-row bands x{world}, owner-sparse NCCL all-to-all of gradient rows' if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
                    'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible']},
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                      'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes': kb[dom], 'kernel_ms': kms[dom]},

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 2
+#define LGR_ABI_VERSION 3
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -46,6 +46,14 @@ typedef struct lgr_view {
   int32_t filter_mode;  /* LGR_FILTER_* */
   int32_t want_aux;     /* 1: also produce point_id_pixel / point_weight_pixel / point_weight (fork 5-tuple) */
   int32_t tile_row_begin, tile_row_end; /* this call renders tile rows [begin,end); 0,0 = all (multi-GPU shard) */
+  /* Multi-GPU band mode (0 = off).  With num_owners = R > 0 the projection also compacts the ids of the Gaussians that
+   * reach the rendered tile band into band_ids_d, grouped by owner rank o = id / ceil(N/R): owner o's ids sit at
+   * band_ids_d[o*ceil(N/R) ... + band_count_d[o]).  Scatter and the per-Gaussian backward then walk only those lists,
+   * and splat records of Gaussians outside the band are not written. */
+  int32_t num_owners;
+  int32_t reserved0;
+  int32_t* band_ids_d;   /* (N) int32, or NULL */
+  int32_t* band_count_d; /* (num_owners) int32, zero-filled by lgr_forward_project */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */
@@ -104,7 +112,15 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  const uint8_t* clamped_d, const int32_t* tile_start_d, const int32_t* sorted_ids_d,
                  const float* image_d, const float* dL_dimage_d, float* dsplat_d,
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
-                 float* dcolors_d, float* dshs_d, void* stream);
+                 float* dcolors_d, float* dshs_d, float* grad_rows_d, void* stream);
+
+/* Band mode only (view->num_owners > 0, precomputed colours): when grad_rows_d != NULL lgr_backward writes, instead of
+ * the dense d*_d outputs (which may then be NULL), one packed row of LGR_ROW_FLOATS floats per listed Gaussian, rows
+ * grouped by owner in list order:  [dmeans3D 0..2 | dmeans2D 3..5 | dopacity 6 | dscales 7..9 | drotations 10..13 |
+ * dcolors 14..16 | id (int bits) 17 | 0 0].  lgr_grad_scatter_add adds received rows whose id lies in [lo,hi) into a
+ * dense shard of (hi-lo) x LGR_ROW_FLOATS floats (row id-lo). */
+#define LGR_ROW_FLOATS 20
+int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream);
 
 /* Diagnostics (not on the data path): per-kernel CUDA-event timing on the launching stream.
  * lgr_profile_enable(1) starts recording; lgr_profile_collect() synchronises the recorded events, writes the summed

@@ -12,10 +12,11 @@ LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
 LGR_TILE_SCRATCH_INTS = 33
-LGR_ABI_VERSION = 2
+LGR_ABI_VERSION = 3
+LGR_ROW_FLOATS = 20
 
 EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
-           'lgr_forward_render', 'lgr_backward', 'lgr_profile_enable', 'lgr_profile_collect',
+           'lgr_forward_render', 'lgr_backward', 'lgr_grad_scatter_add', 'lgr_profile_enable', 'lgr_profile_collect',
            'lgr_profile_kernel_name')
 LGR_PROFILE_KERNELS = 8
 
@@ -25,6 +26,7 @@ class LgrView(ctypes.Structure):
     _fields_ = [('image_height', _i32), ('image_width', _i32), ('tanfovx', _f32), ('tanfovy', _f32),
                 ('scale_modifier', _f32), ('sh_degree', _i32), ('sh_coeffs', _i32), ('filter_mode', _i32),
                 ('want_aux', _i32), ('tile_row_begin', _i32), ('tile_row_end', _i32),
+                ('num_owners', _i32), ('reserved0', _i32), ('band_ids_d', _vp), ('band_count_d', _vp),
                 ('viewmatrix_d', _vp), ('projmatrix_d', _vp), ('campos_d', _vp), ('bg_d', _vp)]
 
 
@@ -53,7 +55,9 @@ def load():
     lib.lgr_forward_render.restype = ctypes.c_int
     lib.lgr_forward_render.argtypes = [ctypes.POINTER(LgrView), _i64, _i64, _i32, _i32] + [_vp] * 15
     lib.lgr_backward.restype = ctypes.c_int
-    lib.lgr_backward.argtypes = [ctypes.POINTER(LgrView), _i64, _i64] + [_vp] * 22
+    lib.lgr_backward.argtypes = [ctypes.POINTER(LgrView), _i64, _i64] + [_vp] * 23
+    lib.lgr_grad_scatter_add.restype = ctypes.c_int
+    lib.lgr_grad_scatter_add.argtypes = [_i64, _vp, _i64, _i64, _vp, _vp]
     lib.lgr_profile_enable.restype = ctypes.c_int
     lib.lgr_profile_enable.argtypes = [ctypes.c_int]
     lib.lgr_profile_collect.restype = ctypes.c_int

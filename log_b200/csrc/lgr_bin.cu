@@ -69,8 +69,13 @@ __global__ void __launch_bounds__(SCATTER_THREADS)
 bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
                    const int32_t* __restrict__ tile_start, int32_t* __restrict__ cursor, uint32_t* __restrict__ inst_key,
                    uint32_t* __restrict__ inst_val) {
-  const int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
+  int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
   if (i >= n) return;
+  if (v.num_owners > 0) {      // band mode: slot i of the owner-grouped id lists
+    const int o = (int)(i / v.owner_chunk);
+    if ((int)(i - (int64_t)o * v.owner_chunk) >= v.band_count[o]) return;
+    i = v.band_ids[i];
+  }
   const int rad = radii[i];
   if (rad <= 0) return;
   const float4 r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);

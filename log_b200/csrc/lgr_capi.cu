@@ -10,7 +10,8 @@ int launch_project_fwd(const View&, int64_t, const float*, const float*, const f
                        const float*, float*, int32_t*, uint8_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_project_bwd(const View&, int64_t, const float*, const float*, const float*, const float*, bool,
                        const int32_t*, const uint8_t*, const float*, float*, float*, float*, float*, float*, float*,
-                       float*, cudaStream_t);
+                       float*, float*, cudaStream_t);
+int launch_grad_scatter_add(int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
 int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, const int32_t*, int32_t*,
                         uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
@@ -30,6 +31,7 @@ static bool view_ok(const lgr_view* v) {
   if (v->tile_row_begin < 0 || v->tile_row_end < v->tile_row_begin) return false;
   const int gy = (v->image_height + TILE - 1) / TILE;
   if (v->tile_row_end > gy) return false;
+  if (v->num_owners < 0 || (v->num_owners > 0 && (!v->band_ids_d || !v->band_count_d))) return false;
   return true;
 }
 
@@ -62,8 +64,13 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
   if (n > 0 && (!means3D_d || !opacities_d || !scales_d || !rotations_d || !splat_d || !radii_d)) return LGR_E_BADARG;
   if (n > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  const View v = make_view(view);
+  const View v = make_view(view, n);
   const int ntiles = v.gx * (v.row1 - v.row0);
+  if (v.num_owners > 0) {
+    if (shs_d) return LGR_E_UNSUPPORTED;          // band mode packs 17-float rows: precomputed colours only
+    cudaError_t e0 = cudaMemsetAsync(v.band_count, 0, sizeof(int32_t) * (size_t)v.num_owners, st);
+    if (e0 != cudaSuccess) return (int)e0;
+  }
   cudaError_t e = cudaMemsetAsync(tile_cursor_d, 0, sizeof(int32_t) * (size_t)ntiles * CSTRIDE, st);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(meta_d, 0, sizeof(int32_t) * LGR_META_INTS, st);
@@ -86,7 +93,7 @@ int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, i
   if (view->want_aux && (!point_id_pixel_d || !point_weight_pixel_d || (n > 0 && !point_weight_d))) return LGR_E_BADARG;
   if (num_instances > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  const View v = make_view(view);
+  const View v = make_view(view, n);
   int rc = launch_bin_and_sort(v, n, num_instances, max_tile_len, num_long_tiles, splat_d, radii_d, tile_start_d, tile_cursor_d,
                                inst_key_d, inst_val_d, inst_tmp_d, sorted_ids_d, st);
   if (rc) return rc;
@@ -100,24 +107,33 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  const uint8_t* clamped_d, const int32_t* tile_start_d, const int32_t* sorted_ids_d,
                  const float* image_d, const float* dL_dimage_d, float* dsplat_d,
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
-                 float* dcolors_d, float* dshs_d, void* stream) {
+                 float* dcolors_d, float* dshs_d, float* grad_rows_d, void* stream) {
   (void)opacities_d;
   if (!view_ok(view) || n < 0 || !tile_start_d || !image_d || !dL_dimage_d) return LGR_E_BADARG;
   if (n == 0) return 0;
   const bool use_sh = shs_d != nullptr;
   if (use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
-  if (!means3D_d || !scales_d || !rotations_d || !splat_d || !radii_d || !dsplat_d || !dmeans3D_d || !dmeans2D_d ||
-      !dopacities_d || !dscales_d || !drotations_d)
-    return LGR_E_BADARG;
-  if (use_sh ? (!dshs_d || !clamped_d || !view->campos_d) : !dcolors_d) return LGR_E_BADARG;
+  if (!means3D_d || !scales_d || !rotations_d || !splat_d || !radii_d || !dsplat_d) return LGR_E_BADARG;
+  if (grad_rows_d) {
+    if (view->num_owners <= 0 || use_sh) return LGR_E_BADARG;
+  } else {
+    if (view->num_owners > 0) return LGR_E_BADARG;   // band mode writes no splat records outside the band: rows only
+    if (!dmeans3D_d || !dmeans2D_d || !dopacities_d || !dscales_d || !drotations_d) return LGR_E_BADARG;
+    if (use_sh ? (!dshs_d || !clamped_d || !view->campos_d) : !dcolors_d) return LGR_E_BADARG;
+  }
   if (num_instances > 0 && !sorted_ids_d) return LGR_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const View v = make_view(view);
+  const View v = make_view(view, n);
   int rc = 0;
   if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, dL_dimage_d, dsplat_d, st);
   if (rc) return rc;
   return launch_project_bwd(v, n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
-                            dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, st);
+                            dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, grad_rows_d, st);
+}
+
+int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream) {
+  if (num_rows < 0 || hi < lo || (num_rows > 0 && (!rows_d || !shard_d))) return LGR_E_BADARG;
+  return launch_grad_scatter_add(num_rows, rows_d, lo, hi, shard_d, (cudaStream_t)stream);
 }
 
 /* ---- diagnostics: per-kernel CUDA-event timing (used by bench.py for the live roofline numbers) ---- */

@@ -68,6 +68,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   const int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
   int rad_out = 0;
   unsigned long long stock_tiles = 0;
+  bool in_band = false;
   if (i < n) {
     float p[3], s[3], R[9], Sg[9];
     load3(means, i, p);
@@ -130,15 +131,30 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
         r2 = make_float4(rgb[0], rgb[1], rgb[2], cv.t[2]);
         if (reach) {
           tile_rect_tight(px, py, rad, hx, hy, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
+          in_band = (x1 > x0) && (y1 > y0);
           for (int ty = y0; ty < y1; ty++)
             for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE, 1);
         }
       }
     }
-    float4* dst = reinterpret_cast<float4*>(splat + i * LGR_SPLAT_FLOATS);
-    dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    if (v.num_owners == 0 || in_band) {      // band mode: records outside the band are never read
+      float4* dst = reinterpret_cast<float4*>(splat + i * LGR_SPLAT_FLOATS);
+      dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    }
     radii[i] = rad_out;
     if (USE_SH && rad_out == 0) clamped[i] = 0;
+  }
+  if (v.num_owners > 0) {                    // compact the ids that reach the band, grouped by owner rank
+    const int lane = threadIdx.x & 31;
+    const int o = in_band ? (int)(i / v.owner_chunk) : -1 - lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, o);
+    if (in_band) {
+      const int leader = __ffs(peers) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(v.band_count + o, __popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      v.band_ids[(int64_t)o * v.owner_chunk + base + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+    }
   }
   // block statistics: D by the stock rule, number of visible Gaussians (one atomic pair per CTA)
   int vis = rad_out > 0;
@@ -161,19 +177,28 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
 // ---------------------------------------------------------------------------------------------------------
 // backward projection: dsplat (d/dpx, d/dpy, d/dconic xyz, d/dopacity, d/drgb) -> input gradients
 // ---------------------------------------------------------------------------------------------------------
-template <bool USE_SH>
+template <bool USE_SH, bool ROWS>
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ scales,
                    const float* __restrict__ rots, const float* __restrict__ shs, const int32_t* __restrict__ radii,
                    const uint8_t* __restrict__ clamped, const float* __restrict__ dsplat, float* __restrict__ dmeans,
                    float* __restrict__ dmeans2D, float* __restrict__ dopac, float* __restrict__ dscales,
-                   float* __restrict__ drots, float* __restrict__ dcolors, float* __restrict__ dshs) {
+                   float* __restrict__ drots, float* __restrict__ dcolors, float* __restrict__ dshs,
+                   float* __restrict__ grad_rows) {
   __shared__ float sV[16], sP[16], sCam[3];
   if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sP[threadIdx.x] = v.proj[threadIdx.x]; }
   if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
+  int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
   if (i >= n) return;
+  int64_t row = 0;
+  if (ROWS) {      // band mode: slot i of the owner-grouped id lists -> Gaussian id, packed output row
+    const int o = (int)(i / v.owner_chunk), sl = (int)(i - (int64_t)o * v.owner_chunk);
+    if (sl >= v.band_count[o]) return;
+    for (int k = 0; k < o; k++) row += v.band_count[k];
+    row += sl;
+    i = v.band_ids[i];
+  }
   float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dop = 0.f, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
   float drgb[3] = {0.f, 0.f, 0.f};
   const bool live = radii[i] > 0;
@@ -312,12 +337,46 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     float* dsh = dshs + (int64_t)i * K * 3;
     for (int k = 0; k < K * 3; k++) dsh[k] = 0.f;
   }
+  if (ROWS) {
+    float4* dst = reinterpret_cast<float4*>(grad_rows + row * LGR_ROW_FLOATS);
+    dst[0] = make_float4(dm[0], dm[1], dm[2], dm2[0]);
+    dst[1] = make_float4(dm2[1], 0.f, dop, dsc[0]);
+    dst[2] = make_float4(dsc[1], dsc[2], dq[0], dq[1]);
+    dst[3] = make_float4(dq[2], dq[3], drgb[0], drgb[1]);
+    dst[4] = make_float4(drgb[2], __int_as_float((int)i), 0.f, 0.f);
+    return;
+  }
   dmeans[3 * i] = dm[0]; dmeans[3 * i + 1] = dm[1]; dmeans[3 * i + 2] = dm[2];
   dmeans2D[3 * i] = dm2[0]; dmeans2D[3 * i + 1] = dm2[1]; dmeans2D[3 * i + 2] = 0.f;
   dopac[i] = dop;
   dscales[3 * i] = dsc[0]; dscales[3 * i + 1] = dsc[1]; dscales[3 * i + 2] = dsc[2];
   reinterpret_cast<float4*>(drots)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
   if (!USE_SH) { dcolors[3 * i] = drgb[0]; dcolors[3 * i + 1] = drgb[1]; dcolors[3 * i + 2] = drgb[2]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// owner side of the multi-GPU gradient exchange: add received packed rows into the dense owner shard
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PROJ_THREADS)
+grad_scatter_add_kernel(int64_t num_rows, const float* __restrict__ rows, int64_t lo, int64_t hi, float* __restrict__ shard) {
+  const int64_t r = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
+  if (r >= num_rows) return;
+  const float4* src = reinterpret_cast<const float4*>(rows + r * LGR_ROW_FLOATS);
+  const float4 e = __ldg(src + 4);
+  const int64_t id = (int64_t)__float_as_int(e.y);
+  if (id < lo || id >= hi) return;
+  float4* dst = reinterpret_cast<float4*>(shard + (id - lo) * LGR_ROW_FLOATS);
+  atomicAdd(dst, __ldg(src)); atomicAdd(dst + 1, __ldg(src + 1)); atomicAdd(dst + 2, __ldg(src + 2));
+  atomicAdd(dst + 3, __ldg(src + 3));
+  atomicAdd(reinterpret_cast<float*>(dst + 4), e.x);
+}
+
+int launch_grad_scatter_add(int64_t num_rows, const float* rows, int64_t lo, int64_t hi, float* shard, cudaStream_t st) {
+  if (num_rows <= 0) return 0;
+  const unsigned blocks = (unsigned)((num_rows + PROJ_THREADS - 1) / PROJ_THREADS);
+  grad_scatter_add_kernel<<<blocks, PROJ_THREADS, 0, st>>>(num_rows, rows, lo, hi, shard);
+  LGR_CHECK_LAUNCH();
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -350,14 +409,16 @@ int launch_project_fwd(const View& v, int64_t n, const float* means, const float
 int launch_project_bwd(const View& v, int64_t n, const float* means, const float* scales, const float* rots,
                        const float* shs, bool use_sh, const int32_t* radii, const uint8_t* clamped, const float* dsplat,
                        float* dmeans, float* dmeans2D, float* dopac, float* dscales, float* drots, float* dcolors,
-                       float* dshs, cudaStream_t st) {
+                       float* dshs, float* grad_rows, cudaStream_t st) {
   if (n == 0) return 0;
   const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
   ProfScope ps(K_PROJECT_BWD, st);
-  if (!use_sh)
-    project_bwd_kernel<false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs);
+  if (grad_rows)
+    project_bwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows);
+  else if (!use_sh)
+    project_bwd_kernel<false, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows);
   else
-    project_bwd_kernel<true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs);
+    project_bwd_kernel<true, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows);
   LGR_CHECK_LAUNCH();
   return 0;
 }

@@ -69,7 +69,8 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep):
+def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep,
+               num_owners=0, band_ids=None, band_count=None):
     dev = s.viewmatrix.device
     vm, pm = _f32c(s.viewmatrix, 'viewmatrix'), _f32c(s.projmatrix, 'projmatrix', dev)
     bg = _f32c(s.bg, 'bg', dev)
@@ -82,6 +83,9 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
     v.sh_degree, v.sh_coeffs = int(s.sh_degree), int(sh_coeffs)
     v.filter_mode, v.want_aux = int(filter_mode), int(bool(want_aux))
     v.tile_row_begin, v.tile_row_end = (0, 0) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+    v.num_owners = int(num_owners)
+    v.band_ids_d = band_ids.data_ptr() if band_ids is not None else None
+    v.band_count_d = band_count.data_ptr() if band_count is not None else None
     v.viewmatrix_d, v.projmatrix_d = vm.data_ptr(), pm.data_ptr()
     v.campos_d = cp.data_ptr() if cp is not None else None
     v.bg_d = bg.data_ptr()
@@ -91,18 +95,25 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
 class RasterState:
     """Buffers produced by the forward and consumed by the backward (kept alive by autograd)."""
     __slots__ = ('view', 'keep', 'n', 'num_instances', 'max_tile_len', 'stock_instances', 'num_visible', 'splat',
-                 'radii', 'clamped', 'tile_start', 'sorted_ids', 'final_T', 'n_contrib', 'image', 'sh')
+                 'radii', 'clamped', 'tile_start', 'sorted_ids', 'final_T', 'n_contrib', 'image', 'sh', 'num_owners',
+                 'band_ids', 'band_count', 'band_counts_host')
 
 
 def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_precomp, shs, filter_mode, want_aux,
-                      tile_rows=None):
-    """Run the forward through the C ABI.  Returns (image, radii, pid, pwp, point_weight, state)."""
+                      tile_rows=None, num_owners=0):
+    """Run the forward through the C ABI.  Returns (image, radii, pid, pwp, point_weight, state).
+    num_owners > 0 (multi-GPU band mode, see log_b200/sharded.py): also compact the ids of the Gaussians reaching the
+    band `tile_rows`, grouped by owner rank; the backward then returns packed gradient rows instead of dense tensors."""
     lib = _capi.load()
     dev = means3D.device
     n = int(means3D.shape[0])
     keep = []
     K = 0 if shs is None else int(shs.shape[1])
-    view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep)
+    band_ids = band_count = None
+    if num_owners > 0:
+        band_ids = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        band_count = torch.empty((num_owners,), dtype=torch.int32, device=dev)
+    view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep, num_owners, band_ids, band_count)
     H, W = view.image_height, view.image_width
     gx, gy = (W + 15) // 16, (H + 15) // 16
     rows = gy if tile_rows is None else int(tile_rows[1]) - int(tile_rows[0])
@@ -120,7 +131,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
                                         _ptr(rotations), _ptr(colors_precomp), _ptr(shs), _ptr(splat), _ptr(radii),
                                         _ptr(clamped), _ptr(tile_start), _ptr(tile_cursor), _ptr(meta), st),
                 'lgr_forward_project')
-    m = meta.tolist()                                   # the one host sync of the forward (8 ints)
+    m = (meta if band_count is None else torch.cat([meta, band_count])).tolist()   # the one host sync of the forward
     D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
     stock_D = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
     u32 = dict(dtype=torch.int32, device=dev)
@@ -146,17 +157,29 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     s.stock_instances, s.num_visible = stock_D, int(m[4])
     s.splat, s.radii, s.clamped, s.tile_start, s.sorted_ids = splat, radii, clamped, tile_start, sorted_ids
     s.final_T, s.n_contrib, s.image, s.sh = final_T, n_contrib, image, shs is not None
+    s.num_owners, s.band_ids, s.band_count = num_owners, band_ids, band_count
+    s.band_counts_host = [int(x) for x in m[_capi.LGR_META_INTS:]] if num_owners > 0 else None
     return image, radii, pid, pwp, pw, s
 
 
 def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scales, rotations, colors_precomp, shs):
-    """Run the backward through the C ABI.  Returns (dmeans3D, dmeans2D, dopacities, dscales, drotations, dcolors, dshs)."""
+    """Run the backward through the C ABI.  Returns (dmeans3D, dmeans2D, dopacities, dscales, drotations, dcolors, dshs);
+    in band mode (state.num_owners > 0) returns the packed gradient rows (M, LGR_ROW_FLOATS) grouped by owner instead."""
     lib = _capi.load()
     dev = means3D.device
     n = state.n
     f32 = dict(dtype=torch.float32, device=dev)
     g = _f32c(grad_image, 'grad_image', dev)
     dsplat = torch.zeros((n, _capi.LGR_GRAD_FLOATS), **f32)
+    if state.num_owners > 0:
+        rows = torch.empty((sum(state.band_counts_host), _capi.LGR_ROW_FLOATS), **f32)
+        _capi.check(lib.lgr_backward(ctypes.byref(state.view), n, state.num_instances, _ptr(means3D), _ptr(opacities),
+                                     _ptr(scales), _ptr(rotations), _ptr(colors_precomp), None, _ptr(state.splat),
+                                     _ptr(state.radii), None, _ptr(state.tile_start), _ptr(state.sorted_ids),
+                                     _ptr(state.image), _ptr(g), _ptr(dsplat), None, None, None, None, None, None, None,
+                                     ctypes.c_void_p(rows.data_ptr()) if rows.numel() else _ptr(dsplat), _stream()),
+                    'lgr_backward')
+        return rows
     dmeans3D = torch.empty((n, 3), **f32)
     dmeans2D = torch.empty((n, 3), **f32)
     dopac = torch.empty((n,), **f32)
@@ -168,7 +191,7 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
                                  _ptr(scales), _ptr(rotations), _ptr(colors_precomp), _ptr(shs), _ptr(state.splat),
                                  _ptr(state.radii), _ptr(state.clamped), _ptr(state.tile_start), _ptr(state.sorted_ids),
                                  _ptr(state.image), _ptr(g), _ptr(dsplat), _ptr(dmeans3D),
-                                 _ptr(dmeans2D), _ptr(dopac), _ptr(dscales), _ptr(drot), _ptr(dcolors), _ptr(dshs),
+                                 _ptr(dmeans2D), _ptr(dopac), _ptr(dscales), _ptr(drot), _ptr(dcolors), _ptr(dshs), None,
                                  _stream()), 'lgr_backward')
     return dmeans3D, dmeans2D, dopac, dscales, drot, dcolors, dshs
 

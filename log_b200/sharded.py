@@ -41,6 +41,40 @@ def unpack_grads(buf: torch.Tensor):
     return buf[:, 0:3], buf[:, 3:6], buf[:, 6], buf[:, 7:10], buf[:, 10:14], buf[:, 14:17]
 
 
+def rows_to_shard(rows: torch.Tensor, lo: int, hi: int, shard: torch.Tensor = None) -> torch.Tensor:
+    """Add packed gradient rows (M, LGR_ROW_FLOATS) whose id lies in [lo,hi) into the dense owner shard
+    (hi-lo, LGR_ROW_FLOATS); columns 0..16 are the 17 gradient floats in pack_grads order."""
+    import ctypes
+    from . import _capi
+    lib = _capi.load()
+    if shard is None:
+        shard = torch.zeros((max(hi - lo, 0), _capi.LGR_ROW_FLOATS), dtype=torch.float32, device=rows.device)
+    if rows.shape[0]:
+        rows = rows.contiguous()
+        _capi.check(lib.lgr_grad_scatter_add(int(rows.shape[0]), ctypes.c_void_p(rows.data_ptr()), int(lo), int(hi),
+                                             ctypes.c_void_p(shard.data_ptr()),
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'lgr_grad_scatter_add')
+    return shard
+
+
+def exchange_rows_to_owners(rows: torch.Tensor, send_counts, num_gaussians: int, group=None) -> torch.Tensor:
+    """The path's only collective: every rank holds packed gradient rows grouped by owner (send_counts[o] rows for owner
+    o); one NCCL all-to-all moves them to their owners, which add them into their dense shard.  Returns this rank's
+    shard (chunk, LGR_ROW_FLOATS); [:, :17] are the summed gradients of Gaussians owner_partition(N)[rank]."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = rows.device
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = rc.tolist()
+    recv = torch.empty((sum(recv_counts), rows.shape[1]), dtype=rows.dtype, device=dev)
+    dist.all_to_all_single(recv, rows.contiguous(), output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+    lo, hi = owner_partition(num_gaussians, world)[rank]
+    chunk = (num_gaussians + world - 1) // world
+    shard = torch.zeros((chunk, rows.shape[1]), dtype=torch.float32, device=dev)
+    return rows_to_shard(recv, lo, hi, shard)
+
+
 def reduce_to_owners(packed: torch.Tensor, group=None) -> torch.Tensor:
     """Sum the per-rank partial gradients; rank r receives rows owner_partition(N)[r] (zero padded to the chunk).
     NCCL: one reduce_scatter over NVLink.  gloo (CPU tests): all_reduce + slice, same result."""

@@ -263,3 +263,43 @@ def test_backward_is_linear_in_the_cotangent(built):
     a, b, c = run_gpu(cam, sc, G1), run_gpu(cam, sc, G2), run_gpu(cam, sc, 2.0 * G1 - 0.5 * G2)
     for k in ['dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations', 'dcolors']:
         assert rel(2.0 * a[k] - 0.5 * b[k], c[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_band_mode_rows_reproduce_dense_gradients(built, world):
+    """Multi-GPU band mode, emulated on one GPU: every "rank" renders its tile band with the owner-grouped id lists,
+    returns packed gradient rows; adding every rank's rows into the owner shards reproduces the dense gradients of the
+    un-sharded run, and the bands add up to the full image."""
+    from log_b200 import rasterize_backward, rasterize_forward, sharded
+    from log_b200._capi import LGR_FILTER_MAX
+    from util import settings_from_camera
+    W, H, n = 208, 144, 4001
+    cam = f32_camera(O.make_camera(W, H, bg=(0.2, 0.3, 0.4)))
+    sc = f32_scene(O.make_scene(n, W, H, 5.0, seed=33))
+    G = O.make_cotangent(3, H, W)
+    full = run_gpu(cam, sc, G)
+    dense = sharded.pack_grads((full['dmeans3D'], full['dmeans2D'], full['dopacities'], full['dscales'], full['drotations'],
+                                full['dcolors']))
+    dev = torch.device('cuda:0')
+    s = settings_from_camera(cam, dev)
+    t = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in sc.items()}
+    Gd = G.to(device=dev, dtype=torch.float32)
+    op = t['opacities'].reshape(-1)
+    rows_all, image = [], torch.zeros(3, H, W, device=dev)
+    for r, band in enumerate(sharded.tile_row_partition(H, world)):
+        img, radii, pid, pwp, pw, st = rasterize_forward(s, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None,
+                                                         LGR_FILTER_MAX, True, band, num_owners=world)
+        assert sum(st.band_counts_host) <= n and len(st.band_counts_host) == world
+        assert torch.equal(radii, full['radii'])
+        image += img
+        rows_all.append(rasterize_backward(st, Gd, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None))
+    assert torch.equal(image, full['image'].detach())
+    rows_all = torch.cat(rows_all)
+    ids = rows_all[:, 17].contiguous().view(torch.int32)
+    assert int(ids.min()) >= 0 and int(ids.max()) < n
+    shards = [sharded.rows_to_shard(rows_all, lo, hi) for lo, hi in sharded.owner_partition(n, world)]
+    got = torch.cat(shards)[:, :17]
+    assert got.shape == dense.shape
+    assert rel(got, dense) < 2e-5
+    for a, b in zip(sharded.unpack_grads(got), sharded.unpack_grads(dense)):
+        assert rel(a, b) < 5e-5
