@@ -117,8 +117,9 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
 /* Band mode only (view->num_owners > 0, precomputed colours): when grad_rows_d != NULL lgr_backward writes, instead of
  * the dense d*_d outputs (which may then be NULL), one packed row of LGR_ROW_FLOATS floats per listed Gaussian, rows
  * grouped by owner in list order:  [dmeans3D 0..2 | dmeans2D 3..5 | dopacity 6 | dscales 7..9 | drotations 10..13 |
- * dcolors 14..16 | id (int bits) 17 | 0 0].  lgr_grad_scatter_add adds received rows whose id lies in [lo,hi) into a
- * dense shard of (hi-lo) x LGR_ROW_FLOATS floats (row id-lo). */
+ * dcolors 14..16 | id (int bits) 17 | radius 18 | 0].  lgr_grad_scatter_add adds received rows whose id lies in [lo,hi)
+ * into a dense shard of (hi-lo) x LGR_ROW_FLOATS floats (row id-lo; slot 18 takes the maximum).  In band mode radii_d is
+ * only valid for Gaussians that can reach the band (0 elsewhere): the owner's radius is shard[:, 18]. */
 #define LGR_ROW_FLOATS 20
 int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream);
 

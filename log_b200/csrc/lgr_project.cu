@@ -69,7 +69,36 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   int rad_out = 0;
   unsigned long long stock_tiles = 0;
   bool in_band = false;
-  if (i < n) {
+  bool work = i < n;
+  if (work && v.num_owners > 0) {
+    // Band mode pre-cull (multi-GPU): with a unit quaternion lambda_max(Sigma3D) = max scale^2, so
+    // lambda_max(cov2D) <= (|T_x|^2 + |T_y|^2) s_max^2 + 0.6 bounds the radius without building the covariance.
+    // Gaussians whose padded extent cannot reach the band rows are dropped here (radii = 0 on this rank).
+    float p[3], s[3];
+    load3(means, i, p);
+    load3(scales, i, s);
+    const float4 q = ldg4(rots + 4 * i);
+    const float qn = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    const float tz = p[0] * sV[2] + p[1] * sV[6] + p[2] * sV[10] + sV[14];
+    if (!(tz > NEAR_Z)) work = false;
+    else if (fabsf(qn - 1.0f) < 1e-3f) {
+      const float ty = p[0] * sV[1] + p[1] * sV[5] + p[2] * sV[9] + sV[13];
+      const float tx = p[0] * sV[0] + p[1] * sV[4] + p[2] * sV[8] + sV[12];
+      const float itz = 1.0f / tz;
+      const float lx = fminf(CLAMP_FOV * v.tanfovx, fabsf(tx * itz)), ly = fminf(CLAMP_FOV * v.tanfovy, fabsf(ty * itz));
+      // |T_x|^2 <= |W|_2^2 |J_x|^2 ; the view rotation's squared spectral norm is bounded by its Frobenius norm
+      const float wf = sV[0] * sV[0] + sV[1] * sV[1] + sV[2] * sV[2] + sV[4] * sV[4] + sV[5] * sV[5] + sV[6] * sV[6] +
+                       sV[8] * sV[8] + sV[9] * sV[9] + sV[10] * sV[10];
+      const float jn = (v.fx * itz) * (v.fx * itz) * (1.0f + lx * lx) + (v.fy * itz) * (v.fy * itz) * (1.0f + ly * ly);
+      const float sm = fmaxf(fabsf(s[0]), fmaxf(fabsf(s[1]), fabsf(s[2]))) * v.scale_mod * 1.001f;
+      const float rb = 3.0f * sqrtf(wf * jn * sm * sm * 1.01f + 0.7f) + 2.0f;
+      const float hw = p[0] * sP[3] + p[1] * sP[7] + p[2] * sP[11] + sP[15];
+      const float hy_ = p[0] * sP[1] + p[1] * sP[5] + p[2] * sP[9] + sP[13];
+      const float py = ((hy_ / (hw + 0.0000001f) + 1.0f) * v.H - 1.0f) * 0.5f;
+      if (py + rb + (TILE - 1) < (float)(v.row0 * TILE) - 1.0f || py - rb > (float)(v.row1 * TILE) + 1.0f) work = false;
+    }
+  }
+  if (work) {
     float p[3], s[3], R[9], Sg[9];
     load3(means, i, p);
     load3(scales, i, s);
@@ -95,6 +124,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
       if ((x1 - x0) * (y1 - y0) > 0) {
         rad_out = rad;
         stock_tiles = (unsigned long long)((x1 - x0) * (max(0, min(y1, v.row1) - max(y0, v.row0))));
+        in_band = stock_tiles > 0;      // band lists follow the stock rectangle so that owners see every radius > 0
         const float idet = 1.0f / det;
         const float o = __ldg(opac + i);
         // conservative half extents of {alpha >= 1/255}:  d^T Conic d <= 2 ln(255 o)  =>  |dx| <= sqrt(q a)
@@ -131,7 +161,6 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
         r2 = make_float4(rgb[0], rgb[1], rgb[2], cv.t[2]);
         if (reach) {
           tile_rect_tight(px, py, rad, hx, hy, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
-          in_band = (x1 > x0) && (y1 > y0);
           for (int ty = y0; ty < y1; ty++)
             for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE, 1);
         }
@@ -143,6 +172,8 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     }
     radii[i] = rad_out;
     if (USE_SH && rad_out == 0) clamped[i] = 0;
+  } else if (i < n) {
+    radii[i] = 0;
   }
   if (v.num_owners > 0) {                    // compact the ids that reach the band, grouped by owner rank
     const int lane = threadIdx.x & 31;
@@ -343,7 +374,7 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     dst[1] = make_float4(dm2[1], 0.f, dop, dsc[0]);
     dst[2] = make_float4(dsc[1], dsc[2], dq[0], dq[1]);
     dst[3] = make_float4(dq[2], dq[3], drgb[0], drgb[1]);
-    dst[4] = make_float4(drgb[2], __int_as_float((int)i), 0.f, 0.f);
+    dst[4] = make_float4(drgb[2], __int_as_float((int)i), (float)radii[i], 0.f);
     return;
   }
   dmeans[3 * i] = dm[0]; dmeans[3 * i + 1] = dm[1]; dmeans[3 * i + 2] = dm[2];
@@ -369,6 +400,8 @@ grad_scatter_add_kernel(int64_t num_rows, const float* __restrict__ rows, int64_
   atomicAdd(dst, __ldg(src)); atomicAdd(dst + 1, __ldg(src + 1)); atomicAdd(dst + 2, __ldg(src + 2));
   atomicAdd(dst + 3, __ldg(src + 3));
   atomicAdd(reinterpret_cast<float*>(dst + 4), e.x);
+  // slot 18: projected radius, max over the bands that listed the Gaussian (non-negative floats order like ints)
+  atomicMax(reinterpret_cast<int*>(dst + 4) + 2, __float_as_int(e.z));
 }
 
 int launch_grad_scatter_add(int64_t num_rows, const float* rows, int64_t lo, int64_t hi, float* shard, cudaStream_t st) {

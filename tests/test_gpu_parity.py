@@ -290,7 +290,7 @@ def test_band_mode_rows_reproduce_dense_gradients(built, world):
         img, radii, pid, pwp, pw, st = rasterize_forward(s, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None,
                                                          LGR_FILTER_MAX, True, band, num_owners=world)
         assert sum(st.band_counts_host) <= n and len(st.band_counts_host) == world
-        assert torch.equal(radii, full['radii'])
+        assert ((radii == full['radii']) | (radii == 0)).all()     # band mode: radii only near the band
         image += img
         rows_all.append(rasterize_backward(st, Gd, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None))
     assert torch.equal(image, full['image'].detach())
@@ -298,6 +298,7 @@ def test_band_mode_rows_reproduce_dense_gradients(built, world):
     ids = rows_all[:, 17].contiguous().view(torch.int32)
     assert int(ids.min()) >= 0 and int(ids.max()) < n
     shards = [sharded.rows_to_shard(rows_all, lo, hi) for lo, hi in sharded.owner_partition(n, world)]
+    assert torch.equal(torch.cat(shards)[:, 18].int(), full['radii'])    # owners recover every radius (max over bands)
     got = torch.cat(shards)[:, :17]
     assert got.shape == dense.shape
     assert rel(got, dense) < 2e-5
