@@ -184,12 +184,21 @@ def main():
     opac = d['opacities'].reshape(-1)
     stats = {}
 
+    phase_ev = []
+
     def step_resident():
         if world > 1:      # band mode: owner-grouped id lists, packed gradient rows, one all-to-all to the owner ranks
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
             img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
                                                              LGR_FILTER_MAX, True, tile_rows, num_owners=world)
+            ev[1].record()
             rows = rasterize_backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
+            ev[2].record()
             g = sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
+            ev[3].record()
+            phase_ev.append(ev)
+            stats['rows'] = int(rows.shape[0])
         else:
             img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
                                                              LGR_FILTER_MAX, True, tile_rows)
@@ -213,10 +222,16 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    phase_ev.clear()
     for _ in range(args.steps):
         step_resident()
     e1.record()
     barrier()
+    phases = None
+    if phase_ev:
+        phases = {k: sum(ev[i].elapsed_time(ev[i + 1]) for ev in phase_ev) / len(phase_ev)
+                  for i, k in enumerate(('forward', 'backward', 'exchange'))}
+        phases['rows_sent_per_rank'] = stats.get('rows')
     prof = _capi.profile_collect()
     _capi.profile_enable(False)
     clk = clocks.stop() if rank == 0 else None
@@ -296,7 +311,7 @@ def main():
                      'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes': kb[dom], 'kernel_ms': kms[dom]},
         'roofline_step': {'b_model_bytes': b_model, 'b_min_bytes': b_min, 'achieved': b_model / (ms_step * 1e-3) / 1e9,
                           'frac': b_model / (ms_step * 1e-3) / 1e9 / peak, 'b_min_frac': b_min / (ms_step * 1e-3) / 1e9 / peak},
-        'kernel_ms': kms, 'gpu_launches': launches, 'clocks': clk, 'e2e': e2e,
+        'kernel_ms': kms, 'phase_ms_rank0': phases, 'gpu_launches': launches, 'clocks': clk, 'e2e': e2e,
     }
     if world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle          # the checker, timed as the CPU baseline (bounded sample)
