@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 3
+#define LGR_ABI_VERSION 4
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -46,14 +46,18 @@ typedef struct lgr_view {
   int32_t filter_mode;  /* LGR_FILTER_* */
   int32_t want_aux;     /* 1: also produce point_id_pixel / point_weight_pixel / point_weight (fork 5-tuple) */
   int32_t tile_row_begin, tile_row_end; /* this call renders tile rows [begin,end); 0,0 = all (multi-GPU shard) */
-  /* Multi-GPU band mode (0 = off).  With num_owners = R > 0 the projection also compacts the ids of the Gaussians that
-   * reach the rendered tile band into band_ids_d, grouped by owner rank o = id / ceil(N/R): owner o's ids sit at
-   * band_ids_d[o*ceil(N/R) ... + band_count_d[o]).  Scatter and the per-Gaussian backward then walk only those lists,
-   * and splat records of Gaussians outside the band are not written. */
+  /* Multi-GPU band mode (0 = off).  With num_owners = R > 0 the projection also compacts, without atomics, the ids of
+   * the Gaussians that reach the rendered tile band: CTA b (256 consecutive ids) stores its ids at
+   * band_ids_d[256 b ...) and their number in band_blk_d[b]; a scan then writes the exclusive prefix of those counts to
+   * band_blk_d[B + b] (B = ceil(N/256) CTAs, B+1 prefix entries) and the per-owner totals to band_count_d[o], owner
+   * o = id / owner_chunk with owner_chunk = LGR_OWNER_CHUNK(N, R) (a multiple of 256, so no CTA straddles owners).
+   * Scatter and the per-Gaussian backward walk only those lists (ascending ids = grouped by owner), and splat records
+   * of Gaussians outside the band are not written. */
   int32_t num_owners;
   int32_t reserved0;
-  int32_t* band_ids_d;   /* (N) int32, or NULL */
-  int32_t* band_count_d; /* (num_owners) int32, zero-filled by lgr_forward_project */
+  int32_t* band_ids_d;   /* (256 B) int32, or NULL */
+  int32_t* band_blk_d;   /* (2 B + 1) int32 */
+  int32_t* band_count_d; /* (num_owners) int32 */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */
@@ -121,6 +125,7 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
  * into a dense shard of (hi-lo) x LGR_ROW_FLOATS floats (row id-lo; slot 18 takes the maximum).  In band mode radii_d is
  * only valid for Gaussians that can reach the band (0 elsewhere): the owner's radius is shard[:, 18]. */
 #define LGR_ROW_FLOATS 20
+#define LGR_OWNER_CHUNK(n, r) ((((n) + (r) - 1) / (r) + 255) / 256 * 256)
 int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream);
 
 /* Diagnostics (not on the data path): per-kernel CUDA-event timing on the launching stream.

@@ -12,7 +12,7 @@ LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
 LGR_TILE_SCRATCH_INTS = 33
-LGR_ABI_VERSION = 3
+LGR_ABI_VERSION = 4
 LGR_ROW_FLOATS = 20
 
 EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
@@ -26,7 +26,7 @@ class LgrView(ctypes.Structure):
     _fields_ = [('image_height', _i32), ('image_width', _i32), ('tanfovx', _f32), ('tanfovy', _f32),
                 ('scale_modifier', _f32), ('sh_degree', _i32), ('sh_coeffs', _i32), ('filter_mode', _i32),
                 ('want_aux', _i32), ('tile_row_begin', _i32), ('tile_row_end', _i32),
-                ('num_owners', _i32), ('reserved0', _i32), ('band_ids_d', _vp), ('band_count_d', _vp),
+                ('num_owners', _i32), ('reserved0', _i32), ('band_ids_d', _vp), ('band_blk_d', _vp), ('band_count_d', _vp),
                 ('viewmatrix_d', _vp), ('projmatrix_d', _vp), ('campos_d', _vp), ('bg_d', _vp)]
 
 
@@ -90,3 +90,8 @@ def profile_collect():
     cnt = (_i32 * LGR_PROFILE_KERNELS)()
     check(lib.lgr_profile_collect(ms, cnt, LGR_PROFILE_KERNELS), 'lgr_profile_collect')
     return {lib.lgr_profile_kernel_name(k).decode(): (ms[k], cnt[k]) for k in range(LGR_PROFILE_KERNELS)}
+
+
+def owner_chunk(n, r):
+    """LGR_OWNER_CHUNK: Gaussians per owner rank, a multiple of 256 so that no projection CTA straddles two owners."""
+    return ((n + r - 1) // r + 255) // 256 * 256

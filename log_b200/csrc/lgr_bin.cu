@@ -71,9 +71,8 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
                    uint32_t* __restrict__ inst_val) {
   int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
   if (i >= n) return;
-  if (v.num_owners > 0) {      // band mode: slot i of the owner-grouped id lists
-    const int o = (int)(i / v.owner_chunk);
-    if ((int)(i - (int64_t)o * v.owner_chunk) >= v.band_count[o]) return;
+  if (v.num_owners > 0) {      // band mode: slot i of the per-CTA id lists written by project_fwd (256 ids per CTA)
+    if ((int)(i % 256) >= v.band_blk[i / 256]) return;
     i = v.band_ids[i];
   }
   const int rad = radii[i];

@@ -12,6 +12,7 @@ int launch_project_bwd(const View&, int64_t, const float*, const float*, const f
                        const int32_t*, const uint8_t*, const float*, float*, float*, float*, float*, float*, float*,
                        float*, float*, cudaStream_t);
 int launch_grad_scatter_add(int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
+int launch_band_scan(const View&, cudaStream_t);
 int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, const int32_t*, int32_t*,
                         uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
@@ -31,7 +32,7 @@ static bool view_ok(const lgr_view* v) {
   if (v->tile_row_begin < 0 || v->tile_row_end < v->tile_row_begin) return false;
   const int gy = (v->image_height + TILE - 1) / TILE;
   if (v->tile_row_end > gy) return false;
-  if (v->num_owners < 0 || (v->num_owners > 0 && (!v->band_ids_d || !v->band_count_d))) return false;
+  if (v->num_owners < 0 || (v->num_owners > 0 && (!v->band_ids_d || !v->band_count_d || !v->band_blk_d))) return false;
   return true;
 }
 
@@ -68,8 +69,6 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
   const int ntiles = v.gx * (v.row1 - v.row0);
   if (v.num_owners > 0) {
     if (shs_d) return LGR_E_UNSUPPORTED;          // band mode packs 17-float rows: precomputed colours only
-    cudaError_t e0 = cudaMemsetAsync(v.band_count, 0, sizeof(int32_t) * (size_t)v.num_owners, st);
-    if (e0 != cudaSuccess) return (int)e0;
   }
   cudaError_t e = cudaMemsetAsync(tile_cursor_d, 0, sizeof(int32_t) * (size_t)ntiles * CSTRIDE, st);
   if (e != cudaSuccess) return (int)e;
@@ -77,6 +76,8 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
   if (e != cudaSuccess) return (int)e;
   int rc = launch_project_fwd(v, n, means3D_d, opacities_d, scales_d, rotations_d, colors_precomp_d, shs_d, splat_d,
                               radii_d, clamped_d, tile_cursor_d, meta_d, st);
+  if (rc) return rc;
+  rc = launch_band_scan(v, st);
   if (rc) return rc;
   return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, st);
 }

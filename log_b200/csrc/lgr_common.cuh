@@ -27,7 +27,9 @@ struct View {
   int sh_degree, sh_K, filter_mode, want_aux;
   int num_owners, owner_chunk;     // band mode: ids grouped by owner o = id / owner_chunk (0 owners = off)
   int32_t* band_ids;
+  int32_t* band_blk;         // [0,B): per-CTA counts ; [B, 2B+1): exclusive prefix
   int32_t* band_count;
+  int band_blocks;           // B
   const float* view;         // (4,4) transposed storage: t_j = sum_i p_i * view[i*4+j] + view[12+j]
   const float* proj;
   const float* campos;
@@ -36,9 +38,10 @@ struct View {
 
 inline View make_view(const lgr_view* v, int64_t n = 0) {
   View o;
-  o.num_owners = v->num_owners; o.band_ids = v->band_ids_d; o.band_count = v->band_count_d;
-  o.owner_chunk = o.num_owners > 0 ? (int)((n + o.num_owners - 1) / o.num_owners) : 0;
-  if (o.owner_chunk < 1) o.owner_chunk = 1;
+  o.num_owners = v->num_owners; o.band_ids = v->band_ids_d; o.band_blk = v->band_blk_d; o.band_count = v->band_count_d;
+  o.owner_chunk = o.num_owners > 0 ? (int)LGR_OWNER_CHUNK(n, (int64_t)o.num_owners) : 256;
+  if (o.owner_chunk < 256) o.owner_chunk = 256;
+  o.band_blocks = (int)((n + 255) / 256);
   o.H = v->image_height; o.W = v->image_width;
   o.gx = (o.W + TILE - 1) / TILE; o.gy = (o.H + TILE - 1) / TILE;
   o.row0 = v->tile_row_begin; o.row1 = v->tile_row_end;

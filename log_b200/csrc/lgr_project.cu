@@ -175,17 +175,18 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   } else if (i < n) {
     radii[i] = 0;
   }
-  if (v.num_owners > 0) {                    // compact the ids that reach the band, grouped by owner rank
-    const int lane = threadIdx.x & 31;
-    const int o = in_band ? (int)(i / v.owner_chunk) : -1 - lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, o);
-    if (in_band) {
-      const int leader = __ffs(peers) - 1;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(v.band_count + o, __popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      v.band_ids[(int64_t)o * v.owner_chunk + base + __popc(peers & ((1u << lane) - 1u))] = (int)i;
-    }
+  if (v.num_owners > 0) {      // atomics-free compaction of the ids that reach the band into this CTA's segment
+    __shared__ int sCnt[PROJ_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, in_band);
+    if (lane == 0) sCnt[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < PROJ_THREADS / 32; w++) { const int c = sCnt[w]; if (w < wid) base += c; total += c; }
+    if (in_band) v.band_ids[(int64_t)blockIdx.x * PROJ_THREADS + base + __popc(bal & ((1u << lane) - 1u))] = (int)i;
+    if (threadIdx.x == 0) v.band_blk[blockIdx.x] = total;
+    __syncthreads();
   }
   // block statistics: D by the stock rule, number of visible Gaussians (one atomic pair per CTA)
   int vis = rad_out > 0;
@@ -224,10 +225,9 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   if (i >= n) return;
   int64_t row = 0;
   if (ROWS) {      // band mode: slot i of the owner-grouped id lists -> Gaussian id, packed output row
-    const int o = (int)(i / v.owner_chunk), sl = (int)(i - (int64_t)o * v.owner_chunk);
-    if (sl >= v.band_count[o]) return;
-    for (int k = 0; k < o; k++) row += v.band_count[k];
-    row += sl;
+    const int b = (int)(i / PROJ_THREADS), sl = (int)(i % PROJ_THREADS);
+    if (sl >= v.band_blk[b]) return;
+    row = (int64_t)v.band_blk[v.band_blocks + b] + sl;
     i = v.band_ids[i];
   }
   float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dop = 0.f, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -383,6 +383,54 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   dscales[3 * i] = dsc[0]; dscales[3 * i + 1] = dsc[1]; dscales[3 * i + 2] = dsc[2];
   reinterpret_cast<float4*>(drots)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
   if (!USE_SH) { dcolors[3 * i] = drgb[0]; dcolors[3 * i + 1] = drgb[1]; dcolors[3 * i + 2] = drgb[2]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// band mode: exclusive prefix of the per-CTA list lengths (row offsets) and per-owner totals
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+band_scan_kernel(View v) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, B = v.band_blocks;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int b = base + tid;
+    const int c = b < B ? v.band_blk[b] : 0;
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (b < B) v.band_blk[B + b] = carry + (wid ? warp_sum[wid - 1] : 0) + x - c;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sum[31];
+    __syncthreads();
+  }
+  if (tid == 0) v.band_blk[2 * B] = carry_s;
+  __syncthreads();
+  // owner o covers CTAs [o*cpb, (o+1)*cpb): total = prefix difference
+  const int cpb = v.owner_chunk / PROJ_THREADS;
+  for (int o = tid; o < v.num_owners; o += 1024) {
+    const int b0 = min(B, o * cpb), b1 = min(B, (o + 1) * cpb);
+    v.band_count[o] = v.band_blk[B + b1] - v.band_blk[B + b0];
+  }
+}
+
+int launch_band_scan(const View& v, cudaStream_t st) {
+  if (v.num_owners <= 0) return 0;
+  band_scan_kernel<<<1, 1024, 0, st>>>(v);
+  LGR_CHECK_LAUNCH();
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

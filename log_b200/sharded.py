@@ -25,9 +25,14 @@ def tile_row_partition(image_height: int, world_size: int) -> List[Tuple[int, in
     return out
 
 
+def owner_chunk(num_gaussians: int, world_size: int) -> int:
+    """Gaussians per owner: ceil(N/R) rounded up to a multiple of 256 (LGR_OWNER_CHUNK in the C header)."""
+    return ((num_gaussians + world_size - 1) // world_size + 255) // 256 * 256
+
+
 def owner_partition(num_gaussians: int, world_size: int) -> List[Tuple[int, int]]:
     """Gaussian index blocks [lo,hi) owning the reduced gradient rows (equal chunk, last ranks may be short)."""
-    chunk = (num_gaussians + world_size - 1) // world_size
+    chunk = owner_chunk(num_gaussians, world_size)
     return [(min(num_gaussians, r * chunk), min(num_gaussians, (r + 1) * chunk)) for r in range(world_size)]
 
 
@@ -70,8 +75,7 @@ def exchange_rows_to_owners(rows: torch.Tensor, send_counts, num_gaussians: int,
     recv = torch.empty((sum(recv_counts), rows.shape[1]), dtype=rows.dtype, device=dev)
     dist.all_to_all_single(recv, rows.contiguous(), output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
     lo, hi = owner_partition(num_gaussians, world)[rank]
-    chunk = (num_gaussians + world - 1) // world
-    shard = torch.zeros((chunk, rows.shape[1]), dtype=torch.float32, device=dev)
+    shard = torch.zeros((owner_chunk(num_gaussians, world), rows.shape[1]), dtype=torch.float32, device=dev)
     return rows_to_shard(recv, lo, hi, shard)
 
 
@@ -81,7 +85,7 @@ def reduce_to_owners(packed: torch.Tensor, group=None) -> torch.Tensor:
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n, f = packed.shape
-    chunk = (n + world - 1) // world
+    chunk = owner_chunk(n, world)
     if n != chunk * world:
         pad = torch.zeros((chunk * world - n, f), dtype=packed.dtype, device=packed.device)
         packed = torch.cat([packed, pad], dim=0)
