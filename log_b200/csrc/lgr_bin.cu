@@ -72,8 +72,11 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
   int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
   if (i >= n) return;
   if (v.num_owners > 0) {      // band mode: slot i of the per-CTA id lists written by project_fwd (256 ids per CTA)
-    if ((int)(i % 256) >= v.band_blk[i / 256]) return;
-    i = v.band_ids[i];
+    const int b = (int)(i / 256), sl = (int)(i % 256);
+    if (sl >= v.band_blk[b]) return;
+    const int id = v.band_ids[i];
+    v.band_rows[v.band_blk[v.band_blocks + b] + sl] = id;      // dense packed-row -> id map for the backward
+    i = id;
   }
   const int rad = radii[i];
   if (rad <= 0) return;

@@ -32,7 +32,7 @@ static bool view_ok(const lgr_view* v) {
   if (v->tile_row_begin < 0 || v->tile_row_end < v->tile_row_begin) return false;
   const int gy = (v->image_height + TILE - 1) / TILE;
   if (v->tile_row_end > gy) return false;
-  if (v->num_owners < 0 || (v->num_owners > 0 && (!v->band_ids_d || !v->band_count_d || !v->band_blk_d))) return false;
+  if (v->num_owners < 0 || (v->num_owners > 0 && (!v->band_ids_d || !v->band_count_d || !v->band_blk_d || !v->band_rows_d))) return false;
   return true;
 }
 
@@ -124,7 +124,7 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   }
   if (num_instances > 0 && !sorted_ids_d) return LGR_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const View v = make_view(view, n);
+  const View v = make_view(view, n);      // band mode: n = number of listed rows; the chunk fields are unused downstream
   int rc = 0;
   if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, dL_dimage_d, dsplat_d, st);
   if (rc) return rc;

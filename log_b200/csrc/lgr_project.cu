@@ -65,7 +65,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sP[threadIdx.x] = v.proj[threadIdx.x]; }
   if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
+  int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
   int rad_out = 0;
   unsigned long long stock_tiles = 0;
   bool in_band = false;
@@ -97,6 +97,24 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
       const float py = ((hy_ / (hw + 0.0000001f) + 1.0f) * v.H - 1.0f) * 0.5f;
       if (py + rb + (TILE - 1) < (float)(v.row0 * TILE) - 1.0f || py - rb > (float)(v.row1 * TILE) + 1.0f) work = false;
     }
+  }
+  if (v.num_owners > 0) {
+    // The survivors are a minority scattered over all warps: compact them inside the CTA so that the heavy projection
+    // below runs on dense warps (it is instruction bound, ~400 instructions per Gaussian).
+    __shared__ int sSurv[PROJ_THREADS];
+    __shared__ int sWcnt[PROJ_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (!work && i < n) radii[i] = 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, work);
+    if (lane == 0) sWcnt[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < PROJ_THREADS / 32; w++) { const int c = sWcnt[w]; if (w < wid) base += c; total += c; }
+    if (work) sSurv[base + __popc(bal & ((1u << lane) - 1u))] = threadIdx.x;
+    __syncthreads();
+    work = threadIdx.x < total;
+    i = work ? (int64_t)blockIdx.x * PROJ_THREADS + sSurv[threadIdx.x] : n;
   }
   if (work) {
     float p[3], s[3], R[9], Sg[9];
@@ -173,7 +191,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     radii[i] = rad_out;
     if (USE_SH && rad_out == 0) clamped[i] = 0;
   } else if (i < n) {
-    radii[i] = 0;
+    radii[i] = 0;      // only reachable outside band mode (i >= n otherwise)
   }
   if (v.num_owners > 0) {      // atomics-free compaction of the ids that reach the band into this CTA's segment
     __shared__ int sCnt[PROJ_THREADS / 32];
@@ -225,10 +243,8 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   if (i >= n) return;
   int64_t row = 0;
   if (ROWS) {      // band mode: slot i of the owner-grouped id lists -> Gaussian id, packed output row
-    const int b = (int)(i / PROJ_THREADS), sl = (int)(i % PROJ_THREADS);
-    if (sl >= v.band_blk[b]) return;
-    row = (int64_t)v.band_blk[v.band_blocks + b] + sl;
-    i = v.band_ids[i];
+    row = i;                                  // thread = packed row; band_rows[row] = Gaussian id (written by the scatter)
+    i = v.band_rows[row];
   }
   float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dop = 0.f, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
   float drgb[3] = {0.f, 0.f, 0.f};
