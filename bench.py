@@ -185,6 +185,14 @@ def main():
     stats = {}
 
     phase_ev = []
+    peer = None
+    if world > 1 and os.environ.get('LGR_EXCHANGE', 'peer') == 'peer':
+        try:
+            peer = sharded.PeerExchange(n)
+        except Exception as e:      # symmetric memory unavailable: NCCL all-to-all route
+            peer = None
+            if rank == 0:
+                print(f'bench.py: peer exchange unavailable ({e!r}); using NCCL all-to-all', file=sys.stderr)
 
     def step_resident():
         if world > 1:      # band mode: owner-grouped id lists, packed gradient rows, one all-to-all to the owner ranks
@@ -193,12 +201,16 @@ def main():
             img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
                                                              LGR_FILTER_MAX, True, tile_rows, num_owners=world)
             ev[1].record()
-            rows = rasterize_backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
-            ev[2].record()
-            g = sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
+            if peer is not None:
+                g = peer.backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col)
+                ev[2].record()
+            else:
+                rows = rasterize_backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
+                ev[2].record()
+                g = sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
             ev[3].record()
             phase_ev.append(ev)
-            stats['rows'] = int(rows.shape[0])
+            stats['rows'] = sum(st.band_counts_host)
         else:
             img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
                                                              LGR_FILTER_MAX, True, tile_rows)
@@ -256,8 +268,11 @@ def main():
                 img, radii, pid, pwp, pw, st = rasterize_forward(settings, t_['means3D'], o_, t_['scales'], t_['rotations'],
                                                                  t_['colors'], None, LGR_FILTER_MAX, True, tile_rows, num_owners=world)
                 loss = (img * Gd).sum()
-                rows = rasterize_backward(st, Gd, t_['means3D'], o_, t_['scales'], t_['rotations'], t_['colors'], None)
-                sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
+                if peer is not None:
+                    peer.backward(st, Gd, t_['means3D'], o_, t_['scales'], t_['rotations'], t_['colors'])
+                else:
+                    rows = rasterize_backward(st, Gd, t_['means3D'], o_, t_['scales'], t_['rotations'], t_['colors'], None)
+                    sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
                 return float(loss.item())
             for v_ in t_.values():
                 v_.requires_grad_(True)
@@ -305,7 +320,7 @@ def main():
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / (ms_step * 1e-3) / 1e6,
         'config': {'workload': f'{args.workload}: {n} Gaussians, {W}x{H}, sh_degree {deg}, fork flavour (5-tuple aux outputs)',
-                   'parallelism': f'tile-row bands x{world}, owner-sparse NCCL all-to-all of gradient rows' if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
+                   'parallelism': (f'tile-row bands x{world}, gradient rows ' + ('pushed to owner ranks over NVLink peer memory (fused in the backward kernel)' if peer is not None else 'NCCL all-to-all to owner ranks')) if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
                    'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible']},
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                      'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes': kb[dom], 'kernel_ms': kms[dom]},

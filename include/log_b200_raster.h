@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 5
+#define LGR_ABI_VERSION 6
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -117,7 +117,8 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  const uint8_t* clamped_d, const int32_t* tile_start_d, const int32_t* sorted_ids_d,
                  const float* image_d, const float* dL_dimage_d, float* dsplat_d,
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
-                 float* dcolors_d, float* dshs_d, float* grad_rows_d, void* stream);
+                 float* dcolors_d, float* dshs_d, float* grad_rows_d, void* const* peer_stage_d, int32_t my_rank,
+                 void* stream);
 
 /* Band mode only (view->num_owners > 0, precomputed colours): when grad_rows_d != NULL lgr_backward writes, instead of
  * the dense d*_d outputs (which may then be NULL), one packed row of LGR_ROW_FLOATS floats per listed Gaussian, rows
@@ -125,9 +126,18 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
  * dcolors 14..16 | id (int bits) 17 | radius 18 | 0].  lgr_grad_scatter_add adds received rows whose id lies in [lo,hi)
  * into a dense shard of (hi-lo) x LGR_ROW_FLOATS floats (row id-lo; slot 18 takes the maximum).  In band mode radii_d is
  * only valid for Gaussians that can reach the band (0 elsewhere): the owner's radius is shard[:, 18]. */
+/* Fused exchange (band mode): when peer_stage_d != NULL it is a DEVICE array of num_owners pointers, entry o being owner
+ * rank o's staging buffer mapped into this process (NVLink peer memory, e.g. torch symmetric memory).  lgr_backward then
+ * stores every packed row straight into its owner's buffer instead of grad_rows_d:
+ *     stage layout: LGR_STAGE_HEADER_FLOATS floats of header (int32 counts[source rank]) followed by
+ *                   num_owners regions of owner_chunk rows; source rank s fills region s from its start.
+ * After a cross-rank barrier the owner calls lgr_grad_scatter_add_staged on its own buffer. */
+#define LGR_STAGE_HEADER_FLOATS 64
 #define LGR_ROW_FLOATS 20
 #define LGR_OWNER_CHUNK(n, r) ((((n) + (r) - 1) / (r) + 255) / 256 * 256)
 int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream);
+int lgr_grad_scatter_add_staged(const float* stage_d, int32_t num_sources, int64_t owner_chunk, int64_t lo, int64_t hi,
+                                float* shard_d, void* stream);
 
 /* Diagnostics (not on the data path): per-kernel CUDA-event timing on the launching stream.
  * lgr_profile_enable(1) starts recording; lgr_profile_collect() synchronises the recorded events, writes the summed

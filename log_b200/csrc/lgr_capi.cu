@@ -10,8 +10,9 @@ int launch_project_fwd(const View&, int64_t, const float*, const float*, const f
                        const float*, float*, int32_t*, uint8_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_project_bwd(const View&, int64_t, const float*, const float*, const float*, const float*, bool,
                        const int32_t*, const uint8_t*, const float*, float*, float*, float*, float*, float*, float*,
-                       float*, float*, cudaStream_t);
+                       float*, float*, void* const*, int, cudaStream_t);
 int launch_grad_scatter_add(int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
+int launch_grad_scatter_add_staged(const float*, int, int64_t, int64_t, int64_t, float*, cudaStream_t);
 int launch_band_scan(const View&, cudaStream_t);
 int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, const int32_t*, int32_t*,
@@ -108,15 +109,17 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  const uint8_t* clamped_d, const int32_t* tile_start_d, const int32_t* sorted_ids_d,
                  const float* image_d, const float* dL_dimage_d, float* dsplat_d,
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
-                 float* dcolors_d, float* dshs_d, float* grad_rows_d, void* stream) {
+                 float* dcolors_d, float* dshs_d, float* grad_rows_d, void* const* peer_stage_d, int32_t my_rank,
+                 void* stream) {
   (void)opacities_d;
   if (!view_ok(view) || n < 0 || !tile_start_d || !image_d || !dL_dimage_d) return LGR_E_BADARG;
-  if (n == 0) return 0;
+  if (n == 0 && !peer_stage_d) return 0;
   const bool use_sh = shs_d != nullptr;
   if (use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
   if (!means3D_d || !scales_d || !rotations_d || !splat_d || !radii_d || !dsplat_d) return LGR_E_BADARG;
-  if (grad_rows_d) {
+  if (grad_rows_d || peer_stage_d) {
     if (view->num_owners <= 0 || use_sh) return LGR_E_BADARG;
+    if (peer_stage_d && (my_rank < 0 || my_rank >= view->num_owners)) return LGR_E_BADARG;
   } else {
     if (view->num_owners > 0) return LGR_E_BADARG;   // band mode writes no splat records outside the band: rows only
     if (!dmeans3D_d || !dmeans2D_d || !dopacities_d || !dscales_d || !drotations_d) return LGR_E_BADARG;
@@ -129,7 +132,13 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, dL_dimage_d, dsplat_d, st);
   if (rc) return rc;
   return launch_project_bwd(v, n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
-                            dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, grad_rows_d, st);
+                            dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, grad_rows_d, peer_stage_d, my_rank, st);
+}
+
+int lgr_grad_scatter_add_staged(const float* stage_d, int32_t num_sources, int64_t owner_chunk, int64_t lo, int64_t hi,
+                                float* shard_d, void* stream) {
+  if (!stage_d || !shard_d || num_sources <= 0 || owner_chunk <= 0 || hi < lo) return LGR_E_BADARG;
+  return launch_grad_scatter_add_staged(stage_d, num_sources, owner_chunk, lo, hi, shard_d, (cudaStream_t)stream);
 }
 
 int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream) {

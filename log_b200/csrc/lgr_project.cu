@@ -234,7 +234,7 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
                    const uint8_t* __restrict__ clamped, const float* __restrict__ dsplat, float* __restrict__ dmeans,
                    float* __restrict__ dmeans2D, float* __restrict__ dopac, float* __restrict__ dscales,
                    float* __restrict__ drots, float* __restrict__ dcolors, float* __restrict__ dshs,
-                   float* __restrict__ grad_rows) {
+                   float* __restrict__ grad_rows, void* const* __restrict__ peer_stage, int my_rank) {
   __shared__ float sV[16], sP[16], sCam[3];
   if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sP[threadIdx.x] = v.proj[threadIdx.x]; }
   if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
@@ -385,7 +385,17 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     for (int k = 0; k < K * 3; k++) dsh[k] = 0.f;
   }
   if (ROWS) {
-    float4* dst = reinterpret_cast<float4*>(grad_rows + row * LGR_ROW_FLOATS);
+    float4* dst;
+    if (peer_stage) {      // fused exchange: the row goes straight into its owner's staging buffer over NVLink
+      int o = 0;
+      int64_t first = 0;
+      while (o + 1 < v.num_owners && row >= first + v.band_count[o]) { first += v.band_count[o]; o++; }
+      float* base = reinterpret_cast<float*>(peer_stage[o]);
+      dst = reinterpret_cast<float4*>(base + LGR_STAGE_HEADER_FLOATS +
+                                      ((int64_t)my_rank * v.owner_chunk + (row - first)) * LGR_ROW_FLOATS);
+    } else {
+      dst = reinterpret_cast<float4*>(grad_rows + row * LGR_ROW_FLOATS);
+    }
     dst[0] = make_float4(dm[0], dm[1], dm[2], dm2[0]);
     dst[1] = make_float4(dm2[1], 0.f, dop, dsc[0]);
     dst[2] = make_float4(dsc[1], dsc[2], dq[0], dq[1]);
@@ -468,6 +478,46 @@ grad_scatter_add_kernel(int64_t num_rows, const float* __restrict__ rows, int64_
   atomicMax(reinterpret_cast<int*>(dst + 4) + 2, __float_as_int(e.z));
 }
 
+// tell every owner how many rows this rank stored into its region (also when it is zero)
+__global__ void push_counts_kernel(View v, void* const* __restrict__ peer_stage, int my_rank) {
+  const int o = threadIdx.x;
+  if (o < v.num_owners) reinterpret_cast<int*>(peer_stage[o])[my_rank] = v.band_count[o];
+}
+
+// rows staged by `num_sources` peers: region s holds counts[s] rows (counts in the header)
+__global__ void __launch_bounds__(PROJ_THREADS)
+grad_scatter_add_staged_kernel(const float* __restrict__ stage, int num_sources, int64_t chunk, int64_t lo, int64_t hi,
+                               float* __restrict__ shard) {
+  const int* counts = reinterpret_cast<const int*>(stage);
+  int64_t total = 0;
+  for (int s = 0; s < num_sources; s++) total += counts[s];
+  for (int64_t t = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * PROJ_THREADS) {
+    int s = 0;
+    int64_t first = 0;
+    while (s + 1 < num_sources && t >= first + counts[s]) { first += counts[s]; s++; }
+    const float4* src = reinterpret_cast<const float4*>(stage + LGR_STAGE_HEADER_FLOATS + ((int64_t)s * chunk + (t - first)) * LGR_ROW_FLOATS);
+    const float4 e = src[4];
+    const int64_t id = (int64_t)__float_as_int(e.y);
+    if (id < lo || id >= hi) continue;
+    float4* dst = reinterpret_cast<float4*>(shard + (id - lo) * LGR_ROW_FLOATS);
+    atomicAdd(dst, src[0]); atomicAdd(dst + 1, src[1]); atomicAdd(dst + 2, src[2]); atomicAdd(dst + 3, src[3]);
+    atomicAdd(reinterpret_cast<float*>(dst + 4), e.x);
+    atomicMax(reinterpret_cast<int*>(dst + 4) + 2, __float_as_int(e.z));
+  }
+}
+
+int launch_grad_scatter_add_staged(const float* stage, int num_sources, int64_t chunk, int64_t lo, int64_t hi, float* shard,
+                                   cudaStream_t st) {
+  if (num_sources <= 0 || chunk <= 0) return 0;
+  // enough CTAs for ~1.5 chunk rows; the grid-stride loop covers the (device-side) true total
+  int64_t nb = (chunk * 3 / 2 + PROJ_THREADS - 1) / PROJ_THREADS;
+  if (nb > (1 << 20)) nb = 1 << 20;
+  const unsigned blocks = (unsigned)nb;
+  grad_scatter_add_staged_kernel<<<blocks, PROJ_THREADS, 0, st>>>(stage, num_sources, chunk, lo, hi, shard);
+  LGR_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_grad_scatter_add(int64_t num_rows, const float* rows, int64_t lo, int64_t hi, float* shard, cudaStream_t st) {
   if (num_rows <= 0) return 0;
   const unsigned blocks = (unsigned)((num_rows + PROJ_THREADS - 1) / PROJ_THREADS);
@@ -506,16 +556,20 @@ int launch_project_fwd(const View& v, int64_t n, const float* means, const float
 int launch_project_bwd(const View& v, int64_t n, const float* means, const float* scales, const float* rots,
                        const float* shs, bool use_sh, const int32_t* radii, const uint8_t* clamped, const float* dsplat,
                        float* dmeans, float* dmeans2D, float* dopac, float* dscales, float* drots, float* dcolors,
-                       float* dshs, float* grad_rows, cudaStream_t st) {
+                       float* dshs, float* grad_rows, void* const* peer_stage, int my_rank, cudaStream_t st) {
+  if (peer_stage) {      // owners must learn this rank's row counts even when they are zero
+    push_counts_kernel<<<1, 64, 0, st>>>(v, peer_stage, my_rank);
+    LGR_CHECK_LAUNCH();
+  }
   if (n == 0) return 0;
   const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
   ProfScope ps(K_PROJECT_BWD, st);
-  if (grad_rows)
-    project_bwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows);
+  if (grad_rows || peer_stage)
+    project_bwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   else if (!use_sh)
-    project_bwd_kernel<false, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows);
+    project_bwd_kernel<false, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   else
-    project_bwd_kernel<true, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows);
+    project_bwd_kernel<true, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   LGR_CHECK_LAUNCH();
   return 0;
 }

@@ -167,7 +167,8 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     return image, radii, pid, pwp, pw, s
 
 
-def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scales, rotations, colors_precomp, shs):
+def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scales, rotations, colors_precomp, shs,
+                       peer_stage=None, my_rank=0):
     """Run the backward through the C ABI.  Returns (dmeans3D, dmeans2D, dopacities, dscales, drotations, dcolors, dshs);
     in band mode (state.num_owners > 0) returns the packed gradient rows (M, LGR_ROW_FLOATS) grouped by owner instead."""
     lib = _capi.load()
@@ -178,12 +179,19 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
     dsplat = torch.zeros((n, _capi.LGR_GRAD_FLOATS), **f32)
     if state.num_owners > 0:
         m_rows = sum(state.band_counts_host)
+        if peer_stage is not None:      # fused exchange: rows are stored straight into the owners' staging buffers
+            _capi.check(lib.lgr_backward(ctypes.byref(state.view), m_rows, state.num_instances, _ptr(means3D), _ptr(opacities),
+                                         _ptr(scales), _ptr(rotations), _ptr(colors_precomp), None, _ptr(state.splat),
+                                         _ptr(state.radii), None, _ptr(state.tile_start), _ptr(state.sorted_ids),
+                                         _ptr(state.image), _ptr(g), _ptr(dsplat), None, None, None, None, None, None, None,
+                                         None, ctypes.c_void_p(peer_stage.data_ptr()), int(my_rank), _stream()), 'lgr_backward')
+            return None
         rows = torch.empty((m_rows, _capi.LGR_ROW_FLOATS), **f32)
         _capi.check(lib.lgr_backward(ctypes.byref(state.view), m_rows, state.num_instances, _ptr(means3D), _ptr(opacities),
                                      _ptr(scales), _ptr(rotations), _ptr(colors_precomp), None, _ptr(state.splat),
                                      _ptr(state.radii), None, _ptr(state.tile_start), _ptr(state.sorted_ids),
                                      _ptr(state.image), _ptr(g), _ptr(dsplat), None, None, None, None, None, None, None,
-                                     ctypes.c_void_p(rows.data_ptr()) if rows.numel() else _ptr(dsplat), _stream()),
+                                     ctypes.c_void_p(rows.data_ptr()) if rows.numel() else _ptr(dsplat), None, 0, _stream()),
                     'lgr_backward')
         return rows
     dmeans3D = torch.empty((n, 3), **f32)
@@ -198,7 +206,7 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
                                  _ptr(state.radii), _ptr(state.clamped), _ptr(state.tile_start), _ptr(state.sorted_ids),
                                  _ptr(state.image), _ptr(g), _ptr(dsplat), _ptr(dmeans3D),
                                  _ptr(dmeans2D), _ptr(dopac), _ptr(dscales), _ptr(drot), _ptr(dcolors), _ptr(dshs), None,
-                                 _stream()), 'lgr_backward')
+                                 None, 0, _stream()), 'lgr_backward')
     return dmeans3D, dmeans2D, dopac, dscales, drot, dcolors, dshs
 
 

@@ -96,3 +96,43 @@ def reduce_to_owners(packed: torch.Tensor, group=None) -> torch.Tensor:
     full = packed.clone()
     dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
     return full[rank * chunk:(rank + 1) * chunk].clone()
+
+
+class PeerExchange:
+    """Fused gradient exchange over NVLink peer memory (torch symmetric memory): the per-Gaussian backward kernel stores
+    each packed gradient row directly into its owner rank's staging buffer, a device-side barrier follows, and the
+    owner adds what it received into its dense shard.  No NCCL call and no host synchronisation on the data path."""
+
+    def __init__(self, num_gaussians: int, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _capi
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n = int(num_gaussians)
+        self.chunk = owner_chunk(self.n, self.world)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        floats = _capi.LGR_STAGE_HEADER_FLOATS + self.world * self.chunk * _capi.LGR_ROW_FLOATS
+        self.stage = symm.empty(floats, dtype=torch.float32, device=dev)
+        self.stage[:_capi.LGR_STAGE_HEADER_FLOATS].zero_()
+        self.handle = symm.rendezvous(self.stage, self.group)
+        self.peer_ptrs = torch.tensor(list(self.handle.buffer_ptrs), dtype=torch.int64, device=dev)
+        self.lo, self.hi = owner_partition(self.n, self.world)[self.rank]
+        self.handle.barrier()
+
+    def backward(self, state, grad_image, means3D, opacities, scales, rotations, colors_precomp) -> torch.Tensor:
+        """Blend backward + per-Gaussian backward with rows pushed to the owners; returns this rank's reduced shard
+        (owner_chunk, LGR_ROW_FLOATS): [:, :17] gradients in pack_grads order, [:, 18] the radius."""
+        import ctypes
+        from . import _capi
+        from .rasterizer import rasterize_backward
+        lib = _capi.load()
+        self.handle.barrier()           # every owner has consumed the previous step's rows
+        rasterize_backward(state, grad_image, means3D, opacities, scales, rotations, colors_precomp, None,
+                           peer_stage=self.peer_ptrs, my_rank=self.rank)
+        self.handle.barrier()           # all rows have landed
+        shard = torch.zeros((self.chunk, _capi.LGR_ROW_FLOATS), dtype=torch.float32, device=self.stage.device)
+        _capi.check(lib.lgr_grad_scatter_add_staged(ctypes.c_void_p(self.stage.data_ptr()), self.world, self.chunk, self.lo,
+                                                    self.hi, ctypes.c_void_p(shard.data_ptr()),
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                    'lgr_grad_scatter_add_staged')
+        return shard

@@ -43,12 +43,17 @@ def _worker(rank, world, port, q):
     img, radii, pid, pwp, pw, st = rasterize_forward(s, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None,
                                                      LGR_FILTER_MAX, True, band, num_owners=world)
     rows = rasterize_backward(st, G, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None)
-    shard = sharded.exchange_rows_to_owners(rows, st.band_counts_host, N)
+    shard = sharded.exchange_rows_to_owners(rows, st.band_counts_host, N)          # NCCL all-to-all route
+    px = sharded.PeerExchange(N)                                                    # fused NVLink push route
+    for _ in range(2):                                                              # twice: staging buffers are reused
+        shard2 = px.backward(st, G, t['means3D'], op, t['scales'], t['rotations'], t['colors'])
     dist.all_reduce(img)                                   # bands are disjoint: the sum is the full image
     shards = [torch.zeros_like(shard) for _ in range(world)]
     dist.all_gather(shards, shard)
+    shards2 = [torch.zeros_like(shard2) for _ in range(world)]
+    dist.all_gather(shards2, shard2)
     if rank == 0:
-        q.put((img.cpu().numpy(), torch.cat(shards)[:N, :17].cpu().numpy()))
+        q.put((img.cpu().numpy(), torch.cat(shards)[:N, :19].cpu().numpy(), torch.cat(shards2)[:N, :19].cpu().numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,7 +68,8 @@ def test_two_rank_band_rendering_matches_single_gpu(built):
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in procs]
-    img, grads = q.get(timeout=600)
+    img, grads_full, grads2_full = q.get(timeout=600)
+    grads, grads2 = grads_full[:, :17], grads2_full[:, :17]
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     cam = O.make_camera(W, H, bg=(0.1, 0.2, 0.3), dtype=torch.float32)
@@ -74,3 +80,7 @@ def test_two_rank_band_rendering_matches_single_gpu(built):
                                 full['dcolors'])).cpu().numpy()
     np.testing.assert_array_equal(img, full['image'].detach().cpu().numpy())
     assert np.linalg.norm(grads - dense) / np.linalg.norm(dense) < 2e-5
+    assert np.linalg.norm(grads2 - dense) / np.linalg.norm(dense) < 2e-5
+    radii = full['radii'].cpu().numpy()
+    np.testing.assert_array_equal(grads_full[:, 18].astype(np.int32), radii)
+    np.testing.assert_array_equal(grads2_full[:, 18].astype(np.int32), radii)
