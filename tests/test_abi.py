@@ -54,3 +54,20 @@ def test_view_struct_layout_matches_header():
         names = decl.split(None, 1)[1] if not decl.startswith('const') else decl.split('*', 1)[1]
         fields += [n.strip(' *') for n in names.split(',')]
     assert fields == [f[0] for f in LgrView._fields_]
+
+
+def test_ctypes_arity_matches_header(built):
+    """Every binding in log_b200/_capi.py declares exactly as many arguments as the C prototype in the header."""
+    from log_b200 import _capi
+    lib = _capi.load()
+    src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    protos = dict(re.findall(r'\b(lgr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S))
+    checked = 0
+    for name, params in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue
+        n_params = 0 if params.strip() in ('', 'void') else params.count(',') + 1
+        assert len(fn.argtypes) == n_params, (name, len(fn.argtypes), n_params)
+        checked += 1
+    assert checked >= 6

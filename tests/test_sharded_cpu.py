@@ -66,7 +66,7 @@ def test_reduce_to_owners_gloo_world2(n):
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
     [p.start() for p in procs]
-    got = q.get(timeout=120)
+    got = q.get(timeout=90)
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     want = sum(torch.randn(n, sharded.GRAD_FLOATS_PRECOMP, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
