@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 6
+#define LGR_ABI_VERSION 7
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -118,7 +118,7 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  const float* image_d, const float* dL_dimage_d, float* dsplat_d,
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
                  float* dcolors_d, float* dshs_d, float* grad_rows_d, void* const* peer_stage_d, int32_t my_rank,
-                 void* stream);
+                 int64_t num_rows, void* stream);
 
 /* Band mode only (view->num_owners > 0, precomputed colours): when grad_rows_d != NULL lgr_backward writes, instead of
  * the dense d*_d outputs (which may then be NULL), one packed row of LGR_ROW_FLOATS floats per listed Gaussian, rows

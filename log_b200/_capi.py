@@ -12,7 +12,7 @@ LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
 LGR_TILE_SCRATCH_INTS = 33
-LGR_ABI_VERSION = 6
+LGR_ABI_VERSION = 7
 LGR_STAGE_HEADER_FLOATS = 64
 LGR_ROW_FLOATS = 20
 
@@ -56,7 +56,7 @@ def load():
     lib.lgr_forward_render.restype = ctypes.c_int
     lib.lgr_forward_render.argtypes = [ctypes.POINTER(LgrView), _i64, _i64, _i32, _i32] + [_vp] * 15
     lib.lgr_backward.restype = ctypes.c_int
-    lib.lgr_backward.argtypes = [ctypes.POINTER(LgrView), _i64, _i64] + [_vp] * 23 + [_i32, _vp]
+    lib.lgr_backward.argtypes = [ctypes.POINTER(LgrView), _i64, _i64] + [_vp] * 23 + [_i32, _i64, _vp]
     lib.lgr_grad_scatter_add_staged.restype = ctypes.c_int
     lib.lgr_grad_scatter_add_staged.argtypes = [_vp, _i32, _i64, _i64, _i64, _vp, _vp]
     lib.lgr_grad_scatter_add.restype = ctypes.c_int

@@ -110,16 +110,17 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  const float* image_d, const float* dL_dimage_d, float* dsplat_d,
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
                  float* dcolors_d, float* dshs_d, float* grad_rows_d, void* const* peer_stage_d, int32_t my_rank,
-                 void* stream) {
+                 int64_t num_rows, void* stream) {
   (void)opacities_d;
   if (!view_ok(view) || n < 0 || !tile_start_d || !image_d || !dL_dimage_d) return LGR_E_BADARG;
-  if (n == 0 && !peer_stage_d) return 0;
+  if (n == 0) return 0;
   const bool use_sh = shs_d != nullptr;
   if (use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
   if (!means3D_d || !scales_d || !rotations_d || !splat_d || !radii_d || !dsplat_d) return LGR_E_BADARG;
   if (grad_rows_d || peer_stage_d) {
     if (view->num_owners <= 0 || use_sh) return LGR_E_BADARG;
     if (peer_stage_d && (my_rank < 0 || my_rank >= view->num_owners)) return LGR_E_BADARG;
+    if (num_rows < 0 || num_rows > n) return LGR_E_BADARG;
   } else {
     if (view->num_owners > 0) return LGR_E_BADARG;   // band mode writes no splat records outside the band: rows only
     if (!dmeans3D_d || !dmeans2D_d || !dopacities_d || !dscales_d || !drotations_d) return LGR_E_BADARG;
@@ -127,11 +128,12 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   }
   if (num_instances > 0 && !sorted_ids_d) return LGR_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const View v = make_view(view, n);      // band mode: n = number of listed rows; the chunk fields are unused downstream
+  const View v = make_view(view, n);
   int rc = 0;
   if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, dL_dimage_d, dsplat_d, st);
   if (rc) return rc;
-  return launch_project_bwd(v, n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
+  const bool rows_mode = grad_rows_d || peer_stage_d;
+  return launch_project_bwd(v, rows_mode ? num_rows : n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
                             dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, grad_rows_d, peer_stage_d, my_rank, st);
 }
 

@@ -180,18 +180,18 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
     if state.num_owners > 0:
         m_rows = sum(state.band_counts_host)
         if peer_stage is not None:      # fused exchange: rows are stored straight into the owners' staging buffers
-            _capi.check(lib.lgr_backward(ctypes.byref(state.view), m_rows, state.num_instances, _ptr(means3D), _ptr(opacities),
+            _capi.check(lib.lgr_backward(ctypes.byref(state.view), n, state.num_instances, _ptr(means3D), _ptr(opacities),
                                          _ptr(scales), _ptr(rotations), _ptr(colors_precomp), None, _ptr(state.splat),
                                          _ptr(state.radii), None, _ptr(state.tile_start), _ptr(state.sorted_ids),
                                          _ptr(state.image), _ptr(g), _ptr(dsplat), None, None, None, None, None, None, None,
-                                         None, ctypes.c_void_p(peer_stage.data_ptr()), int(my_rank), _stream()), 'lgr_backward')
+                                         None, ctypes.c_void_p(peer_stage.data_ptr()), int(my_rank), m_rows, _stream()), 'lgr_backward')
             return None
         rows = torch.empty((m_rows, _capi.LGR_ROW_FLOATS), **f32)
-        _capi.check(lib.lgr_backward(ctypes.byref(state.view), m_rows, state.num_instances, _ptr(means3D), _ptr(opacities),
+        _capi.check(lib.lgr_backward(ctypes.byref(state.view), n, state.num_instances, _ptr(means3D), _ptr(opacities),
                                      _ptr(scales), _ptr(rotations), _ptr(colors_precomp), None, _ptr(state.splat),
                                      _ptr(state.radii), None, _ptr(state.tile_start), _ptr(state.sorted_ids),
                                      _ptr(state.image), _ptr(g), _ptr(dsplat), None, None, None, None, None, None, None,
-                                     ctypes.c_void_p(rows.data_ptr()) if rows.numel() else _ptr(dsplat), None, 0, _stream()),
+                                     ctypes.c_void_p(rows.data_ptr()) if rows.numel() else _ptr(dsplat), None, 0, m_rows, _stream()),
                     'lgr_backward')
         return rows
     dmeans3D = torch.empty((n, 3), **f32)
@@ -206,7 +206,7 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
                                  _ptr(state.radii), _ptr(state.clamped), _ptr(state.tile_start), _ptr(state.sorted_ids),
                                  _ptr(state.image), _ptr(g), _ptr(dsplat), _ptr(dmeans3D),
                                  _ptr(dmeans2D), _ptr(dopac), _ptr(dscales), _ptr(drot), _ptr(dcolors), _ptr(dshs), None,
-                                 None, 0, _stream()), 'lgr_backward')
+                                 None, 0, 0, _stream()), 'lgr_backward')
     return dmeans3D, dmeans2D, dopac, dscales, drot, dcolors, dshs
 
 
