@@ -240,15 +240,16 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
-  if (i >= n) return;
+  const bool active = i < n;
+  if (!ROWS && !active) return;
   int64_t row = 0;
-  if (ROWS) {      // band mode: slot i of the owner-grouped id lists -> Gaussian id, packed output row
-    row = i;                                  // thread = packed row; band_rows[row] = Gaussian id (written by the scatter)
+  if (ROWS && active) {      // band mode: thread = packed row; band_rows[row] = Gaussian id (written by the scatter)
+    row = i;
     i = v.band_rows[row];
   }
   float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dop = 0.f, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
   float drgb[3] = {0.f, 0.f, 0.f};
-  const bool live = radii[i] > 0;
+  const bool live = active && radii[i] > 0;
   const int K = v.sh_K;
   if (live) {
     const float4 g0 = ldg4(dsplat + i * LGR_GRAD_FLOATS);       // d/dpx d/dpy d/dconx d/dcony
@@ -385,22 +386,37 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     for (int k = 0; k < K * 3; k++) dsh[k] = 0.f;
   }
   if (ROWS) {
-    float4* dst;
-    if (peer_stage) {      // fused exchange: the row goes straight into its owner's staging buffer over NVLink
-      int o = 0;
-      int64_t first = 0;
-      while (o + 1 < v.num_owners && row >= first + v.band_count[o]) { first += v.band_count[o]; o++; }
-      float* base = reinterpret_cast<float*>(peer_stage[o]);
-      dst = reinterpret_cast<float4*>(base + LGR_STAGE_HEADER_FLOATS +
-                                      ((int64_t)my_rank * v.owner_chunk + (row - first)) * LGR_ROW_FLOATS);
-    } else {
-      dst = reinterpret_cast<float4*>(grad_rows + row * LGR_ROW_FLOATS);
+    // Rows are staged in shared memory and written out by the whole CTA as contiguous 16-byte-per-lane runs: the rows of
+    // a CTA are consecutive in their owner's buffer, and NVLink peer stores want full 128-byte packets, not 16-byte
+    // pieces at an 80-byte stride.
+    __shared__ float4 s_rows[PROJ_THREADS * (LGR_ROW_FLOATS / 4)];
+    __shared__ float4* s_dst[PROJ_THREADS];
+    if (active) {
+      float4* dst;
+      if (peer_stage) {      // fused exchange: the row goes straight into its owner's staging buffer over NVLink
+        int o = 0;
+        int64_t first = 0;
+        while (o + 1 < v.num_owners && row >= first + v.band_count[o]) { first += v.band_count[o]; o++; }
+        dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(peer_stage[o]) + LGR_STAGE_HEADER_FLOATS +
+                                        ((int64_t)my_rank * v.owner_chunk + (row - first)) * LGR_ROW_FLOATS);
+      } else {
+        dst = reinterpret_cast<float4*>(grad_rows + row * LGR_ROW_FLOATS);
+      }
+      float4* sr = s_rows + threadIdx.x * 5;
+      sr[0] = make_float4(dm[0], dm[1], dm[2], dm2[0]);
+      sr[1] = make_float4(dm2[1], 0.f, dop, dsc[0]);
+      sr[2] = make_float4(dsc[1], dsc[2], dq[0], dq[1]);
+      sr[3] = make_float4(dq[2], dq[3], drgb[0], drgb[1]);
+      sr[4] = make_float4(drgb[2], __int_as_float((int)i), (float)radii[i], 0.f);
+      s_dst[threadIdx.x] = dst;
     }
-    dst[0] = make_float4(dm[0], dm[1], dm[2], dm2[0]);
-    dst[1] = make_float4(dm2[1], 0.f, dop, dsc[0]);
-    dst[2] = make_float4(dsc[1], dsc[2], dq[0], dq[1]);
-    dst[3] = make_float4(dq[2], dq[3], drgb[0], drgb[1]);
-    dst[4] = make_float4(drgb[2], __int_as_float((int)i), (float)radii[i], 0.f);
+    __syncthreads();
+    const int64_t left = n - (int64_t)blockIdx.x * PROJ_THREADS;
+    const int cnt = left < PROJ_THREADS ? (int)left : PROJ_THREADS;
+    for (int idx = threadIdx.x; idx < cnt * 5; idx += PROJ_THREADS) {
+      const int r = idx / 5;
+      s_dst[r][idx - 5 * r] = s_rows[idx];
+    }
     return;
   }
   dmeans[3 * i] = dm[0]; dmeans[3 * i + 1] = dm[1]; dmeans[3 * i + 2] = dm[2];
