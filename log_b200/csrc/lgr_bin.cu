@@ -87,6 +87,27 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
   int x0, y0, x1, y1;
   tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
   const uint32_t key = __float_as_uint(depth);   // depth > 0.2 : IEEE bits are order preserving
+  const int w = x1 - x0, cnt = w * (y1 - y0);
+  if (cnt <= 4) {
+    // the common case (small splats): all slot requests are issued before any dependent store, so the returning
+    // atomics overlap instead of forming a serial chain of L2 round trips
+    int t[4], slot[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int ty = y0 + k / max(w, 1), tx = x0 + k % max(w, 1);
+      t[k] = k < cnt ? (ty - v.row0) * v.gx + tx : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) slot[k] = t[k] >= 0 ? atomicAdd(cursor + t[k] * CSTRIDE, 1) : 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (t[k] >= 0) {
+        const int pos = __ldg(tile_start + t[k]) + slot[k];
+        inst_key[pos] = key;
+        inst_val[pos] = (uint32_t)i;
+      }
+    return;
+  }
   for (int ty = y0; ty < y1; ty++)
     for (int tx = x0; tx < x1; tx++) {
       const int t = (ty - v.row0) * v.gx + tx;

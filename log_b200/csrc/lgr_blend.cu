@@ -53,6 +53,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float eval_alpha(float opacity, float G) { return fminf(ALPHA_MAX, __fmul_rn(opacity, G)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+// keep a shared-window address in a register (the compiler otherwise rebuilds it from SR_CgaCtaId inside hot loops)
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
 __device__ __forceinline__ void red_shared_max_u32(uint32_t addr, unsigned v) {
   asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -187,7 +202,8 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   const float pxf = (float)st.x, pyf = (float)st.y;
   const int beg = tile_start[tile], len = tile_start[tile + 1] - beg;
   float* xg = s_x + warp * 64;
-  const uint32_t s_g_addr = smem_u32(s_g);
+  const uint32_t s_g_lane = pin_reg(smem_u32(s_g) + 4u * (uint32_t)lane);   // this lane's column of the accumulators
+  const uint32_t s_rec_addr = pin_reg(smem_u32(s_rec));
   const float tcx = (float)((tile % v.gx) * TILE) + 7.5f, tcy = (float)((v.row0 + tile / v.gx) * TILE) + 7.5f;
 
   float I0 = 0.f, I1 = 0.f, I2 = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
@@ -244,9 +260,9 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
           const int e = c0 + j;
-          const float4* rec = s_rec + 3 * e;
-          const float4 r0 = rec[0];
-          const float2 r1 = *reinterpret_cast<const float2*>(rec + 1);    // (conic_z, opacity)
+          const uint32_t rec = s_rec_addr + 48u * (uint32_t)e;
+          const float4 r0 = lds_f4(rec);
+          const float2 r1 = lds_f2(rec + 16u);                            // (conic_z, opacity)
           const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
           const float power = eval_power2(r0, r1.x, dx, dy);
           const float G = ex2_approx(power);
@@ -260,7 +276,7 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           if (!__any_sync(FULL, contrib)) continue;
           float wG = 0.f, w = 0.f;
           if (contrib) {
-            const float4 r2 = rec[2];
+            const float4 r2 = lds_f4(rec + 32u);
             w = alpha * T;
             const float cdot = r2.x * dp0 + r2.y * dp1 + r2.z * dp2;
             // colour behind j (+ bg T_final):  S = I - P - c w
@@ -278,7 +294,7 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           sum = fmaf(wt[4], a1.x, sum); sum = fmaf(wt[5], a1.y, sum); sum = fmaf(wt[6], a1.z, sum); sum = fmaf(wt[7], a1.w, sum);
           sum = fmaf(wt[8], a2.x, sum); sum = fmaf(wt[9], a2.y, sum); sum = fmaf(wt[10], a2.z, sum); sum = fmaf(wt[11], a2.w, sum);
           sum += __shfl_down_sync(FULL, sum, 9) + __shfl_down_sync(FULL, sum, 18);
-          if (lane < 9) red_shared_add_f32(s_g_addr + 4u * (e * 9 + lane), sum);
+          if (lane < 9) red_shared_add_f32(s_g_lane + 36u * (uint32_t)e, sum);
           __syncwarp();
         }
         if (__all_sync(FULL, done)) break;
