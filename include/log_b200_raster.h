@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 7
+#define LGR_ABI_VERSION 8
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -59,6 +59,8 @@ typedef struct lgr_view {
   int32_t* band_blk_d;   /* (2 B + 1) int32 */
   int32_t* band_count_d; /* (num_owners) int32 */
   int32_t* band_rows_d;  /* (N) int32: dense packed-row -> id map, written by lgr_forward_render */
+  float* band_dsplat_d;  /* (N,12) or NULL: the backward's dsplat_d; lgr_forward_render zeroes the rows of listed
+                            Gaussians so that the caller need not zero-fill all N rows */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */

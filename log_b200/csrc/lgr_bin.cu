@@ -76,6 +76,10 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
     if (sl >= v.band_blk[b]) return;
     const int id = v.band_ids[i];
     v.band_rows[v.band_blk[v.band_blocks + b] + sl] = id;      // dense packed-row -> id map for the backward
+    if (v.band_dsplat) {                                       // the sweep's accumulators: zero only the listed rows
+      float4* z = reinterpret_cast<float4*>(v.band_dsplat + (int64_t)id * LGR_GRAD_FLOATS);
+      z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     i = id;
   }
   const int rad = radii[i];

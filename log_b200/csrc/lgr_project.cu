@@ -60,9 +60,15 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
                    int32_t* __restrict__ radii, uint8_t* __restrict__ clamped, int32_t* __restrict__ tile_count,
                    int32_t* __restrict__ meta) {
   __shared__ float sV[16], sP[16], sCam[3];
-  __shared__ unsigned long long sStock[PROJ_THREADS / 32];
+  __shared__ float sWf;
+  __shared__ unsigned sStock[PROJ_THREADS / 32];
   __shared__ int sVis[PROJ_THREADS / 32];
   if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sP[threadIdx.x] = v.proj[threadIdx.x]; }
+  if (threadIdx.x == 32) {
+    float a = 0.f;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { const float w = v.view[r * 4 + c]; a += w * w; }
+    sWf = a;
+  }
   if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
@@ -84,18 +90,19 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     else if (fabsf(qn - 1.0f) < 1e-3f) {
       const float ty = p[0] * sV[1] + p[1] * sV[5] + p[2] * sV[9] + sV[13];
       const float tx = p[0] * sV[0] + p[1] * sV[4] + p[2] * sV[8] + sV[12];
-      const float itz = 1.0f / tz;
+      const float itz = __fdividef(1.0f, tz);
       const float lx = fminf(CLAMP_FOV * v.tanfovx, fabsf(tx * itz)), ly = fminf(CLAMP_FOV * v.tanfovy, fabsf(ty * itz));
-      // |T_x|^2 <= |W|_2^2 |J_x|^2 ; the view rotation's squared spectral norm is bounded by its Frobenius norm
-      const float wf = sV[0] * sV[0] + sV[1] * sV[1] + sV[2] * sV[2] + sV[4] * sV[4] + sV[5] * sV[5] + sV[6] * sV[6] +
-                       sV[8] * sV[8] + sV[9] * sV[9] + sV[10] * sV[10];
+      // |T|_2^2 <= |W|_F^2 |J|_F^2 ; sWf = squared Frobenius norm of the view rotation (3 for a rotation)
       const float jn = (v.fx * itz) * (v.fx * itz) * (1.0f + lx * lx) + (v.fy * itz) * (v.fy * itz) * (1.0f + ly * ly);
-      const float sm = fmaxf(fabsf(s[0]), fmaxf(fabsf(s[1]), fabsf(s[2]))) * v.scale_mod * 1.001f;
-      const float rb = 3.0f * sqrtf(wf * jn * sm * sm * 1.01f + 0.7f) + 2.0f;
+      const float sm = fmaxf(fabsf(s[0]), fmaxf(fabsf(s[1]), fabsf(s[2]))) * v.scale_mod;
+      const float rb2 = 9.0f * (sWf * jn * sm * sm * 1.03f + 0.7f);          // (3 sqrt(lambda_bound))^2, inflated
       const float hw = p[0] * sP[3] + p[1] * sP[7] + p[2] * sP[11] + sP[15];
       const float hy_ = p[0] * sP[1] + p[1] * sP[5] + p[2] * sP[9] + sP[13];
-      const float py = ((hy_ / (hw + 0.0000001f) + 1.0f) * v.H - 1.0f) * 0.5f;
-      if (py + rb + (TILE - 1) < (float)(v.row0 * TILE) - 1.0f || py - rb > (float)(v.row1 * TILE) + 1.0f) work = false;
+      const float py = (__fdividef(hy_, hw + 0.0000001f) * 1.00001f + 1.0f) * (0.5f * v.H) - 0.5f;
+      // distance from py to the band's pixel interval, minus the tile padding and a 3 px safety margin
+      const float lo = (float)(v.row0 * TILE) - (float)(TILE + 2), hi = (float)(v.row1 * TILE) + 3.0f;
+      const float dist = fmaxf(fmaxf(lo - py, py - hi), 0.0f);
+      if (dist * dist > rb2 * 1.02f + 4.0f * dist) work = false;           // dist > rb + 2  (conservatively)
     }
   }
   if (v.num_owners > 0) {
@@ -207,20 +214,18 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     __syncthreads();
   }
   // block statistics: D by the stock rule, number of visible Gaussians (one atomic pair per CTA)
-  int vis = rad_out > 0;
+  {
+    const unsigned st_w = __reduce_add_sync(0xffffffffu, (unsigned)stock_tiles);      // < 2^32 per warp
+    const int vis_w = __popc(__ballot_sync(0xffffffffu, rad_out > 0));
+    if ((threadIdx.x & 31) == 0) { sStock[threadIdx.x >> 5] = st_w; sVis[threadIdx.x >> 5] = vis_w; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long a = 0; int b = 0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    stock_tiles += __shfl_xor_sync(0xffffffffu, stock_tiles, o);
-    vis += __shfl_xor_sync(0xffffffffu, vis, o);
-  }
-  if ((threadIdx.x & 31) == 0) { sStock[threadIdx.x >> 5] = stock_tiles; sVis[threadIdx.x >> 5] = vis; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long a = 0; int b = 0;
-#pragma unroll
-    for (int w = 0; w < PROJ_THREADS / 32; w++) { a += sStock[w]; b += sVis[w]; }
-    if (a) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 2), a);
-    if (b) atomicAdd(meta + 4, b);
+      for (int w = 0; w < PROJ_THREADS / 32; w++) { a += sStock[w]; b += sVis[w]; }
+      if (a) atomicAdd(reinterpret_cast<unsigned long long*>(meta + 2), a);
+      if (b) atomicAdd(meta + 4, b);
+    }
   }
 }
 

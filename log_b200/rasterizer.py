@@ -70,7 +70,7 @@ def _stream():
 
 
 def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep,
-               num_owners=0, band_ids=None, band_count=None, band_blk=None, band_rows=None):
+               num_owners=0, band_ids=None, band_count=None, band_blk=None, band_rows=None, band_dsplat=None):
     dev = s.viewmatrix.device
     vm, pm = _f32c(s.viewmatrix, 'viewmatrix'), _f32c(s.projmatrix, 'projmatrix', dev)
     bg = _f32c(s.bg, 'bg', dev)
@@ -88,6 +88,7 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
     v.band_count_d = band_count.data_ptr() if band_count is not None else None
     v.band_blk_d = band_blk.data_ptr() if band_blk is not None else None
     v.band_rows_d = band_rows.data_ptr() if band_rows is not None else None
+    v.band_dsplat_d = band_dsplat.data_ptr() if band_dsplat is not None else None
     v.viewmatrix_d, v.projmatrix_d = vm.data_ptr(), pm.data_ptr()
     v.campos_d = cp.data_ptr() if cp is not None else None
     v.bg_d = bg.data_ptr()
@@ -111,14 +112,15 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     n = int(means3D.shape[0])
     keep = []
     K = 0 if shs is None else int(shs.shape[1])
-    band_ids = band_count = band_blk = band_rows = None
+    band_ids = band_count = band_blk = band_rows = band_dsplat = None
     if num_owners > 0:
         band_rows = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        band_dsplat = torch.empty((max(n, 1), _capi.LGR_GRAD_FLOATS), dtype=torch.float32, device=dev)
         nb = (n + 255) // 256
         band_ids = torch.empty((max(256 * nb, 1),), dtype=torch.int32, device=dev)
         band_blk = torch.empty((2 * nb + 1,), dtype=torch.int32, device=dev)
         band_count = torch.empty((num_owners,), dtype=torch.int32, device=dev)
-    view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep, num_owners, band_ids, band_count, band_blk, band_rows)
+    view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep, num_owners, band_ids, band_count, band_blk, band_rows, band_dsplat)
     H, W = view.image_height, view.image_width
     gx, gy = (W + 15) // 16, (H + 15) // 16
     rows = gy if tile_rows is None else int(tile_rows[1]) - int(tile_rows[0])
@@ -162,7 +164,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     s.stock_instances, s.num_visible = stock_D, int(m[4])
     s.splat, s.radii, s.clamped, s.tile_start, s.sorted_ids = splat, radii, clamped, tile_start, sorted_ids
     s.final_T, s.n_contrib, s.image, s.sh = final_T, n_contrib, image, shs is not None
-    s.num_owners, s.band_ids, s.band_count = num_owners, (band_ids, band_blk, band_rows), band_count
+    s.num_owners, s.band_ids, s.band_count = num_owners, (band_ids, band_blk, band_rows, band_dsplat), band_count
     s.band_counts_host = [int(x) for x in m[_capi.LGR_META_INTS:]] if num_owners > 0 else None
     return image, radii, pid, pwp, pw, s
 
@@ -176,7 +178,11 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
     n = state.n
     f32 = dict(dtype=torch.float32, device=dev)
     g = _f32c(grad_image, 'grad_image', dev)
-    dsplat = torch.zeros((n, _capi.LGR_GRAD_FLOATS), **f32)
+    if state.num_owners > 0 and state.band_ids[3] is not None:
+        dsplat = state.band_ids[3]          # rows of listed Gaussians were zeroed by the forward's scatter kernel
+        state.band_ids = state.band_ids[:3] + (None,)      # one backward per forward
+    else:
+        dsplat = torch.zeros((n, _capi.LGR_GRAD_FLOATS), **f32)
     if state.num_owners > 0:
         m_rows = sum(state.band_counts_host)
         if peer_stage is not None:      # fused exchange: rows are stored straight into the owners' staging buffers
