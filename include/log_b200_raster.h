@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 8
+#define LGR_ABI_VERSION 9
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -100,12 +100,15 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
  *            max_tile_len exceeds the shared-memory sort capacity (lgr_sort_smem_capacity()), else may be NULL
  *   out: sorted_ids_d (num_instances) int32 (kept for backward); image_d (3,H,W); final_T_d (H,W);
  *        n_contrib_d (H,W) int32; when view->want_aux: point_id_pixel_d (H,W) int32, point_weight_pixel_d (H,W),
- *        point_weight_d (N) -- must be zero-filled by the caller. */
+ *        point_weight_d (N) -- must be zero-filled by the caller;
+ *        point_count_d (N) int32 or NULL -- zero-filled by the caller; receives, per Gaussian, the number of pixels whose
+ *        point_id_pixel is that Gaussian (the histogram LoG builds with torch.unique, renderer.py:156-159). */
 int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, int32_t max_tile_len,
                        int32_t num_long_tiles, const float* splat_d, const int32_t* radii_d, const int32_t* tile_start_d,
                        int32_t* tile_cursor_d, uint32_t* inst_key_d, uint32_t* inst_val_d, uint32_t* inst_tmp_d,
                        int32_t* sorted_ids_d, float* image_d, float* final_T_d, int32_t* n_contrib_d,
-                       int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d, void* stream);
+                       int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d,
+                       int32_t* point_count_d, void* stream);
 int32_t lgr_sort_smem_capacity(void);
 
 /* Backward: per-tile gradient sweep (front to back, re-using the rendered image_d of the forward for the colour
@@ -140,6 +143,13 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
 int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream);
 int lgr_grad_scatter_add_staged(const float* stage_d, int32_t num_sources, int64_t owner_chunk, int64_t lo, int64_t hi,
                                 float* shard_d, void* stream);
+
+/* Sorted compaction of the non-zero entries of point_count_d: ids_out_d / counts_out_d (capacity min(N, H*W)) receive the
+ * ids in ascending order and their pixel counts, *num_out_d their number.  Equals
+ * torch.unique(point_id_pixel, sorted=True, return_counts=True) with the -1 entry dropped (renderer.py:156-159).
+ * scratch_d: 2*ceil(N/1024)+1 int32. */
+int lgr_point_compact(int64_t n, const int32_t* point_count_d, int32_t* scratch_d, int32_t* ids_out_d,
+                      int32_t* counts_out_d, int32_t* num_out_d, void* stream);
 
 /* Diagnostics (not on the data path): per-kernel CUDA-event timing on the launching stream.
  * lgr_profile_enable(1) starts recording; lgr_profile_collect() synchronises the recorded events, writes the summed

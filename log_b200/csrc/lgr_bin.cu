@@ -369,6 +369,85 @@ tile_sort_kernel(const int32_t* __restrict__ tile_list /* nullptr: tile = blockI
 
 int sort_smem_capacity() { return SORT_CAP_LARGE; }
 
+// ---------------------------------------------------------------------------------------------------------
+// point_id / point_count: sorted compaction of the non-zero entries of the per-Gaussian winner histogram
+// (replaces torch.unique(point_id_pixel, sorted=True, return_counts=True) of LoG/render/renderer.py:156-159)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PC_THREADS = 1024;
+
+__global__ void __launch_bounds__(PC_THREADS)
+pc_block_count_kernel(int64_t n, const int32_t* __restrict__ count, int32_t* __restrict__ blk) {
+  const int64_t i = (int64_t)blockIdx.x * PC_THREADS + threadIdx.x;
+  const int c = __syncthreads_count(i < n && count[i] > 0);
+  if (threadIdx.x == 0) blk[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024)
+pc_scan_kernel(int nb, int32_t* __restrict__ blk /* [0,nb) counts -> [nb, 2nb] exclusive prefix */, int32_t* __restrict__ num_out) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int b = base + tid;
+    const int c = b < nb ? blk[b] : 0;
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (b < nb) blk[nb + b] = carry + (wid ? warp_sum[wid - 1] : 0) + x - c;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sum[31];
+    __syncthreads();
+  }
+  if (tid == 0) { blk[2 * nb] = carry_s; *num_out = carry_s; }
+}
+
+__global__ void __launch_bounds__(PC_THREADS)
+pc_compact_kernel(int64_t n, const int32_t* __restrict__ count, const int32_t* __restrict__ blk, int nb,
+                  int32_t* __restrict__ ids_out, int32_t* __restrict__ counts_out) {
+  __shared__ int wsum[PC_THREADS / 32];
+  const int64_t i = (int64_t)blockIdx.x * PC_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = i < n ? count[i] : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, c > 0);
+  if (lane == 0) wsum[wid] = __popc(bal);
+  __syncthreads();
+  int base = blk[nb + blockIdx.x];
+  for (int w = 0; w < wid; w++) base += wsum[w];
+  if (c > 0) {
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    ids_out[pos] = (int32_t)i;
+    counts_out[pos] = c;
+  }
+}
+
+int launch_point_compact(int64_t n, const int32_t* count, int32_t* blk, int32_t* ids_out, int32_t* counts_out, int32_t* num_out,
+                         cudaStream_t st) {
+  const int nb = (int)((n + PC_THREADS - 1) / PC_THREADS);
+  if (nb == 0) {
+    cudaError_t e = cudaMemsetAsync(num_out, 0, sizeof(int32_t), st);
+    return e == cudaSuccess ? 0 : (int)e;
+  }
+  pc_block_count_kernel<<<nb, PC_THREADS, 0, st>>>(n, count, blk);
+  LGR_CHECK_LAUNCH();
+  pc_scan_kernel<<<1, 1024, 0, st>>>(nb, blk, num_out);
+  LGR_CHECK_LAUNCH();
+  pc_compact_kernel<<<nb, PC_THREADS, 0, st>>>(n, count, blk, nb, ids_out, counts_out);
+  LGR_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_tile_scan(int ntiles, int32_t* tile_start, int32_t* cursor, int32_t* meta, cudaStream_t st) {
   ProfScope ps(K_TILE_SCAN, st);
   tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(ntiles, tile_start, cursor, meta, SORT_CAP_SMALL_FWD);

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(BLEND_THREADS)
 blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
                  const float* __restrict__ splat, float* __restrict__ image, float* __restrict__ final_T,
                  int32_t* __restrict__ n_contrib, int32_t* __restrict__ pid_pixel, float* __restrict__ pw_pixel,
-                 unsigned* __restrict__ point_weight_bits) {
+                 unsigned* __restrict__ point_weight_bits, int32_t* __restrict__ point_count) {
   __shared__ float4 s_rec[BATCH * 3];
   __shared__ unsigned s_w[AUX ? BATCH : 1];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -168,7 +168,10 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
     image[2 * HW + pix] = C2 + T * __ldg(v.bg + 2);
     final_T[pix] = T;
     n_contrib[pix] = last;
-    if (AUX) { pid_pixel[pix] = wid; pw_pixel[pix] = wmax; }
+    if (AUX) {
+      pid_pixel[pix] = wid; pw_pixel[pix] = wmax;
+      if (point_count && wid >= 0) atomicAdd(point_count + wid, 1);      // histogram of the per-pixel winners
+    }
   }
 }
 
@@ -335,14 +338,14 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
 // ---------------------------------------------------------------------------------------------------------
 int launch_blend_fwd(const View& v, const int32_t* tile_start, const int32_t* sorted_ids, const float* splat,
                      float* image, float* final_T, int32_t* n_contrib, int32_t* pid_pixel, float* pw_pixel,
-                     float* point_weight, cudaStream_t st) {
+                     float* point_weight, int32_t* point_count, cudaStream_t st) {
   const int ntiles = v.gx * (v.row1 - v.row0);
   if (ntiles <= 0) return 0;
   ProfScope ps(K_BLEND_FWD, st);
   if (v.want_aux)
-    blend_fwd_kernel<true><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight));
+    blend_fwd_kernel<true><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight), point_count);
   else
-    blend_fwd_kernel<false><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight));
+    blend_fwd_kernel<false><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight), point_count);
   LGR_CHECK_LAUNCH();
   return 0;
 }

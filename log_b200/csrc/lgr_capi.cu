@@ -19,7 +19,8 @@ int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, c
                         uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
 int sort_smem_capacity();
 int launch_blend_fwd(const View&, const int32_t*, const int32_t*, const float*, float*, float*, int32_t*, int32_t*,
-                     float*, float*, cudaStream_t);
+                     float*, float*, int32_t*, cudaStream_t);
+int launch_point_compact(int64_t, const int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_blend_bwd(const View&, const int32_t*, const int32_t*, const float*, const float*, const float*, float*,
                      cudaStream_t);
 }  // namespace lgr
@@ -87,7 +88,8 @@ int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, i
                        int32_t num_long_tiles, const float* splat_d, const int32_t* radii_d, const int32_t* tile_start_d,
                        int32_t* tile_cursor_d, uint32_t* inst_key_d, uint32_t* inst_val_d, uint32_t* inst_tmp_d,
                        int32_t* sorted_ids_d, float* image_d, float* final_T_d, int32_t* n_contrib_d,
-                       int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d, void* stream) {
+                       int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d,
+                       int32_t* point_count_d, void* stream) {
   if (!view_ok(view) || n < 0 || num_instances < 0 || num_long_tiles < 0 || !tile_start_d || !tile_cursor_d || !image_d || !final_T_d ||
       !n_contrib_d)
     return LGR_E_BADARG;
@@ -100,7 +102,7 @@ int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, i
                                inst_key_d, inst_val_d, inst_tmp_d, sorted_ids_d, st);
   if (rc) return rc;
   return launch_blend_fwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, final_T_d, n_contrib_d, point_id_pixel_d,
-                          point_weight_pixel_d, point_weight_d, st);
+                          point_weight_pixel_d, point_weight_d, view->want_aux ? point_count_d : nullptr, st);
 }
 
 int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const float* means3D_d,
@@ -135,6 +137,12 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   const bool rows_mode = grad_rows_d || peer_stage_d;
   return launch_project_bwd(v, rows_mode ? num_rows : n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
                             dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, grad_rows_d, peer_stage_d, my_rank, st);
+}
+
+int lgr_point_compact(int64_t n, const int32_t* point_count_d, int32_t* scratch_d, int32_t* ids_out_d,
+                      int32_t* counts_out_d, int32_t* num_out_d, void* stream) {
+  if (n < 0 || !num_out_d || (n > 0 && (!point_count_d || !scratch_d || !ids_out_d || !counts_out_d))) return LGR_E_BADARG;
+  return launch_point_compact(n, point_count_d, scratch_d, ids_out_d, counts_out_d, num_out_d, (cudaStream_t)stream);
 }
 
 int lgr_grad_scatter_add_staged(const float* stage_d, int32_t num_sources, int64_t owner_chunk, int64_t lo, int64_t hi,

@@ -99,7 +99,7 @@ class RasterState:
     """Buffers produced by the forward and consumed by the backward (kept alive by autograd)."""
     __slots__ = ('view', 'keep', 'n', 'num_instances', 'max_tile_len', 'stock_instances', 'num_visible', 'splat',
                  'radii', 'clamped', 'tile_start', 'sorted_ids', 'final_T', 'n_contrib', 'image', 'sh', 'num_owners',
-                 'band_ids', 'band_count', 'band_counts_host')
+                 'band_ids', 'band_count', 'band_counts_host', 'point_count')
 
 
 def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_precomp, shs, filter_mode, want_aux,
@@ -150,20 +150,22 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     image = torch.empty((3, H, W), **f32) if tile_rows is None else torch.zeros((3, H, W), **f32)
     final_T = torch.empty((H, W), **f32) if tile_rows is None else torch.ones((H, W), **f32)
     n_contrib = torch.empty((H, W), **i32) if tile_rows is None else torch.zeros((H, W), **i32)
-    pid = pwp = pw = None
+    pid = pwp = pw = pc = None
     if want_aux:
+        pc = torch.zeros((n,), **i32)
         pid = torch.empty((H, W), **i32) if tile_rows is None else torch.full((H, W), -1, **i32)
         pwp = torch.empty((H, W), **f32) if tile_rows is None else torch.zeros((H, W), **f32)
         pw = torch.zeros((n,), **f32)
     _capi.check(lib.lgr_forward_render(ctypes.byref(view), n, D, max_len, num_long, _ptr(splat), _ptr(radii), _ptr(tile_start),
                                        _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
                                        _ptr(sorted_ids), _ptr(image), _ptr(final_T), _ptr(n_contrib), _ptr(pid),
-                                       _ptr(pwp), _ptr(pw), st), 'lgr_forward_render')
+                                       _ptr(pwp), _ptr(pw), _ptr(pc), st), 'lgr_forward_render')
     s = RasterState()
     s.view, s.keep, s.n, s.num_instances, s.max_tile_len = view, keep, n, D, max_len
     s.stock_instances, s.num_visible = stock_D, int(m[4])
     s.splat, s.radii, s.clamped, s.tile_start, s.sorted_ids = splat, radii, clamped, tile_start, sorted_ids
     s.final_T, s.n_contrib, s.image, s.sh = final_T, n_contrib, image, shs is not None
+    s.point_count = pc
     s.num_owners, s.band_ids, s.band_count = num_owners, (band_ids, band_blk, band_rows, band_dsplat), band_count
     s.band_counts_host = [int(x) for x in m[_capi.LGR_META_INTS:]] if num_owners > 0 else None
     return image, radii, pid, pwp, pw, s
@@ -216,7 +218,27 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
     return dmeans3D, dmeans2D, dopac, dscales, drot, dcolors, dshs
 
 
+def point_id_count(point_count: torch.Tensor):
+    """(point_id, point_count) exactly as LoG builds them at renderer.py:156-159 with
+    ``torch.unique(point_id_pixel, sorted=True, return_counts=True)`` minus the -1 entry -- but from the per-Gaussian
+    winner histogram the blend kernel already produced (``rasterizer.last_point_count``): no sort over H x W."""
+    lib = _capi.load()
+    n = int(point_count.shape[0])
+    dev = point_count.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    scratch = torch.empty((2 * ((n + 1023) // 1024) + 1,), **i32)
+    ids = torch.empty((n,), **i32)
+    cnt = torch.empty((n,), **i32)
+    num = torch.empty((1,), **i32)
+    _capi.check(lib.lgr_point_compact(n, _ptr(point_count), _ptr(scratch), _ptr(ids), _ptr(cnt),
+                                      ctypes.c_void_p(num.data_ptr()), _stream()), 'lgr_point_compact')
+    k = int(num.item())
+    return ids[:k], cnt[:k]
+
+
 class _RasterizeGaussians(torch.autograd.Function):
+    last_point_count = None
+
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, colors_precomp, shs, scales, rotations, settings, filter_mode, want_aux,
                 tile_rows):
@@ -229,6 +251,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         sh = _f32c(shs, 'shs', dev)
         image, radii, pid, pwp, pw, state = rasterize_forward(settings, m, o, sc, r, c, sh, filter_mode, want_aux, tile_rows)
         state.image = None          # the backward re-reads the rendered image: saved below so autograd guards it
+        _RasterizeGaussians.last_point_count = state.point_count
         ctx.state = state
         ctx.opacity_shape = opacities.shape
         ctx.save_for_backward(m, o, sc, r, c if c is not None else torch.empty(0, device=dev),
@@ -285,8 +308,11 @@ class GaussianRasterizer(nn.Module):
             filter_mode = LGR_FILTER_MAX if use_filter else LGR_FILTER_NONE
         else:
             filter_mode = LGR_FILTER_ADD
-        return _RasterizeGaussians.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
-                                         self.raster_settings, filter_mode, fork, self.tile_rows)
+        out = _RasterizeGaussians.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
+                                        self.raster_settings, filter_mode, fork, self.tile_rows)
+        # fork flavour: per-Gaussian histogram of the per-pixel winners (feeds point_id_count())
+        self.last_point_count = _RasterizeGaussians.last_point_count if fork else None
+        return out
 
 
 class StockGaussianRasterizer(GaussianRasterizer):

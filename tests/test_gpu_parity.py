@@ -304,3 +304,25 @@ def test_band_mode_rows_reproduce_dense_gradients(built, world):
     assert rel(got, dense) < 2e-5
     for a, b in zip(sharded.unpack_grads(got), sharded.unpack_grads(dense)):
         assert rel(a, b) < 5e-5
+
+
+@pytest.mark.parametrize('W,H,n,r', [(200, 120, 3000, 6.0), (64, 64, 0, 3.0), (333, 211, 20000, 2.0)])
+def test_point_id_count_equals_torch_unique(built, W, H, n, r):
+    """(point_id, point_count) from the blend kernel's winner histogram equals what LoG computes with
+    torch.unique over the H x W id map (renderer.py:156-159)."""
+    from log_b200 import GaussianRasterizer, point_id_count
+    from util import settings_from_camera
+    dev = torch.device('cuda:0')
+    cam = f32_camera(O.make_camera(W, H))
+    sc = O.make_scene(max(n, 1), W, H, r, seed=8, dtype=torch.float32)
+    t = {k: v[:n].to(dev) for k, v in sc.items()}
+    rast = GaussianRasterizer(settings_from_camera(cam, dev))
+    out = rast(means3D=t['means3D'], means2D=torch.zeros(n, 3, device=dev), shs=None, colors_precomp=t['colors'],
+               opacities=t['opacities'], scales=t['scales'], rotations=t['rotations'], cov3D_precomp=None)
+    pid_pixel = out[2]
+    want_id, want_cnt = torch.unique(pid_pixel, sorted=True, return_counts=True)
+    if want_id.numel() and want_id[0] == -1:
+        want_id, want_cnt = want_id[1:], want_cnt[1:]
+    got_id, got_cnt = point_id_count(rast.last_point_count)
+    assert torch.equal(got_id.long(), want_id.long()) and torch.equal(got_cnt.long(), want_cnt.long())
+    assert int(rast.last_point_count.sum()) == int((pid_pixel >= 0).sum())
