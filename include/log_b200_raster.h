@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 9
+#define LGR_ABI_VERSION 10
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -150,6 +150,16 @@ int lgr_grad_scatter_add_staged(const float* stage_d, int32_t num_sources, int64
  * scratch_d: 2*ceil(N/1024)+1 int32. */
 int lgr_point_compact(int64_t n, const int32_t* point_count_d, int32_t* scratch_d, int32_t* ids_out_d,
                       int32_t* counts_out_d, int32_t* num_out_d, void* stream);
+
+/* Fused sparse Adam step: replaces SparseOptimizer.step's gather / _single_tensor_adam / scatter
+ * (LoG/model/sparse_optimizer.py:41-78, 163-196) for one parameter.  For every k < rows and c < row_floats, with
+ * i = index_d[k]:   m = b1 m + (1-b1) g ;  v = b2 v + (1-b2) g^2 ;  [vmax = max(vmax, v)] ;
+ *                   param -= lr / (1 - b1^step) * m / (sqrt(v or vmax) / sqrt(1 - b2^step) + eps)
+ * in place on param_d / exp_avg_d / exp_avg_sq_d [/ max_exp_avg_sq_d, NULL = no amsgrad] (N, row_floats);
+ * grad_d is the compact (rows, row_floats) gradient of the gathered rows; index_d int64 (rows), unique. */
+int lgr_sparse_adam(int64_t rows, int32_t row_floats, const int64_t* index_d, const float* grad_d, float* param_d,
+                    float* exp_avg_d, float* exp_avg_sq_d, float* max_exp_avg_sq_d, int64_t step, double lr, double beta1,
+                    double beta2, double eps, void* stream);
 
 /* Diagnostics (not on the data path): per-kernel CUDA-event timing on the launching stream.
  * lgr_profile_enable(1) starts recording; lgr_profile_collect() synchronises the recorded events, writes the summed

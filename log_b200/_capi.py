@@ -12,12 +12,12 @@ LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
 LGR_TILE_SCRATCH_INTS = 33
-LGR_ABI_VERSION = 9
+LGR_ABI_VERSION = 10
 LGR_STAGE_HEADER_FLOATS = 64
 LGR_ROW_FLOATS = 20
 
 EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
-           'lgr_forward_render', 'lgr_backward', 'lgr_grad_scatter_add', 'lgr_grad_scatter_add_staged', 'lgr_point_compact', 'lgr_profile_enable', 'lgr_profile_collect',
+           'lgr_forward_render', 'lgr_backward', 'lgr_grad_scatter_add', 'lgr_grad_scatter_add_staged', 'lgr_point_compact', 'lgr_sparse_adam', 'lgr_profile_enable', 'lgr_profile_collect',
            'lgr_profile_kernel_name')
 LGR_PROFILE_KERNELS = 8
 
@@ -55,6 +55,9 @@ def load():
     lib.lgr_forward_project.argtypes = [ctypes.POINTER(LgrView), _i64] + [_vp] * 13
     lib.lgr_forward_render.restype = ctypes.c_int
     lib.lgr_forward_render.argtypes = [ctypes.POINTER(LgrView), _i64, _i64, _i32, _i32] + [_vp] * 16
+    lib.lgr_sparse_adam.restype = ctypes.c_int
+    lib.lgr_sparse_adam.argtypes = [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double,
+                                    ctypes.c_double, ctypes.c_double, _vp]
     lib.lgr_point_compact.restype = ctypes.c_int
     lib.lgr_point_compact.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.lgr_backward.restype = ctypes.c_int

@@ -2,6 +2,7 @@
 // caller's stream.  No allocation, no host synchronisation, no CPU fallback.
 #include "lgr_common.cuh"
 #include "lgr_prof.cuh"
+#include <math.h>
 
 namespace lgr {
 int launch_compute_radius(int64_t, const float*, const float*, const float*, const float*, const float*, float, float,
@@ -20,6 +21,8 @@ int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, c
 int sort_smem_capacity();
 int launch_blend_fwd(const View&, const int32_t*, const int32_t*, const float*, float*, float*, int32_t*, int32_t*,
                      float*, float*, int32_t*, cudaStream_t);
+int launch_sparse_adam(int64_t, int, const int64_t*, const float*, float*, float*, float*, float*, float, float, float, float,
+                       float, float, float, cudaStream_t);
 int launch_point_compact(int64_t, const int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_blend_bwd(const View&, const int32_t*, const int32_t*, const float*, const float*, const float*, float*,
                      cudaStream_t);
@@ -137,6 +140,19 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   const bool rows_mode = grad_rows_d || peer_stage_d;
   return launch_project_bwd(v, rows_mode ? num_rows : n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
                             dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, grad_rows_d, peer_stage_d, my_rank, st);
+}
+
+int lgr_sparse_adam(int64_t rows, int32_t row_floats, const int64_t* index_d, const float* grad_d, float* param_d,
+                    float* exp_avg_d, float* exp_avg_sq_d, float* max_exp_avg_sq_d, int64_t step, double lr, double beta1,
+                    double beta2, double eps, void* stream) {
+  if (rows < 0 || row_floats <= 0 || step < 1) return LGR_E_BADARG;
+  if (rows > 0 && (!index_d || !grad_d || !param_d || !exp_avg_d || !exp_avg_sq_d)) return LGR_E_BADARG;
+  // scalar preparation in double, exactly like the Python reference (sparse_optimizer.py:64-70)
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  const double step_size = lr / bc1;
+  return launch_sparse_adam(rows, row_floats, index_d, grad_d, param_d, exp_avg_d, exp_avg_sq_d, max_exp_avg_sq_d,
+                            (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)sqrt(bc2),
+                            (float)(-step_size), (float)eps, (cudaStream_t)stream);
 }
 
 int lgr_point_compact(int64_t n, const int32_t* point_count_d, int32_t* scratch_d, int32_t* ids_out_d,

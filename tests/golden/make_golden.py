@@ -81,8 +81,47 @@ def main():
         val = ref_sh.SH2RGB(torch.from_numpy(dc)) + ref_sh.eval_sh_wobase(torch.from_numpy(dirs), torch.from_numpy(rest[:, :K]), degree=deg)
         out[f'sh_rgb_deg{deg}'] = val.numpy()
     out['sh_rgb_deg0'] = ref_sh.SH2RGB(torch.from_numpy(dc)).numpy()
+    # sparse Adam (LoG/model/sparse_optimizer.py:41-78 _single_tensor_adam), float32 as LoG runs it
+    make_adam_golden()
     np.savez_compressed(os.path.join(HERE, 'reference_geometry_sh.npz'), **out)
     print('wrote', os.path.join(HERE, 'reference_geometry_sh.npz'), {k: v.shape for k, v in out.items() if 'cam0' in k or 'sh' in k})
+
+
+def make_adam_golden():
+    torch.set_default_dtype(torch.float32)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_sparse_optimizer', os.path.join(REF, 'LoG/model/sparse_optimizer.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(77)
+    N, K = 500, 180
+    out = {}
+    for name, C in (('xyz', 3), ('rotation', 4), ('opacity', 1)):
+        param = torch.randn(N, C, generator=g)
+        m = torch.randn(N, C, generator=g) * 0.01
+        v = torch.rand(N, C, generator=g) * 1e-4
+        vmax = v * (1 + torch.rand(N, C, generator=g))
+        index = torch.randperm(N, generator=g)[:K].sort().values
+        for step, lr, ams in ((1, 1.6e-4, False), (37, 5e-3, False), (1000, 1e-3, True)):
+            grad = torch.randn(K, C, generator=g) * (10.0 ** float(torch.randint(-4, 1, (1,), generator=g)))
+            p_in, m_in, v_in, vm_in = param.clone(), m.clone(), v.clone(), vmax.clone()
+            # what SparseOptimizer.step does around the call (sparse_optimizer.py:163-196): gather, update, scatter back
+            ps, ms, vs = p_in[index].clone(), m_in[index].clone(), v_in[index].clone()
+            vms = vm_in[index].clone() if ams else None
+            ps, ms, vs, vms = mod._single_tensor_adam(ps, grad, ms, vs, vms, step, lr, eps=1e-15)
+            p_out, m_out, v_out, vm_out = p_in.clone(), m_in.clone(), v_in.clone(), vm_in.clone()
+            p_out[index], m_out[index], v_out[index] = ps, ms, vs
+            if ams:
+                vm_out[index] = vms
+            key = f'adam_{name}_s{step}_'
+            for k_, t_ in (('param_in', p_in), ('m_in', m_in), ('v_in', v_in), ('vmax_in', vm_in), ('grad', grad),
+                           ('param_out', p_out), ('m_out', m_out), ('v_out', v_out), ('vmax_out', vm_out)):
+                out[key + k_] = t_.numpy()
+            out[key + 'index'] = index.numpy().astype(np.int64)
+            out[key + 'hyper'] = np.array([step, lr, 0.9, 0.999, 1e-15, float(ams)], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, 'reference_sparse_adam.npz'), **out)
+    print('wrote reference_sparse_adam.npz', len(out))
+    torch.set_default_dtype(torch.float64)
 
 
 if __name__ == '__main__':
