@@ -50,7 +50,7 @@ def test_kernel_matches_reference(built, prefix):
     close(p.cpu().numpy(), G[prefix + 'param_out'], np.abs(G[prefix + 'param_in']).max())
     close(m.cpu().numpy(), G[prefix + 'm_out'], max(np.abs(G[prefix + 'm_in']).max(), gmax))
     close(v.cpu().numpy(), G[prefix + 'v_out'], max(np.abs(G[prefix + 'v_in']).max(), gmax ** 2))
-    close(vm.cpu().numpy(), G[prefix + 'vmax_out' if ams else 'vmax_in'], max(np.abs(G[prefix + 'vmax_in']).max(), gmax ** 2))
+    close(vm.cpu().numpy(), G[prefix + ('vmax_out' if ams else 'vmax_in')], max(np.abs(G[prefix + 'vmax_in']).max(), gmax ** 2))
     # rows that were not listed are untouched
     mask = np.ones(p.shape[0], bool)
     mask[G[prefix + 'index']] = False
