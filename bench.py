@@ -96,6 +96,12 @@ def algorithmic_bytes(n, H, W, D, sh_degree):
     return k, b_min, b_min + 112 * D
 
 
+def workload_name(w):
+    n, W, H, r, deg = WORKLOADS[w]
+    return (f'{w}: {n} synthetic Gaussians (median sigma {r} px), {W}x{H}, sh_degree {deg}, forward+backward, '
+            'fork flavour (max(cov,0.3) filter, 5-tuple aux outputs)')
+
+
 def make_inputs(workload, dtype=torch.float32):
     from log_b200.synthetic import make_camera, make_cotangent, make_scene
     n, W, H, r, deg = WORKLOADS[workload]
@@ -132,7 +138,7 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': 'gaussians_per_s_fwd_bwd', 'value': val, 'unit': 'Gaussians/s', 'n_gpus': 0,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / dt / 1e6,
-        'config': {'workload': f'{args.workload}: {n} Gaussians, {W}x{H}, sh_degree {deg}', 'sample': sample},
+        'config': {'workload': workload_name(args.workload), 'sample': sample},
         'cpu_baseline': {'value': val, 'unit': 'Gaussians/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': 'Gaussians/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
@@ -349,7 +355,7 @@ def main():
         'metric': 'gaussians_per_s_fwd_bwd', 'value': n / (ms_step * 1e-3), 'unit': 'Gaussians/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / (ms_step * 1e-3) / 1e6,
-        'config': {'workload': f'{args.workload}: {n} Gaussians, {W}x{H}, sh_degree {deg}, fork flavour (5-tuple aux outputs)',
+        'config': {'workload': workload_name(args.workload),
                    'parallelism': (f'tile-row bands x{world}, gradient rows ' + ('pushed to owner ranks over NVLink peer memory (fused in the backward kernel)' if peer is not None else 'NCCL all-to-all to owner ranks')) if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
                    'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible']},
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
