@@ -1,10 +1,12 @@
 // Tile binning: exclusive scan of the per-tile counts, scatter of (depth, id) instances into per-tile bins,
-// and the per-tile stable LSD radix sort by (depth, id).
+// and the per-tile sort by (depth, id).
 //
 // Design (B200): instead of one global 64-bit key sort over all D instances (6+ passes x 24 B/instance through
 // HBM), instances are counting-sorted into tile bins (one 8-byte scattered write each) and every tile's list is
-// then radix-sorted entirely in shared memory by one CTA (one 8-byte read + one 4-byte write per instance).
-// Lists that do not fit the 227 KB of shared memory take the same code path over global scratch.
+// then sorted entirely in shared memory by one CTA (one 8-byte read + one 4-byte write per instance): an MSD bucket
+// partition on the highest differing bits of the unique (depth, id) composite, finished by rank counting inside the
+// buckets.  Lists that do not fit the 227 KB of shared memory take a stable LSD radix sort over global scratch.
+// Also here: the sorted compaction behind point_id / point_count.
 #include "lgr_common.cuh"
 #include "lgr_prof.cuh"
 
@@ -122,7 +124,7 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// per-tile stable LSD radix sort
+// stable LSD radix sort (fallback for lists longer than the shared-memory capacity; operates on global scratch)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;

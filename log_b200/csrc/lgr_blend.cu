@@ -1,12 +1,13 @@
-// Per-tile front-to-back alpha compositing (forward) and the back-to-front gradient sweep (backward).
+// Per-tile front-to-back alpha compositing (forward) and the gradient sweep (backward).
 //
 // One CTA of 256 threads per 16x16 tile; warp w owns the 8x4 pixel sub-tile ((w&1)*8, (w>>1)*4), one pixel per
 // lane.  The tile's depth-sorted list is staged through shared memory 256 splats at a time (coalesced id read,
-// 3 x 16-byte gather per splat).  Each warp then tests 32 staged splats at once against its sub-tile
-// (lane = splat, conservative alpha>=1/255 box), ballots, and only walks the hits (lane = pixel, broadcast LDS).
-// With small splats this skips ~3/4 of the (pixel, splat) pairs the classic per-thread loop evaluates.
-// Backward: same front-to-back walk; per hit the 9 partial gradients are reduced across the warp through a
-// shared-memory transpose, accumulated per staged splat in shared memory, and flushed with 3 vector atomics per splat.
+// 3 x 16-byte gather per splat, 48-byte staged record).  Each warp then tests 32 staged splats at once against its
+// sub-tile (lane = splat, conservative alpha>=1/255 box), ballots, and only walks the hits (lane = pixel, broadcast
+// LDS).  With small splats this skips ~90 % of the (pixel, splat) pairs the classic per-thread loop evaluates.
+// Backward: the same front-to-back walk (closed form of the published recurrence, see below); per hit every lane
+// publishes two scalars and 27 lanes reduce them against fixed weights held in registers (pixel-coordinate moments
+// and cotangent-weighted sums); the moments become gradients once per staged splat, then 3 vector atomics per splat.
 #include "lgr_common.cuh"
 #include "lgr_prof.cuh"
 
