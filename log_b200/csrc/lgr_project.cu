@@ -244,7 +244,16 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sP[threadIdx.x] = v.proj[threadIdx.x]; }
   if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
   __syncthreads();
-  int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
+  // Fused exchange: rank r starts with the rows of owner r+1, r+2, ... so that the ranks do not all push into the same
+  // destination at the same time (rows are grouped by owner in ascending order).
+  int64_t blk = blockIdx.x;
+  if (ROWS && peer_stage) {
+    int64_t first = 0;
+    for (int o = 0; o <= my_rank && o < v.num_owners - 1; o++) first += v.band_count[o];
+    if (my_rank == v.num_owners - 1) first = 0;
+    blk = (blk + first / PROJ_THREADS) % gridDim.x;
+  }
+  int64_t i = blk * PROJ_THREADS + threadIdx.x;
   const bool active = i < n;
   if (!ROWS && !active) return;
   int64_t row = 0;
@@ -416,7 +425,7 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
       s_dst[threadIdx.x] = dst;
     }
     __syncthreads();
-    const int64_t left = n - (int64_t)blockIdx.x * PROJ_THREADS;
+    const int64_t left = n - blk * PROJ_THREADS;
     const int cnt = left < PROJ_THREADS ? (int)left : PROJ_THREADS;
     for (int idx = threadIdx.x; idx < cnt * 5; idx += PROJ_THREADS) {
       const int r = idx / 5;

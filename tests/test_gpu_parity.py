@@ -326,3 +326,47 @@ def test_point_id_count_equals_torch_unique(built, W, H, n, r):
     got_id, got_cnt = point_id_count(rast.last_point_count)
     assert torch.equal(got_id.long(), want_id.long()) and torch.equal(got_cnt.long(), want_cnt.long())
     assert int(rast.last_point_count.sum()) == int((pid_pixel >= 0).sum())
+
+
+@pytest.mark.parametrize('world', [2, 5])
+def test_fused_push_route_emulated_on_one_gpu(built, world):
+    """The fused exchange (project_bwd stores packed rows straight into the owners' staging buffers, then
+    lgr_grad_scatter_add_staged) exercised on ONE GPU: the "peer" pointers are local buffers, one per virtual rank."""
+    import ctypes
+    from log_b200 import _capi, rasterize_backward, rasterize_forward, sharded
+    from log_b200._capi import LGR_FILTER_MAX
+    from util import settings_from_camera
+    W, H, n = 224, 160, 6001
+    cam = f32_camera(O.make_camera(W, H, bg=(0.1, 0.2, 0.3)))
+    sc = f32_scene(O.make_scene(n, W, H, 4.0, seed=41))
+    G = O.make_cotangent(3, H, W)
+    full = run_gpu(cam, sc, G)
+    dense = sharded.pack_grads((full['dmeans3D'], full['dmeans2D'], full['dopacities'], full['dscales'], full['drotations'],
+                                full['dcolors']))
+    dev = torch.device('cuda:0')
+    s = settings_from_camera(cam, dev)
+    t = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in sc.items()}
+    Gd, op = G.to(device=dev, dtype=torch.float32), t['opacities'].reshape(-1)
+    chunk = sharded.owner_chunk(n, world)
+    floats = _capi.LGR_STAGE_HEADER_FLOATS + world * chunk * _capi.LGR_ROW_FLOATS
+    stages = [torch.full((floats,), float('nan'), device=dev) for _ in range(world)]     # garbage where nothing is written
+    for st_ in stages:
+        st_[:_capi.LGR_STAGE_HEADER_FLOATS].view(torch.int32).fill_(12345)              # stale counts must be overwritten
+    ptrs = torch.tensor([st_.data_ptr() for st_ in stages], dtype=torch.int64, device=dev)
+    for r, band in enumerate(sharded.tile_row_partition(H, world)):
+        *_, st = rasterize_forward(s, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None, LGR_FILTER_MAX, True,
+                                   band, num_owners=world)
+        assert rasterize_backward(st, Gd, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None,
+                                  peer_stage=ptrs, my_rank=r) is None
+    lib = _capi.load()
+    shards = []
+    for o, (lo, hi) in enumerate(sharded.owner_partition(n, world)):
+        shard = torch.zeros((chunk, _capi.LGR_ROW_FLOATS), device=dev)
+        _capi.check(lib.lgr_grad_scatter_add_staged(ctypes.c_void_p(stages[o].data_ptr()), world, chunk, lo, hi,
+                                                    ctypes.c_void_p(shard.data_ptr()),
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'staged')
+        shards.append(shard[:hi - lo])
+    got = torch.cat(shards)
+    assert torch.isfinite(got).all()
+    assert rel(got[:, :17], dense) < 2e-5
+    assert torch.equal(got[:, 18].int(), full['radii'])
