@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)')
     os.makedirs(LIB_DIR, exist_ok=True)
     tmp = LIB_PATH + '.tmp'
-    cmd = [nvcc] + NVCC_FLAGS + ['-shared', '-o', tmp] + sources()
+    extra = os.environ.get('LGR_NVCC_EXTRA', '').split()      # e.g. -DLGR_BWD_MIN_CTAS=5 for tuning experiments
+    cmd = [nvcc] + NVCC_FLAGS + extra + ['-shared', '-o', tmp] + sources()
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
         print(' '.join(cmd))

@@ -14,6 +14,13 @@
 namespace lgr {
 
 constexpr int BLEND_THREADS = TILE_PIX;   // 256
+// minimum resident CTAs per SM the compiler must make room for (register cap = 65536 / (256 * N)); measured, see DESIGN.md
+#ifndef LGR_FWD_MIN_CTAS
+#define LGR_FWD_MIN_CTAS 5
+#endif
+#ifndef LGR_BWD_MIN_CTAS
+#define LGR_BWD_MIN_CTAS 4
+#endif
 constexpr int BATCH = 256;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -94,7 +101,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // forward
 // ---------------------------------------------------------------------------------------------------------
 template <bool AUX>
-__global__ void __launch_bounds__(BLEND_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS, LGR_FWD_MIN_CTAS)
 blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
                  const float* __restrict__ splat, float* __restrict__ image, float* __restrict__ final_T,
                  int32_t* __restrict__ n_contrib, int32_t* __restrict__ pid_pixel, float* __restrict__ pw_pixel,
@@ -194,7 +201,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
 // combined with two shuffles and 9 lanes add into the per-splat accumulators.  The moments are turned into
 // d/dmean2D, d/dconic, d/dopacity once per staged splat when the batch is flushed (X = splat centre, same coordinates):
 //     sum wG dx = X M00 - M10,   sum wG dx^2 = X^2 M00 - 2 X M10 + M20,   sum wG dx dy = XY M00 - X M01 - Y M10 + M11 ...
-__global__ void __launch_bounds__(BLEND_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS, LGR_BWD_MIN_CTAS)
 blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
                  const float* __restrict__ splat, const float* __restrict__ image,
                  const float* __restrict__ dL_dimage, float* __restrict__ dsplat) {
