@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 10
+#define LGR_ABI_VERSION 11
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -54,7 +54,12 @@ typedef struct lgr_view {
    * Scatter and the per-Gaussian backward walk only those lists (ascending ids = grouped by owner), and splat records
    * of Gaussians outside the band are not written. */
   int32_t num_owners;
-  int32_t reserved0;
+  int32_t raw_params;    /* 0: scales/opacities/rotations/colors_precomp are activated values (the reference call, default).
+                            1: they are LoG's raw parameters and the activations of
+                            LoG/model/activation.py:36-44 are fused into the projection and its backward:
+                            scale = exp(raw), opacity = sigmoid(raw), rotation = raw / max(|raw|, 1e-12),
+                            colour = C0 * raw + 0.5 (SH2RGB, sh_utils.py:72-73); gradients are w.r.t. the raw values.
+                            Precomputed colours only. */
   int32_t* band_ids_d;   /* (256 B) int32, or NULL */
   int32_t* band_blk_d;   /* (2 B + 1) int32 */
   int32_t* band_count_d; /* (num_owners) int32 */

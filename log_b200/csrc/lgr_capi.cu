@@ -9,7 +9,7 @@ int launch_compute_radius(int64_t, const float*, const float*, const float*, con
                           float, float, float*, cudaStream_t);
 int launch_project_fwd(const View&, int64_t, const float*, const float*, const float*, const float*, const float*,
                        const float*, float*, int32_t*, uint8_t*, int32_t*, int32_t*, cudaStream_t);
-int launch_project_bwd(const View&, int64_t, const float*, const float*, const float*, const float*, bool,
+int launch_project_bwd(const View&, int64_t, const float*, const float*, const float*, const float*, const float*, bool,
                        const int32_t*, const uint8_t*, const float*, float*, float*, float*, float*, float*, float*,
                        float*, float*, void* const*, int, cudaStream_t);
 int launch_grad_scatter_add(int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
@@ -62,6 +62,7 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
                         int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, void* stream) {
   if (!view_ok(view) || n < 0 || !tile_start_d || !tile_cursor_d || !meta_d) return LGR_E_BADARG;
   if ((colors_precomp_d != nullptr) == (shs_d != nullptr) && n > 0) return LGR_E_BADARG;   // exactly one colour source
+  if (view->raw_params && shs_d) return LGR_E_UNSUPPORTED;   // fused activations: precomputed (DC) colours only
   if (shs_d) {
     if (!view->campos_d || !clamped_d) return LGR_E_BADARG;
     if (view->sh_degree < 0 || view->sh_degree > 3) return LGR_E_UNSUPPORTED;
@@ -116,12 +117,12 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  float* dmeans3D_d, float* dmeans2D_d, float* dopacities_d, float* dscales_d, float* drotations_d,
                  float* dcolors_d, float* dshs_d, float* grad_rows_d, void* const* peer_stage_d, int32_t my_rank,
                  int64_t num_rows, void* stream) {
-  (void)opacities_d;
   if (!view_ok(view) || n < 0 || !tile_start_d || !image_d || !dL_dimage_d) return LGR_E_BADARG;
   if (n == 0) return 0;
   const bool use_sh = shs_d != nullptr;
   if (use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
   if (!means3D_d || !scales_d || !rotations_d || !splat_d || !radii_d || !dsplat_d) return LGR_E_BADARG;
+  if (view->raw_params && (!opacities_d || use_sh)) return LGR_E_BADARG;
   if (grad_rows_d || peer_stage_d) {
     if (view->num_owners <= 0 || use_sh) return LGR_E_BADARG;
     if (peer_stage_d && (my_rank < 0 || my_rank >= view->num_owners)) return LGR_E_BADARG;
@@ -138,7 +139,7 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, dL_dimage_d, dsplat_d, st);
   if (rc) return rc;
   const bool rows_mode = grad_rows_d || peer_stage_d;
-  return launch_project_bwd(v, rows_mode ? num_rows : n, means3D_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
+  return launch_project_bwd(v, rows_mode ? num_rows : n, means3D_d, opacities_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
                             dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, grad_rows_d, peer_stage_d, my_rank, st);
 }
 

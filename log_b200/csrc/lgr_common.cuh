@@ -25,6 +25,7 @@ struct View {
   int row0, row1;            // tile rows rendered by this call [row0,row1)
   float tanfovx, tanfovy, fx, fy, scale_mod;
   int sh_degree, sh_K, filter_mode, want_aux;
+  int raw_params;            // 1: inputs are LoG's raw parameters, activations fused (activation.py:36-44)
   int num_owners, owner_chunk;     // band mode: ids grouped by owner o = id / owner_chunk (0 owners = off)
   int32_t* band_ids;
   int32_t* band_blk;         // [0,B): per-CTA counts ; [B, 2B+1): exclusive prefix
@@ -52,6 +53,7 @@ inline View make_view(const lgr_view* v, int64_t n = 0) {
   o.fx = o.W / (2.0f * v->tanfovx); o.fy = o.H / (2.0f * v->tanfovy);
   o.scale_mod = v->scale_modifier;
   o.sh_degree = v->sh_degree; o.sh_K = v->sh_coeffs; o.filter_mode = v->filter_mode; o.want_aux = v->want_aux;
+  o.raw_params = v->raw_params;
   o.view = v->viewmatrix_d; o.proj = v->projmatrix_d; o.campos = v->campos_d; o.bg = v->bg_d;
   return o;
 }
@@ -123,6 +125,13 @@ __device__ __forceinline__ void cov2d(const float* __restrict__ V, const float p
   o.a = o.a_raw; o.c = o.c_raw;
   if (filter_mode == LGR_FILTER_ADD) { o.a += FILTER_VAR; o.c += FILTER_VAR; }
   else if (filter_mode == LGR_FILTER_MAX) { o.a = fmaxf(o.a, FILTER_VAR); o.c = fmaxf(o.c, FILTER_VAR); }
+}
+
+// LoG's parameter activations (LoG/model/activation.py:5-21, 36-44), used when View::raw_params is set.
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float4 act_normalize(float4 q, float& inv_norm) {
+  inv_norm = 1.0f / fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);     // F.normalize eps
+  return make_float4(q.x * inv_norm, q.y * inv_norm, q.z * inv_norm, q.w * inv_norm);
 }
 
 // 3 sqrt(lambda_max)  (compute_radius_kernel.cu:139-152)

@@ -84,7 +84,12 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     load3(means, i, p);
     load3(scales, i, s);
     const float4 q = ldg4(rots + 4 * i);
-    const float qn = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    float qn = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    if (v.raw_params) {      // activations fused: exp scales, rotation normalised by construction
+#pragma unroll
+      for (int k = 0; k < 3; k++) s[k] = expf(s[k]);
+      qn = qn > 1e-24f ? 1.0f : qn;
+    }
     const float tz = p[0] * sV[2] + p[1] * sV[6] + p[2] * sV[10] + sV[14];
     if (!(tz > NEAR_Z)) work = false;
     else if (fabsf(qn - 1.0f) < 1e-3f) {
@@ -127,9 +132,16 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     float p[3], s[3], R[9], Sg[9];
     load3(means, i, p);
     load3(scales, i, s);
+    float4 q = ldg4(rots + 4 * i);
+    if (v.raw_params) {
+      float inv;
+#pragma unroll
+      for (int k = 0; k < 3; k++) s[k] = expf(s[k]);
+      q = act_normalize(q, inv);
+    }
 #pragma unroll
     for (int k = 0; k < 3; k++) s[k] *= v.scale_mod;
-    quat_to_R(ldg4(rots + 4 * i), R);
+    quat_to_R(q, R);
     cov3d(s, R, Sg);
     Cov2D cv;
     cov2d(sV, p, Sg, v.fx, v.fy, v.tanfovx, v.tanfovy, v.filter_mode, cv);
@@ -151,7 +163,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
         stock_tiles = (unsigned long long)((x1 - x0) * (max(0, min(y1, v.row1) - max(y0, v.row0))));
         in_band = stock_tiles > 0;      // band lists follow the stock rectangle so that owners see every radius > 0
         const float idet = 1.0f / det;
-        const float o = __ldg(opac + i);
+        const float o = v.raw_params ? act_sigmoid(__ldg(opac + i)) : __ldg(opac + i);
         // conservative half extents of {alpha >= 1/255}:  d^T Conic d <= 2 ln(255 o)  =>  |dx| <= sqrt(q a)
         float hx = 0.f, hy = 0.f;
         bool reach = o * 255.0f >= 1.0f;
@@ -178,6 +190,10 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
           clamped[i] = cl;
         } else {
           load3(colors, i, rgb);
+          if (v.raw_params) {      // SH2RGB (sh_utils.py:72-73)
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) rgb[ch] = fmaf(SH_C0, rgb[ch], 0.5f);
+          }
         }
         // conic pre-multiplied by log2(e): the blend evaluates alpha = o * 2^(-0.5 d^T C' d)
         const float kdet = LOG2E * idet;
@@ -234,8 +250,8 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
 // ---------------------------------------------------------------------------------------------------------
 template <bool USE_SH, bool ROWS>
 __global__ void __launch_bounds__(PROJ_THREADS)
-project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ scales,
-                   const float* __restrict__ rots, const float* __restrict__ shs, const int32_t* __restrict__ radii,
+project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ opac,
+                   const float* __restrict__ scales, const float* __restrict__ rots, const float* __restrict__ shs, const int32_t* __restrict__ radii,
                    const uint8_t* __restrict__ clamped, const float* __restrict__ dsplat, float* __restrict__ dmeans,
                    float* __restrict__ dmeans2D, float* __restrict__ dopac, float* __restrict__ dscales,
                    float* __restrict__ drots, float* __restrict__ dcolors, float* __restrict__ dshs,
@@ -272,9 +288,15 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     float p[3], s0[3], s[3], R[9], Sg[9];
     load3(means, i, p);
     load3(scales, i, s0);
+    float4 q = ldg4(rots + 4 * i);
+    float q_inv = 1.0f;
+    if (v.raw_params) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) s0[k] = expf(s0[k]);
+      q = act_normalize(q, q_inv);
+    }
 #pragma unroll
     for (int k = 0; k < 3; k++) s[k] = s0[k] * v.scale_mod;
-    const float4 q = ldg4(rots + 4 * i);
     quat_to_R(q, R);
     cov3d(s, R, Sg);
     Cov2D cv;
@@ -398,6 +420,20 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   } else if (USE_SH) {
     float* dsh = dshs + (int64_t)i * K * 3;
     for (int k = 0; k < K * 3; k++) dsh[k] = 0.f;
+  }
+  if (v.raw_params && live) {      // chain rule through LoG's activations (activation.py:36-44)
+    float s_act[3];
+    load3(scales, i, s_act);
+#pragma unroll
+    for (int k = 0; k < 3; k++) dsc[k] *= expf(s_act[k]);                       // d exp(x) = exp(x)
+    const float o = act_sigmoid(__ldg(opac + i));
+    dop *= o * (1.0f - o);                                                        // d sigmoid = o (1 - o)
+    float inv;
+    const float4 qn = act_normalize(ldg4(rots + 4 * i), inv);
+    const float dot = qn.x * dq[0] + qn.y * dq[1] + qn.z * dq[2] + qn.w * dq[3];
+    dq[0] = (dq[0] - qn.x * dot) * inv; dq[1] = (dq[1] - qn.y * dot) * inv;       // d (r/|r|) = (I - q q^T) / |r|
+    dq[2] = (dq[2] - qn.z * dot) * inv; dq[3] = (dq[3] - qn.w * dot) * inv;
+    if (!USE_SH) { drgb[0] *= SH_C0; drgb[1] *= SH_C0; drgb[2] *= SH_C0; }        // d (C0 x + 0.5) = C0
   }
   if (ROWS) {
     // Rows are staged in shared memory and written out by the whole CTA as contiguous 16-byte-per-lane runs: the rows of
@@ -583,7 +619,7 @@ int launch_project_fwd(const View& v, int64_t n, const float* means, const float
   return 0;
 }
 
-int launch_project_bwd(const View& v, int64_t n, const float* means, const float* scales, const float* rots,
+int launch_project_bwd(const View& v, int64_t n, const float* means, const float* opac, const float* scales, const float* rots,
                        const float* shs, bool use_sh, const int32_t* radii, const uint8_t* clamped, const float* dsplat,
                        float* dmeans, float* dmeans2D, float* dopac, float* dscales, float* drots, float* dcolors,
                        float* dshs, float* grad_rows, void* const* peer_stage, int my_rank, cudaStream_t st) {
@@ -595,11 +631,11 @@ int launch_project_bwd(const View& v, int64_t n, const float* means, const float
   const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
   ProfScope ps(K_PROJECT_BWD, st);
   if (grad_rows || peer_stage)
-    project_bwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
+    project_bwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   else if (!use_sh)
-    project_bwd_kernel<false, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
+    project_bwd_kernel<false, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   else
-    project_bwd_kernel<true, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
+    project_bwd_kernel<true, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   LGR_CHECK_LAUNCH();
   return 0;
 }

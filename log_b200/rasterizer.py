@@ -70,7 +70,8 @@ def _stream():
 
 
 def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep,
-               num_owners=0, band_ids=None, band_count=None, band_blk=None, band_rows=None, band_dsplat=None):
+               num_owners=0, band_ids=None, band_count=None, band_blk=None, band_rows=None, band_dsplat=None,
+               raw_params=False):
     dev = s.viewmatrix.device
     vm, pm = _f32c(s.viewmatrix, 'viewmatrix'), _f32c(s.projmatrix, 'projmatrix', dev)
     bg = _f32c(s.bg, 'bg', dev)
@@ -84,6 +85,7 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
     v.filter_mode, v.want_aux = int(filter_mode), int(bool(want_aux))
     v.tile_row_begin, v.tile_row_end = (0, 0) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
     v.num_owners = int(num_owners)
+    v.raw_params = int(bool(raw_params))
     v.band_ids_d = band_ids.data_ptr() if band_ids is not None else None
     v.band_count_d = band_count.data_ptr() if band_count is not None else None
     v.band_blk_d = band_blk.data_ptr() if band_blk is not None else None
@@ -103,10 +105,12 @@ class RasterState:
 
 
 def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_precomp, shs, filter_mode, want_aux,
-                      tile_rows=None, num_owners=0):
+                      tile_rows=None, num_owners=0, raw_params=False):
     """Run the forward through the C ABI.  Returns (image, radii, pid, pwp, point_weight, state).
     num_owners > 0 (multi-GPU band mode, see log_b200/sharded.py): also compact the ids of the Gaussians reaching the
-    band `tile_rows`, grouped by owner rank; the backward then returns packed gradient rows instead of dense tensors."""
+    band `tile_rows`, grouped by owner rank; the backward then returns packed gradient rows instead of dense tensors.
+    raw_params=True: scales / opacities / rotations / colors_precomp are LoG's RAW parameters; exp / sigmoid / normalize /
+    SH2RGB (LoG/model/activation.py:36-44) run inside the projection kernels and the gradients are w.r.t. the raw values."""
     lib = _capi.load()
     dev = means3D.device
     n = int(means3D.shape[0])
@@ -120,7 +124,8 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         band_ids = torch.empty((max(256 * nb, 1),), dtype=torch.int32, device=dev)
         band_blk = torch.empty((2 * nb + 1,), dtype=torch.int32, device=dev)
         band_count = torch.empty((num_owners,), dtype=torch.int32, device=dev)
-    view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep, num_owners, band_ids, band_count, band_blk, band_rows, band_dsplat)
+    view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep, num_owners, band_ids, band_count, band_blk, band_rows, band_dsplat,
+                      raw_params)
     H, W = view.image_height, view.image_width
     gx, gy = (W + 15) // 16, (H + 15) // 16
     rows = gy if tile_rows is None else int(tile_rows[1]) - int(tile_rows[0])
@@ -241,7 +246,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, colors_precomp, shs, scales, rotations, settings, filter_mode, want_aux,
-                tile_rows):
+                tile_rows, raw_params=False):
         dev = means3D.device
         m = _f32c(means3D, 'means3D')
         o = _f32c(opacities, 'opacities', dev)
@@ -249,7 +254,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         r = _f32c(rotations, 'rotations', dev)
         c = _f32c(colors_precomp, 'colors_precomp', dev)
         sh = _f32c(shs, 'shs', dev)
-        image, radii, pid, pwp, pw, state = rasterize_forward(settings, m, o, sc, r, c, sh, filter_mode, want_aux, tile_rows)
+        image, radii, pid, pwp, pw, state = rasterize_forward(settings, m, o, sc, r, c, sh, filter_mode, want_aux, tile_rows,
+                                                              raw_params=raw_params)
         state.image = None          # the backward re-reads the rendered image: saved below so autograd guards it
         _RasterizeGaussians.last_point_count = state.point_count
         ctx.state = state
@@ -270,7 +276,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         sh = sh if ctx.has_sh else None
         ctx.state.image = image
         dm3, dm2, dop, dsc, drot, dcol, dsh = rasterize_backward(ctx.state, grad_image, m, o, sc, r, c, sh)
-        return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None
+        return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None, None
 
 
 class GaussianRasterizer(nn.Module):
@@ -296,7 +302,7 @@ class GaussianRasterizer(nn.Module):
                               s.image_width / (2.0 * s.tanfovx), s.image_height / (2.0 * s.tanfovy), s.tanfovx, s.tanfovy)
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None, use_filter=True):
+                cov3D_precomp=None, use_filter=True, raw_params=False):
         if (shs is None) == (colors_precomp is None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
         if cov3D_precomp is not None:
@@ -308,8 +314,10 @@ class GaussianRasterizer(nn.Module):
             filter_mode = LGR_FILTER_MAX if use_filter else LGR_FILTER_NONE
         else:
             filter_mode = LGR_FILTER_ADD
+        if raw_params and shs is not None:
+            raise NotImplementedError('raw_params (fused activations) supports precomputed colours only')
         out = _RasterizeGaussians.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
-                                        self.raster_settings, filter_mode, fork, self.tile_rows)
+                                        self.raster_settings, filter_mode, fork, self.tile_rows, raw_params)
         # fork flavour: per-Gaussian histogram of the per-pixel winners (feeds point_id_count())
         self.last_point_count = _RasterizeGaussians.last_point_count if fork else None
         return out

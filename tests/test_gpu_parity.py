@@ -370,3 +370,51 @@ def test_fused_push_route_emulated_on_one_gpu(built, world):
     assert torch.isfinite(got).all()
     assert rel(got[:, :17], dense) < 2e-5
     assert torch.equal(got[:, 18].int(), full['radii'])
+
+
+def test_fused_activations_match_torch_activations(built):
+    """with raw_params=True the kernels apply LoG's activations (activation.py:36-44: exp, sigmoid,
+    F.normalize, SH2RGB) themselves; image and gradients w.r.t. the RAW parameters equal torch activations followed by
+    the ordinary call, and the fp64 oracle differentiated through the same activations."""
+    from log_b200 import GaussianRasterizer
+    from util import settings_from_camera
+    W, H, n = 176, 112, 2500
+    cam = f32_camera(O.make_camera(W, H, bg=(0.3, 0.2, 0.1)))
+    sc = f32_scene(O.make_scene(n, W, H, 4.0, seed=55))
+    g = torch.Generator().manual_seed(1)
+    raw64 = dict(means3D=sc['means3D'], scales=torch.log(sc['scales']), opacities=torch.logit(sc['opacities'].clamp(0.02, 0.98)),
+                 rotations=sc['rotations'] * (0.5 + torch.rand(n, 1, generator=g, dtype=torch.float64) * 2.0),   # un-normalised
+                 colors=(sc['colors'] - 0.5) / O.C0)
+    raw64 = {k: v.to(torch.float32).to(torch.float64) for k, v in raw64.items()}
+    G = O.make_cotangent(3, H, W).to(torch.float32)
+    dev = torch.device('cuda:0')
+    rast = GaussianRasterizer(settings_from_camera(cam, dev))
+
+    def run(fused):
+        t = {k: v.to(device=dev, dtype=torch.float32).requires_grad_(True) for k, v in raw64.items()}
+        m2d = torch.zeros(n, 3, device=dev, requires_grad=True)
+        if fused:
+            out = rast(means3D=t['means3D'], means2D=m2d, shs=None, colors_precomp=t['colors'], opacities=t['opacities'],
+                       scales=t['scales'], rotations=t['rotations'], cov3D_precomp=None, raw_params=True)
+        else:
+            out = rast(means3D=t['means3D'], means2D=m2d, shs=None, colors_precomp=t['colors'] * O.C0 + 0.5,
+                       opacities=torch.sigmoid(t['opacities']), scales=torch.exp(t['scales']),
+                       rotations=torch.nn.functional.normalize(t['rotations']), cov3D_precomp=None)
+        (out[0] * G.to(dev)).sum().backward()
+        return out[0].detach(), {k: v.grad for k, v in t.items()}, m2d.grad
+
+    img_f, g_f, m2_f = run(True)
+    img_t, g_t, m2_t = run(False)
+    assert rel(img_f, img_t) < 1e-5
+    assert rel(m2_f, m2_t) < 1e-4
+    for k in g_t:
+        assert rel(g_f[k], g_t[k]) < 1e-4, (k, rel(g_f[k], g_t[k]))
+    # and against the oracle, differentiated through the same activations in float64
+    leaves = {k: v.clone().requires_grad_(True) for k, v in raw64.items()}
+    out = O.render(leaves['means3D'], torch.sigmoid(leaves['opacities']), torch.exp(leaves['scales']),
+                   torch.nn.functional.normalize(leaves['rotations']), cam, colors_precomp=leaves['colors'] * O.C0 + 0.5,
+                   filter_mode=O.FILTER_MAX)
+    (out['image'] * G.to(torch.float64)).sum().backward()
+    assert rel(img_f, out['image'].detach()) < 1e-4
+    for k in g_t:
+        assert rel(g_f[k], leaves[k].grad) < 2e-4, (k, rel(g_f[k], leaves[k].grad))
