@@ -232,7 +232,9 @@ constexpr int MSD_STACK = 512;
 struct MsdShared {
   int hist[RADIX];
   int bstart[RADIX + 1];
-  int wsum[SORT_WARPS];
+  // 16-byte aligned so that the vectorised LDS.128 of wsum[] does not also cover bstart[RADIX] (written by thread
+  // RADIX-1 in the same barrier interval: harmless, the lane is discarded, but racecheck reports it byte-wise)
+  alignas(16) int wsum[SORT_WARPS];
   unsigned long long wmin[SORT_WARPS], wmax[SORT_WARPS];
   int stack_beg[MSD_STACK], stack_len[MSD_STACK];
   int top, shift, overflow;
