@@ -352,7 +352,7 @@ def main():
     ach = kb[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:      # the ncu capture is of the single-GPU full-image launch
         traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
     launches = sum(v[1] for v in prof.values())
     line = {
