@@ -196,7 +196,15 @@ def main():
     # 2.55; 8 GPUs: peer 2.68 / nccl 1.85.  The fused NVLink push wins while few ranks write into each owner; at 8 ranks
     # all ranks push their owner-grouped rows in the same owner order (incast) and NCCL's staggered all-to-all is faster.
     route = os.environ.get('LGR_EXCHANGE', 'peer' if world <= 4 else 'nccl')
-    if world > 1 and route == 'peer':
+    # LGR_MULTI=shard: Gaussian-sharded ranks exchanging splat records / 2D gradients (log_b200/sharded.py:SplatExchange)
+    # instead of replicated Gaussians + gradient rows.  Opt-in until its first hardware run has been checked in.
+    shard = None
+    if world > 1 and os.environ.get('LGR_MULTI', 'band') == 'shard':
+        shard = sharded.SplatExchange.over_symmetric_memory(n, H)
+        lo_, hi_ = shard.lo, shard.hi
+        loc = {k: v[lo_:hi_].contiguous() for k, v in d.items()}
+        loc_op = loc['opacities'].reshape(-1)
+    if world > 1 and route == 'peer' and shard is None:
         try:
             peer = sharded.PeerExchange(n)
         except Exception as e:      # symmetric memory unavailable: NCCL all-to-all route
@@ -205,6 +213,22 @@ def main():
                 print(f'bench.py: peer exchange unavailable ({e!r}); using NCCL all-to-all', file=sys.stderr)
 
     def step_resident():
+        if shard is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            img, radii, pid, pwp, st = shard.forward(settings, loc['means3D'], loc_op, loc['scales'], loc['rotations'],
+                                                     loc['colors'] if deg == 0 else None, loc['shs'] if deg > 0 else None,
+                                                     filter_mode=LGR_FILTER_MAX, want_aux=True)
+            ev[1].record()
+            shard.blend_backward_and_return(st, dG)
+            ev[2].record()
+            shard.barrier()
+            g = shard.gather_and_project_backward(st)
+            ev[3].record()
+            phase_ev.append(ev)
+            stats['rows'] = st.num_rows
+            stats['D'], stats['D_stock'], stats['maxlen'], stats['visible'] = st.num_instances, st.stock_instances, st.max_tile_len, st.num_rows
+            return g
         if world > 1:      # band mode: owner-grouped id lists, packed gradient rows, one all-to-all to the owner ranks
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
@@ -272,6 +296,10 @@ def main():
 
         copy_stream = torch.cuda.Stream(device=dev)
 
+        if shard is not None:      # a rank only ever needs its own Gaussians
+            host = {k: v[shard.lo:shard.hi] for k, v in host.items()}
+            h2d_bytes = sum(v.numel() * 4 for k, v in host.items() if not (k == 'colors' and deg > 0)) + host_G.numel() * 4
+
         def h2d():
             """Issue this step's host->device copies on the copy stream; returns (tensors, cotangent, event)."""
             with torch.cuda.stream(copy_stream):
@@ -285,6 +313,13 @@ def main():
             torch.cuda.current_stream().wait_event(ev)
             for v_ in list(t_.values()) + [Gd]:
                 v_.record_stream(torch.cuda.current_stream())
+            if shard is not None:
+                img, radii, pid, pwp, st = shard.forward(settings, t_['means3D'], t_['opacities'].reshape(-1), t_['scales'],
+                                                         t_['rotations'], t_['colors'] if deg == 0 else None,
+                                                         t_.get('shs') if deg > 0 else None, filter_mode=LGR_FILTER_MAX, want_aux=True)
+                loss = (img * Gd).sum()
+                shard.backward(st, Gd)
+                return loss
             if world > 1:
                 o_ = t_['opacities'].reshape(-1)
                 img, radii, pid, pwp, pw, st = rasterize_forward(settings, t_['means3D'], o_, t_['scales'], t_['rotations'],
@@ -360,7 +395,7 @@ def main():
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / (ms_step * 1e-3) / 1e6,
         'config': {'workload': workload_name(args.workload),
-                   'parallelism': (f'tile-row bands x{world}, gradient rows ' + ('pushed to owner ranks over NVLink peer memory (fused in the backward kernel)' if peer is not None else 'NCCL all-to-all to owner ranks')) if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
+                   'parallelism': (f'Gaussians sharded x{world} + tile-row bands x{world}: splat records pushed to the band owners, 2D gradients returned, over NVLink peer memory (shard mode)') if shard is not None else (f'tile-row bands x{world}, gradient rows ' + ('pushed to owner ranks over NVLink peer memory (fused in the backward kernel)' if peer is not None else 'NCCL all-to-all to owner ranks')) if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
                    'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible']},
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                      'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes': kb[dom], 'kernel_ms': kms[dom]},

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 11
+#define LGR_ABI_VERSION 12
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -148,6 +148,62 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
 int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream);
 int lgr_grad_scatter_add_staged(const float* stage_d, int32_t num_sources, int64_t owner_chunk, int64_t lo, int64_t hi,
                                 float* shard_d, void* stream);
+
+/* ---- Multi-GPU shard mode (BASELINE configs 4 and 5): Gaussians sharded over the ranks, tile-row bands owned
+ * by ranks, projected splat records pushed to the band owners over NVLink peer memory, 2D gradients returned the same
+ * way.  The reference has no multi-GPU path; log_b200/sharded.py:SplatExchange is the host side.
+ *
+ * Every rank allocates one exchange buffer of the same size in peer-mapped memory (e.g. torch symmetric memory);
+ * peer_base_d is a DEVICE array of num_ranks pointers, entry r = rank r's buffer as mapped into this process.  All
+ * offsets are in floats from the buffer start and must be multiples of 4 (16-byte alignment):
+ *   off_count : int32[num_ranks]      rows received from each source rank
+ *   off_splat : float[num_ranks*cap][12]  received splat records, region s (rows s*cap ..) from source rank s
+ *   off_radii : int32[num_ranks*cap]   off_gid : int32[num_ranks*cap] (global Gaussian index of the row)
+ *   off_dsplat: float[num_ranks*cap][12]  RETURNED 2D gradients, region o from band owner o, in pushed row order
+ *   off_weight: uint32[num_ranks*cap] / off_pcount: int32[num_ranks*cap]  RETURNED point_weight bits / point counts
+ * cap = LGR_OWNER_CHUNK(N, num_ranks) rows per (source, owner) pair; rank r owns Gaussians [r*cap, min(N,(r+1)*cap)).
+ * Band owner o renders the tile rows tile_row_partition(H, num_ranks)[o] (the first gy % R bands have one more row). */
+typedef struct lgr_shard_layout {
+  int32_t num_ranks, my_rank;
+  int64_t cap;
+  int64_t off_count, off_splat, off_radii, off_gid, off_dsplat, off_weight, off_pcount;
+} lgr_shard_layout;
+#define LGR_SHARD_MAX_RANKS 32
+/* int32 scratch of lgr_shard_send, kept until lgr_shard_gather of the same step: 2*R*B + R with B = ceil(max(n,1)/256) */
+#define LGR_SHARD_SEND_INTS(n_local, r) (2 * (int64_t)(r) * ((((n_local) > 0 ? (n_local) : 1) + 255) / 256) + (r))
+
+/* Source rank, after lgr_forward_project of its own n_local Gaussians with a FULL-IMAGE view (splat_d, radii_d): assign
+ * rows without atomics and push records / radii / global ids (gid_base + i) into the band owners' buffers, and the row
+ * counts into their headers.  A cross-rank barrier must follow before owners call lgr_shard_recv_bin. */
+int lgr_shard_send(const lgr_view* view, const lgr_shard_layout* layout, int64_t n_local, int64_t gid_base,
+                   const float* splat_d, const int32_t* radii_d, int32_t* send_scratch_d, void* const* peer_base_d,
+                   void* stream);
+
+/* Band owner: view->tile_row_begin/end = its band.  Counts tiles of the received rows, clears the radii of unused slots,
+ * zeroes the dsplat_d rows (num_ranks*cap, 12) of used slots, then scans: tile_start_d / tile_cursor_d / meta_d exactly
+ * as lgr_forward_project leaves them.  Continue with lgr_forward_render(view, n = num_ranks*cap, ..., splat_d =
+ * exchange_d + off_splat, radii_d = exchange_d + off_radii, ...): point_id_pixel then holds ROW indices (map them
+ * through the gid array), point_weight_d / point_count_d are per row. */
+int lgr_shard_recv_bin(const lgr_view* view, const lgr_shard_layout* layout, float* exchange_d, float* dsplat_d,
+                       int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, void* stream);
+
+/* The per-tile gradient sweep alone (first half of lgr_backward): accumulates into dsplat_d (n,12). */
+int lgr_blend_backward(const lgr_view* view, int64_t n, int64_t num_instances, const float* splat_d,
+                       const int32_t* tile_start_d, const int32_t* sorted_ids_d, const float* image_d,
+                       const float* dL_dimage_d, float* dsplat_d, void* stream);
+
+/* Band owner: send per-row data (rows_d: (num_ranks*cap, row_floats) fp32/int32, row_floats = 12 or 1) back to the
+ * ranks that pushed the rows, into their buffers at dst_offset_floats (off_dsplat / off_weight / off_pcount).
+ * total_rows: sum of the received counts (sizes the grid only).  A cross-rank barrier must follow. */
+int lgr_shard_return_rows(const lgr_shard_layout* layout, const float* exchange_d, int64_t total_rows, const void* rows_d,
+                          int32_t row_floats, int64_t dst_offset_floats, void* const* peer_base_d, void* stream);
+
+/* Source rank: sum what the band owners returned into dense arrays of the local shard: dsplat_local_d (n_local,12) --
+ * feed it to lgr_backward(view, n_local, num_instances = 0, ...) for the per-Gaussian backward --, and optionally
+ * point_weight_d (n_local) fp32 (max over bands) / point_count_d (n_local) int32 (sum over bands). */
+int lgr_shard_gather(const lgr_view* view, const lgr_shard_layout* layout, int64_t n_local, const float* splat_d,
+                     const int32_t* radii_d, const int32_t* send_scratch_d, const float* exchange_d,
+                     float* dsplat_local_d, float* point_weight_d, int32_t* point_count_d, void* stream);
 
 /* Sorted compaction of the non-zero entries of point_count_d: ids_out_d / counts_out_d (capacity min(N, H*W)) receive the
  * ids in ascending order and their pixel counts, *num_out_d their number.  Equals

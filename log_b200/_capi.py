@@ -12,13 +12,15 @@ LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
 LGR_TILE_SCRATCH_INTS = 33
-LGR_ABI_VERSION = 11
+LGR_ABI_VERSION = 12
 LGR_STAGE_HEADER_FLOATS = 64
 LGR_ROW_FLOATS = 20
 
 EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
            'lgr_forward_render', 'lgr_backward', 'lgr_grad_scatter_add', 'lgr_grad_scatter_add_staged', 'lgr_point_compact', 'lgr_sparse_adam', 'lgr_profile_enable', 'lgr_profile_collect',
-           'lgr_profile_kernel_name')
+           'lgr_profile_kernel_name', 'lgr_shard_send', 'lgr_shard_recv_bin', 'lgr_blend_backward', 'lgr_shard_return_rows',
+           'lgr_shard_gather')
+LGR_SHARD_MAX_RANKS = 32
 LGR_PROFILE_KERNELS = 8
 
 
@@ -29,6 +31,17 @@ class LgrView(ctypes.Structure):
                 ('want_aux', _i32), ('tile_row_begin', _i32), ('tile_row_end', _i32),
                 ('num_owners', _i32), ('raw_params', _i32), ('band_ids_d', _vp), ('band_blk_d', _vp), ('band_count_d', _vp), ('band_rows_d', _vp), ('band_dsplat_d', _vp),
                 ('viewmatrix_d', _vp), ('projmatrix_d', _vp), ('campos_d', _vp), ('bg_d', _vp)]
+
+
+class LgrShardLayout(ctypes.Structure):
+    """struct lgr_shard_layout (multi-GPU shard mode): float offsets into every rank's exchange buffer."""
+    _fields_ = [('num_ranks', _i32), ('my_rank', _i32), ('cap', _i64), ('off_count', _i64), ('off_splat', _i64),
+                ('off_radii', _i64), ('off_gid', _i64), ('off_dsplat', _i64), ('off_weight', _i64), ('off_pcount', _i64)]
+
+
+def shard_send_ints(n_local, r):
+    """LGR_SHARD_SEND_INTS: int32 scratch of lgr_shard_send (kept until lgr_shard_gather)."""
+    return 2 * r * ((max(n_local, 1) + 255) // 256) + r
 
 
 class LgrError(RuntimeError):
@@ -66,6 +79,17 @@ def load():
     lib.lgr_grad_scatter_add_staged.argtypes = [_vp, _i32, _i64, _i64, _i64, _vp, _vp]
     lib.lgr_grad_scatter_add.restype = ctypes.c_int
     lib.lgr_grad_scatter_add.argtypes = [_i64, _vp, _i64, _i64, _vp, _vp]
+    lay = ctypes.POINTER(LgrShardLayout)
+    lib.lgr_shard_send.restype = ctypes.c_int
+    lib.lgr_shard_send.argtypes = [ctypes.POINTER(LgrView), lay, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
+    lib.lgr_shard_recv_bin.restype = ctypes.c_int
+    lib.lgr_shard_recv_bin.argtypes = [ctypes.POINTER(LgrView), lay, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.lgr_blend_backward.restype = ctypes.c_int
+    lib.lgr_blend_backward.argtypes = [ctypes.POINTER(LgrView), _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.lgr_shard_return_rows.restype = ctypes.c_int
+    lib.lgr_shard_return_rows.argtypes = [lay, _vp, _i64, _vp, _i32, _i64, _vp, _vp]
+    lib.lgr_shard_gather.restype = ctypes.c_int
+    lib.lgr_shard_gather.argtypes = [ctypes.POINTER(LgrView), lay, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.lgr_profile_enable.restype = ctypes.c_int
     lib.lgr_profile_enable.argtypes = [ctypes.c_int]
     lib.lgr_profile_collect.restype = ctypes.c_int

@@ -26,6 +26,12 @@ int launch_sparse_adam(int64_t, int, const int64_t*, const float*, float*, float
 int launch_point_compact(int64_t, const int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_blend_bwd(const View&, const int32_t*, const int32_t*, const float*, const float*, const float*, float*,
                      cudaStream_t);
+int launch_shard_send(const View&, const ShardLayout&, int64_t, int64_t, const float*, const int32_t*, int32_t*, void* const*,
+                      cudaStream_t);
+int launch_shard_recv_count(const View&, const ShardLayout&, float*, float*, int32_t*, int32_t*, cudaStream_t);
+int launch_shard_return(const ShardLayout&, const float*, int64_t, const void*, int, int64_t, void* const*, cudaStream_t);
+int launch_shard_gather(const View&, const ShardLayout&, int64_t, const float*, const int32_t*, const int32_t*, const float*,
+                        float*, float*, int32_t*, cudaStream_t);
 }  // namespace lgr
 
 using namespace lgr;
@@ -171,6 +177,80 @@ int lgr_grad_scatter_add_staged(const float* stage_d, int32_t num_sources, int64
 int lgr_grad_scatter_add(int64_t num_rows, const float* rows_d, int64_t lo, int64_t hi, float* shard_d, void* stream) {
   if (num_rows < 0 || hi < lo || (num_rows > 0 && (!rows_d || !shard_d))) return LGR_E_BADARG;
   return launch_grad_scatter_add(num_rows, rows_d, lo, hi, shard_d, (cudaStream_t)stream);
+}
+
+/* ---- multi-GPU shard mode ---- */
+static bool layout_ok(const lgr_shard_layout* l) {
+  if (!l || l->num_ranks <= 0 || l->num_ranks > LGR_SHARD_MAX_RANKS || l->my_rank < 0 || l->my_rank >= l->num_ranks) return false;
+  if (l->cap <= 0 || l->cap % 256) return false;
+  const int64_t offs[7] = {l->off_count, l->off_splat, l->off_radii, l->off_gid, l->off_dsplat, l->off_weight, l->off_pcount};
+  for (int k = 0; k < 7; k++) if (offs[k] < 0 || offs[k] % 4) return false;
+  return true;
+}
+
+static ShardLayout make_layout(const lgr_shard_layout* l) {
+  ShardLayout o;
+  o.R = l->num_ranks; o.me = l->my_rank; o.cap = l->cap;
+  o.off_count = l->off_count; o.off_splat = l->off_splat; o.off_radii = l->off_radii; o.off_gid = l->off_gid;
+  o.off_dsplat = l->off_dsplat; o.off_weight = l->off_weight; o.off_pcount = l->off_pcount;
+  return o;
+}
+
+int lgr_shard_send(const lgr_view* view, const lgr_shard_layout* layout, int64_t n_local, int64_t gid_base,
+                   const float* splat_d, const int32_t* radii_d, int32_t* send_scratch_d, void* const* peer_base_d,
+                   void* stream) {
+  if (!view_ok(view) || !layout_ok(layout) || n_local < 0 || gid_base < 0 || !send_scratch_d || !peer_base_d) return LGR_E_BADARG;
+  if (n_local > layout->cap || (n_local > 0 && (!splat_d || !radii_d))) return LGR_E_BADARG;
+  if (view->num_owners != 0 || view->tile_row_begin != 0 || (view->tile_row_end != 0 && view->tile_row_end != (view->image_height + TILE - 1) / TILE))
+    return LGR_E_BADARG;      // the source side works on the full image
+  if (gid_base + n_local > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
+  return launch_shard_send(make_view(view, n_local), make_layout(layout), n_local, gid_base, splat_d, radii_d, send_scratch_d,
+                           peer_base_d, (cudaStream_t)stream);
+}
+
+int lgr_shard_recv_bin(const lgr_view* view, const lgr_shard_layout* layout, float* exchange_d, float* dsplat_d,
+                       int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, void* stream) {
+  if (!view_ok(view) || !layout_ok(layout) || !exchange_d || !dsplat_d || !tile_start_d || !tile_cursor_d || !meta_d) return LGR_E_BADARG;
+  if (view->num_owners != 0) return LGR_E_BADARG;
+  if ((int64_t)layout->num_ranks * layout->cap > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const View v = make_view(view, (int64_t)layout->num_ranks * layout->cap);
+  const int ntiles = v.gx * (v.row1 - v.row0);
+  cudaError_t e = cudaMemsetAsync(tile_cursor_d, 0, sizeof(int32_t) * (size_t)(ntiles > 0 ? ntiles : 1) * CSTRIDE, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(meta_d, 0, sizeof(int32_t) * LGR_META_INTS, st);
+  if (e != cudaSuccess) return (int)e;
+  int rc = launch_shard_recv_count(v, make_layout(layout), exchange_d, dsplat_d, tile_cursor_d, meta_d, st);
+  if (rc) return rc;
+  return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, st);
+}
+
+int lgr_blend_backward(const lgr_view* view, int64_t n, int64_t num_instances, const float* splat_d,
+                       const int32_t* tile_start_d, const int32_t* sorted_ids_d, const float* image_d,
+                       const float* dL_dimage_d, float* dsplat_d, void* stream) {
+  if (!view_ok(view) || n < 0 || num_instances < 0 || !tile_start_d || !image_d || !dL_dimage_d) return LGR_E_BADARG;
+  if (num_instances == 0 || n == 0) return 0;
+  if (!splat_d || !sorted_ids_d || !dsplat_d) return LGR_E_BADARG;
+  return launch_blend_bwd(make_view(view, n), tile_start_d, sorted_ids_d, splat_d, image_d, dL_dimage_d, dsplat_d,
+                          (cudaStream_t)stream);
+}
+
+int lgr_shard_return_rows(const lgr_shard_layout* layout, const float* exchange_d, int64_t total_rows, const void* rows_d,
+                          int32_t row_floats, int64_t dst_offset_floats, void* const* peer_base_d, void* stream) {
+  if (!layout_ok(layout) || !exchange_d || !peer_base_d || total_rows < 0 || row_floats <= 0) return LGR_E_BADARG;
+  if (dst_offset_floats < 0 || dst_offset_floats % 4 || (total_rows > 0 && !rows_d)) return LGR_E_BADARG;
+  return launch_shard_return(make_layout(layout), exchange_d, total_rows, rows_d, row_floats, dst_offset_floats, peer_base_d,
+                             (cudaStream_t)stream);
+}
+
+int lgr_shard_gather(const lgr_view* view, const lgr_shard_layout* layout, int64_t n_local, const float* splat_d,
+                     const int32_t* radii_d, const int32_t* send_scratch_d, const float* exchange_d,
+                     float* dsplat_local_d, float* point_weight_d, int32_t* point_count_d, void* stream) {
+  if (!view_ok(view) || !layout_ok(layout) || n_local < 0 || n_local > layout->cap) return LGR_E_BADARG;
+  if (n_local == 0) return 0;
+  if (!splat_d || !radii_d || !send_scratch_d || !exchange_d || !dsplat_local_d) return LGR_E_BADARG;
+  return launch_shard_gather(make_view(view, n_local), make_layout(layout), n_local, splat_d, radii_d, send_scratch_d, exchange_d,
+                             dsplat_local_d, point_weight_d, point_count_d, (cudaStream_t)stream);
 }
 
 /* ---- diagnostics: per-kernel CUDA-event timing (used by bench.py for the live roofline numbers) ---- */

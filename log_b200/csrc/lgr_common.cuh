@@ -58,6 +58,13 @@ inline View make_view(const lgr_view* v, int64_t n = 0) {
   return o;
 }
 
+// Kernel-side copy of lgr_shard_layout (multi-GPU shard mode, lgr_shard.cu).
+struct ShardLayout {
+  int R, me;
+  int64_t cap;
+  int64_t off_count, off_splat, off_radii, off_gid, off_dsplat, off_weight, off_pcount;
+};
+
 // ---- projected splat record: 3 x float4 per Gaussian ---------------------------------------------------
 //   r0 = (px, py, conic_x, conic_y)      r1 = (conic_z, opacity, hx, hy)      r2 = (r, g, b, depth)
 // The conic is stored pre-multiplied by log2(e) so that the blend can use ex2.approx directly.

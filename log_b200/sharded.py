@@ -136,3 +136,247 @@ class PeerExchange:
                                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
                     'lgr_grad_scatter_add_staged')
         return shard
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Shard mode: Gaussians sharded over the ranks, splat records pushed to the band owners, 2D gradients returned.
+# (csrc/lgr_shard.cu; C ABI: lgr_shard_send / lgr_shard_recv_bin / lgr_blend_backward / lgr_shard_return_rows /
+# lgr_shard_gather.)  Unlike band mode above nothing is replicated and no per-Gaussian gradient is ever reduced: the rank
+# that owns a Gaussian projects it, and runs its backward, exactly once.
+# ---------------------------------------------------------------------------------------------------------------------
+def owner_of_row(tile_row: int, image_height: int, world_size: int) -> int:
+    """Rank whose band (tile_row_partition) holds `tile_row`; mirrors owner_of_row() in csrc/lgr_shard.cu."""
+    gy = (image_height + 15) // 16
+    base, extra = divmod(gy, world_size)
+    split = extra * (base + 1)
+    return tile_row // (base + 1) if tile_row < split else extra + (tile_row - split) // max(base, 1)
+
+
+def shard_layout(num_gaussians: int, world_size: int, rank: int):
+    """(LgrShardLayout, floats per exchange buffer).  Every region starts on a 256-byte boundary."""
+    from . import _capi
+    cap = owner_chunk(num_gaussians, world_size)
+    rows = world_size * cap
+    off = 0
+
+    def take(floats):
+        nonlocal off
+        o = off
+        off += (floats + 63) // 64 * 64
+        return o
+    lay = _capi.LgrShardLayout()
+    lay.num_ranks, lay.my_rank, lay.cap = world_size, rank, cap
+    lay.off_count = take(max(world_size, 64))
+    lay.off_splat = take(rows * _capi.LGR_SPLAT_FLOATS)
+    lay.off_radii = take(rows)
+    lay.off_gid = take(rows)
+    lay.off_dsplat = take(rows * _capi.LGR_GRAD_FLOATS)
+    lay.off_weight = take(rows)
+    lay.off_pcount = take(rows)
+    return lay, off
+
+
+class ShardStep:
+    """Per-step buffers of SplatExchange (forward -> backward)."""
+    pass
+
+
+class SplatExchange:
+    """One rank's end of the shard-mode exchange.
+
+    own_buffer : this rank's exchange buffer, a float32 CUDA tensor of shard_layout()[1] floats in peer-mapped memory.
+    peer_ptrs  : `world` device addresses -- entry r is rank r's exchange buffer as mapped into THIS process (entry
+                 `rank` = own_buffer.data_ptr()).
+    barrier    : callable enqueueing a cross-rank barrier on the current stream (symmetric memory: handle.barrier).
+    Use SplatExchange.over_symmetric_memory(N, H) under torchrun; tests drive several instances inside one process
+    with plain local buffers and a no-op barrier, phase by phase."""
+
+    def __init__(self, num_gaussians: int, image_height: int, rank: int, world: int, own_buffer, peer_ptrs, barrier):
+        from . import _capi
+        self.n, self.rank, self.world = int(num_gaussians), int(rank), int(world)
+        if not 0 < self.world <= _capi.LGR_SHARD_MAX_RANKS:
+            raise ValueError(f'shard mode supports 1..{_capi.LGR_SHARD_MAX_RANKS} ranks, got {world}')
+        self.layout, self.floats = shard_layout(self.n, self.world, self.rank)
+        self.cap = int(self.layout.cap)
+        self.lo, self.hi = owner_partition(self.n, self.world)[self.rank]
+        self.band = tile_row_partition(image_height, self.world)[self.rank]
+        self.image_height = int(image_height)
+        peer_ptrs = [int(p) for p in peer_ptrs]
+        if own_buffer.dtype != torch.float32 or own_buffer.numel() < self.floats or not own_buffer.is_cuda:
+            raise ValueError(f'the exchange buffer must be a float32 CUDA tensor of >= {self.floats} elements')
+        if len(peer_ptrs) != self.world or peer_ptrs[self.rank] != own_buffer.data_ptr():
+            raise ValueError('peer_ptrs needs one address per rank, entry `rank` being own_buffer')
+        self.buf, self.barrier = own_buffer, barrier
+        dev = self.buf.device
+        self.peer_ptrs = torch.tensor(peer_ptrs, dtype=torch.int64, device=dev)
+        L, rows = self.layout, self.world * self.cap
+        self.count = self.buf[L.off_count:L.off_count + self.world].view(torch.int32)
+        self.recv_splat = self.buf[L.off_splat:L.off_splat + rows * 12].view(rows, 12)
+        self.recv_radii = self.buf[L.off_radii:L.off_radii + rows].view(torch.int32)
+        self.recv_gid = self.buf[L.off_gid:L.off_gid + rows].view(torch.int32)
+        self.dsplat_rows = torch.empty((rows, _capi.LGR_GRAD_FLOATS), dtype=torch.float32, device=dev)
+        self.count.zero_()
+        self.recv_radii.zero_()
+
+    @classmethod
+    def over_symmetric_memory(cls, num_gaussians: int, image_height: int, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        _, floats = shard_layout(num_gaussians, world, rank)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        buf = symm.empty(floats, dtype=torch.float32, device=dev)
+        handle = symm.rendezvous(buf, group)
+        self = cls(num_gaussians, image_height, rank, world, buf, list(handle.buffer_ptrs), handle.barrier)
+        self.handle = handle
+        handle.barrier()
+        return self
+
+    # ---- phases (forward() / backward() below string them together with the barriers) --------------------------
+    def project_and_send(self, settings, means3D, opacities, scales, rotations, colors_precomp=None, shs=None,
+                         filter_mode=None, want_aux=True, raw_params=False) -> ShardStep:
+        """Project this rank's shard (inputs are the LOCAL rows [lo,hi) of the model) and push the visible records."""
+        import ctypes
+        from . import _capi
+        from .rasterizer import _f32c, _make_view, _ptr, _stream
+        lib = _capi.load()
+        filter_mode = _capi.LGR_FILTER_MAX if filter_mode is None else filter_mode
+        dev = self.buf.device
+        n = int(means3D.shape[0])
+        if n != self.hi - self.lo:
+            raise ValueError(f'rank {self.rank} owns Gaussians [{self.lo},{self.hi}): expected {self.hi - self.lo} rows, got {n}')
+        s = ShardStep()
+        s.inputs = tuple(_f32c(t, k, dev) for k, t in (('means3D', means3D), ('opacities', opacities), ('scales', scales),
+                                                       ('rotations', rotations), ('colors_precomp', colors_precomp), ('shs', shs)))
+        m, o, sc, r, c, sh = s.inputs
+        s.keep, s.n, s.want_aux, s.settings = [], n, bool(want_aux), settings
+        K = 0 if sh is None else int(sh.shape[1])
+        s.view_full = _make_view(settings, filter_mode, want_aux, K, None, s.keep, raw_params=raw_params)
+        s.view_band = _make_view(settings, filter_mode, want_aux, K, self.band, s.keep, raw_params=raw_params)
+        H, W = s.view_full.image_height, s.view_full.image_width
+        if H != self.image_height:
+            raise ValueError('image height differs from the one the bands were cut for')
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        i32 = dict(dtype=torch.int32, device=dev)
+        s.splat = torch.empty((n, _capi.LGR_SPLAT_FLOATS), dtype=torch.float32, device=dev)
+        s.radii = torch.empty((n,), **i32)
+        s.clamped = torch.empty((n,), dtype=torch.uint8, device=dev) if sh is not None else None
+        s.tile_start_full = torch.empty((gx * gy + 1,), **i32)
+        cursor = torch.empty((_capi.LGR_TILE_SCRATCH_INTS * gx * gy,), **i32)
+        meta = torch.empty((_capi.LGR_META_INTS,), **i32)
+        st = _stream()
+        _capi.check(lib.lgr_forward_project(ctypes.byref(s.view_full), n, _ptr(m), _ptr(o), _ptr(sc), _ptr(r), _ptr(c), _ptr(sh),
+                                            _ptr(s.splat), _ptr(s.radii), _ptr(s.clamped), _ptr(s.tile_start_full), _ptr(cursor),
+                                            _ptr(meta), st), 'lgr_forward_project')
+        s.send_scratch = torch.empty((_capi.shard_send_ints(n, self.world),), **i32)
+        _capi.check(lib.lgr_shard_send(ctypes.byref(s.view_full), ctypes.byref(self.layout), n, self.lo, _ptr(s.splat),
+                                       _ptr(s.radii), _ptr(s.send_scratch), ctypes.c_void_p(self.peer_ptrs.data_ptr()), st),
+                    'lgr_shard_send')
+        return s
+
+    def receive_and_render(self, s: ShardStep):
+        """Bin, sort and blend the rows received for this rank's band.  Returns (image, radii of the local shard,
+        point_id_pixel with GLOBAL Gaussian indices, point_weight_pixel); image / maps are full size, band rows filled."""
+        import ctypes
+        from . import _capi
+        from .rasterizer import _ptr, _stream
+        lib = _capi.load()
+        dev = self.buf.device
+        v = s.view_band
+        H, W = v.image_height, v.image_width
+        gx = (W + 15) // 16
+        ntiles = gx * (self.band[1] - self.band[0])
+        rows = self.world * self.cap
+        i32, f32 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.float32, device=dev)
+        s.tile_start = torch.empty((ntiles + 1,), **i32)
+        cursor = torch.empty((_capi.LGR_TILE_SCRATCH_INTS * max(ntiles, 1),), **i32)
+        meta = torch.empty((_capi.LGR_META_INTS,), **i32)
+        st = _stream()
+        _capi.check(lib.lgr_shard_recv_bin(ctypes.byref(v), ctypes.byref(self.layout), _ptr(self.buf), _ptr(self.dsplat_rows),
+                                           _ptr(s.tile_start), _ptr(cursor), _ptr(meta), st), 'lgr_shard_recv_bin')
+        m = torch.cat([meta, self.count]).tolist()                 # the one host sync of the forward
+        D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
+        s.num_instances, s.max_tile_len, s.num_rows = D, max_len, int(sum(m[_capi.LGR_META_INTS:]))
+        s.stock_instances = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
+        inst_key = torch.empty((D,), **i32)
+        inst_val = torch.empty((D,), **i32)
+        inst_tmp = torch.empty((2 * D,), **i32) if max_len > lib.lgr_sort_smem_capacity() else None
+        s.sorted_ids = torch.empty((D,), **i32)
+        s.image = torch.zeros((3, H, W), **f32)
+        final_T = torch.ones((H, W), **f32)
+        n_contrib = torch.zeros((H, W), **i32)
+        pid = pwp = s.pw_rows = s.pc_rows = None
+        if s.want_aux:
+            pid = torch.full((H, W), -1, **i32)
+            pwp = torch.zeros((H, W), **f32)
+            s.pw_rows = torch.zeros((rows,), **f32)
+            s.pc_rows = torch.zeros((rows,), **i32)
+        _capi.check(lib.lgr_forward_render(ctypes.byref(v), rows, D, max_len, num_long, _ptr(self.recv_splat), _ptr(self.recv_radii),
+                                           _ptr(s.tile_start), _ptr(cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
+                                           _ptr(s.sorted_ids), _ptr(s.image), _ptr(final_T), _ptr(n_contrib), _ptr(pid), _ptr(pwp),
+                                           _ptr(s.pw_rows), _ptr(s.pc_rows), st), 'lgr_forward_render')
+        if pid is not None:                                          # rows -> global Gaussian indices
+            pid = torch.where(pid >= 0, self.recv_gid[pid.clamp_min(0).long()], pid)
+        return s.image, s.radii, pid, pwp
+
+    def blend_backward_and_return(self, s: ShardStep, grad_image):
+        """Gradient sweep over this rank's band, then the 2D gradients (and the per-row aux outputs) go back to the ranks
+        that pushed the rows."""
+        import ctypes
+        from . import _capi
+        from .rasterizer import _f32c, _ptr, _stream
+        lib = _capi.load()
+        s.grad_image = _f32c(grad_image, 'grad_image', self.buf.device)
+        st, L, peers = _stream(), self.layout, ctypes.c_void_p(self.peer_ptrs.data_ptr())
+        rows = self.world * self.cap
+        _capi.check(lib.lgr_blend_backward(ctypes.byref(s.view_band), rows, s.num_instances, _ptr(self.recv_splat),
+                                           _ptr(s.tile_start), _ptr(s.sorted_ids), _ptr(s.image), _ptr(s.grad_image),
+                                           _ptr(self.dsplat_rows), st), 'lgr_blend_backward')
+        for data, width, off in ((self.dsplat_rows, _capi.LGR_GRAD_FLOATS, L.off_dsplat), (s.pw_rows, 1, L.off_weight),
+                                 (s.pc_rows, 1, L.off_pcount)):
+            if data is not None:
+                _capi.check(lib.lgr_shard_return_rows(ctypes.byref(L), _ptr(self.buf), s.num_rows, _ptr(data), width, off, peers, st),
+                            'lgr_shard_return_rows')
+
+    def gather_and_project_backward(self, s: ShardStep):
+        """Sum the returned rows per local Gaussian and run the per-Gaussian backward of the local shard.  Returns
+        ((dmeans3D, dmeans2D, dopacities, dscales, drotations, dcolors, dshs), point_weight, point_count) for the
+        Gaussians [lo,hi) this rank owns."""
+        import ctypes
+        from . import _capi
+        from .rasterizer import _ptr, _stream
+        lib = _capi.load()
+        dev = self.buf.device
+        n = s.n
+        m, o, sc, r, c, sh = s.inputs
+        f32 = dict(dtype=torch.float32, device=dev)
+        dsplat = torch.empty((n, _capi.LGR_GRAD_FLOATS), **f32)
+        pw = torch.empty((n,), **f32) if s.want_aux else None
+        pc = torch.empty((n,), dtype=torch.int32, device=dev) if s.want_aux else None
+        st = _stream()
+        _capi.check(lib.lgr_shard_gather(ctypes.byref(s.view_full), ctypes.byref(self.layout), n, _ptr(s.splat), _ptr(s.radii),
+                                         _ptr(s.send_scratch), _ptr(self.buf), _ptr(dsplat), _ptr(pw), _ptr(pc), st),
+                    'lgr_shard_gather')
+        dmeans3D, dmeans2D = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)
+        dopac, dscales, drot = torch.empty((n,), **f32), torch.empty((n, 3), **f32), torch.empty((n, 4), **f32)
+        dcolors = torch.empty((n, 3), **f32) if c is not None else None
+        dshs = torch.empty_like(sh) if sh is not None else None
+        if n:
+            _capi.check(lib.lgr_backward(ctypes.byref(s.view_full), n, 0, _ptr(m), _ptr(o), _ptr(sc), _ptr(r), _ptr(c), _ptr(sh),
+                                         _ptr(s.splat), _ptr(s.radii), _ptr(s.clamped), _ptr(s.tile_start_full), None,
+                                         _ptr(s.image), _ptr(s.grad_image), _ptr(dsplat), _ptr(dmeans3D), _ptr(dmeans2D),
+                                         _ptr(dopac), _ptr(dscales), _ptr(drot), _ptr(dcolors), _ptr(dshs), None, None, 0, 0, st),
+                        'lgr_backward')
+        return (dmeans3D, dmeans2D, dopac, dscales, drot, dcolors, dshs), pw, pc
+
+    # ---- the calls a training loop makes -----------------------------------------------------------------------
+    def forward(self, settings, means3D, opacities, scales, rotations, colors_precomp=None, shs=None, **kw):
+        self.barrier()          # every rank is done with the previous step's buffers
+        s = self.project_and_send(settings, means3D, opacities, scales, rotations, colors_precomp, shs, **kw)
+        self.barrier()          # all records have landed
+        return self.receive_and_render(s) + (s,)
+
+    def backward(self, s: ShardStep, grad_image):
+        self.blend_backward_and_return(s, grad_image)
+        self.barrier()          # all returned rows have landed
+        return self.gather_and_project_backward(s)

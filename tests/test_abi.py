@@ -71,3 +71,45 @@ def test_ctypes_arity_matches_header(built):
         assert len(fn.argtypes) == n_params, (name, len(fn.argtypes), n_params)
         checked += 1
     assert checked >= 6
+
+
+def test_ctypes_argument_kinds_match_header(built):
+    """Beyond the count: every bound argument has the C parameter's kind (pointer / int32 / int64 / float / double)."""
+    from log_b200 import _capi
+    lib = _capi.load()
+    src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    protos = dict(re.findall(r'\b(lgr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S))
+    scalar = {'int64_t': ctypes.c_int64, 'int32_t': ctypes.c_int32, 'int': ctypes.c_int, 'float': ctypes.c_float,
+              'double': ctypes.c_double}
+    for name, params in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None or params.strip() in ('', 'void'):
+            continue
+        for k, (decl, bound) in enumerate(zip(params.split(','), fn.argtypes)):
+            decl = decl.strip()
+            if '*' in decl:
+                assert bound is ctypes.c_void_p or issubclass(bound, ctypes._Pointer), (name, k, decl, bound)
+            else:
+                ctype = decl.replace('const', '').split()[0]
+                want = scalar[ctype]
+                assert ctypes.sizeof(bound) == ctypes.sizeof(want) and bound(1).value == want(1).value, (name, k, decl, bound)
+                assert (bound in (ctypes.c_float, ctypes.c_double)) == (want in (ctypes.c_float, ctypes.c_double)), (name, k, decl)
+
+
+def test_shard_layout_struct_matches_header():
+    from log_b200._capi import LgrShardLayout
+    src = open(HEADER).read()
+    body = re.search(r'typedef struct lgr_shard_layout \{(.*?)\} lgr_shard_layout;', src, flags=re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields, kinds = [], []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        for nm in names.split(','):
+            fields.append(nm.strip())
+            kinds.append({'int32_t': ctypes.c_int32, 'int64_t': ctypes.c_int64}[ctype])
+    assert fields == [f[0] for f in LgrShardLayout._fields_]
+    assert kinds == [f[1] for f in LgrShardLayout._fields_]
+    assert ctypes.sizeof(LgrShardLayout) == 8 + 8 * 8

@@ -71,3 +71,55 @@ def test_reduce_to_owners_gloo_world2(n):
     assert all(p.exitcode == 0 for p in procs)
     want = sum(torch.randn(n, sharded.GRAD_FLOATS_PRECOMP, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
     np.testing.assert_allclose(got, want.numpy(), rtol=1e-6, atol=1e-6)
+
+
+# ---- shard mode (SplatExchange) host logic -------------------------------------------------------------------------
+def test_owner_of_row_inverts_tile_row_partition():
+    from log_b200 import sharded
+    for H in (16, 40, 90, 1080, 2160):
+        for world in (1, 2, 3, 5, 8, 16, 32):
+            for o, (a, b) in enumerate(sharded.tile_row_partition(H, world)):
+                for y in range(a, b):
+                    assert sharded.owner_of_row(y, H, world) == o, (H, world, y)
+
+
+def test_shard_layout_regions_are_aligned_and_disjoint():
+    from log_b200 import _capi, sharded
+    for n, world in ((1, 1), (300, 4), (6001, 3), (10_000_000, 8)):
+        lay, floats = sharded.shard_layout(n, world, world - 1)
+        cap = sharded.owner_chunk(n, world)
+        assert lay.cap == cap and lay.num_ranks == world and lay.my_rank == world - 1
+        rows = world * cap
+        regions = [(lay.off_count, world), (lay.off_splat, rows * 12), (lay.off_radii, rows), (lay.off_gid, rows),
+                   (lay.off_dsplat, rows * 12), (lay.off_weight, rows), (lay.off_pcount, rows)]
+        end = 0
+        for off, size in regions:
+            assert off % 64 == 0 and off >= end, (off, end)       # 256-byte aligned, in order, no overlap
+            end = off + size
+        assert floats >= end
+        # every rank computes the same offsets (only my_rank differs)
+        other, floats2 = sharded.shard_layout(n, world, 0)
+        assert floats2 == floats and all(getattr(other, f) == getattr(lay, f) for f, _ in _capi.LgrShardLayout._fields_ if f != 'my_rank')
+        # a shard never exceeds the rows one (source, owner) region can hold
+        assert all(hi - lo <= cap for lo, hi in sharded.owner_partition(n, world))
+
+
+def test_shard_send_scratch_size_matches_header_macro():
+    import re
+    from log_b200 import _capi
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'log_b200_raster.h')).read()
+    assert re.search(r'#define LGR_SHARD_SEND_INTS\(n_local, r\) \(2 \* \(int64_t\)\(r\) \* \(\(\(\(n_local\) > 0 \? \(n_local\) : 1\) \+ 255\) / 256\) \+ \(r\)\)', hdr)
+    for n, r in ((0, 4), (1, 1), (256, 2), (257, 2), (1_250_048, 8)):
+        assert _capi.shard_send_ints(n, r) == 2 * r * ((max(n, 1) + 255) // 256) + r
+    assert int(re.search(r'#define LGR_SHARD_MAX_RANKS (\d+)', hdr).group(1)) == _capi.LGR_SHARD_MAX_RANKS
+
+
+def test_splat_exchange_rejects_cpu_buffers_and_bad_peer_lists():
+    import pytest
+    from log_b200 import sharded
+    _, floats = sharded.shard_layout(1000, 2, 0)
+    buf = torch.zeros(floats)
+    with pytest.raises(ValueError):
+        sharded.SplatExchange(1000, 64, 0, 2, buf, [buf.data_ptr(), 0], barrier=lambda: None)      # CPU tensor
+    with pytest.raises(ValueError):
+        sharded.SplatExchange(1000, 64, 0, 40, buf, [0] * 40, barrier=lambda: None)                # too many ranks
