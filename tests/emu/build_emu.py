@@ -1,0 +1,98 @@
+"""Translate the integer / byte CUDA kernels (log_b200/csrc/lgr_bin.cu, lgr_shard.cu) to host C++ on top of the SIMT
+emulation in tests/emu/cuda_runtime.h and build tests/emu/_build/libemu.so.  Test infrastructure only.
+
+The translation touches exactly two constructs, mechanically:
+  kernel<<<grid, block, smem, stream>>>(args);   ->  emu::launch(dim3(grid), dim3(block), smem, [=]() { kernel(args); });
+  extern __shared__ T name[];                    ->  T* name = reinterpret_cast<T*>(emu::dyn_smem());
+Everything else (the kernel bodies) is compiled verbatim.
+"""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, 'log_b200', 'csrc')
+BUILD = os.path.join(HERE, '_build')
+LIB = os.path.join(BUILD, 'libemu.so')
+SOURCES = ['lgr_bin.cu', 'lgr_shard.cu']
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, ''
+    for ch in s:
+        if ch in '([{':
+            depth += 1
+        elif ch in ')]}':
+            depth -= 1
+        if ch == ',' and depth == 0:
+            out.append(cur.strip())
+            cur = ''
+        else:
+            cur += ch
+    out.append(cur.strip())
+    return out
+
+
+def translate(src: str) -> str:
+    src = re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'\1* \2 = reinterpret_cast<\1*>(emu::dyn_smem());', src)
+    out, pos = '', 0
+    while True:
+        k = src.find('<<<', pos)
+        if k < 0:
+            return out + src[pos:]
+        # kernel name (with optional template arguments) ends right before '<<<'
+        j = k
+        while src[j - 1].isspace():
+            j -= 1
+        if src[j - 1] == '>':
+            depth, j = 1, j - 1
+            while depth:
+                j -= 1
+                depth += {'>': 1, '<': -1}.get(src[j], 0)
+        while src[j - 1].isalnum() or src[j - 1] in '_:':
+            j -= 1
+        name = src[j:k].strip()
+        e = src.index('>>>', k)
+        cfg = _split_top(src[k + 3:e])
+        assert 2 <= len(cfg) <= 4, cfg
+        a = e + 3
+        while src[a].isspace():
+            a += 1
+        assert src[a] == '(', src[a:a + 40]
+        depth, b = 1, a
+        while depth:
+            b += 1
+            depth += {'(': 1, ')': -1}.get(src[b], 0)
+        args = src[a + 1:b]
+        smem = cfg[2] if len(cfg) > 2 else '0'
+        out += src[pos:j] + f'emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}), [=]() {{ {name}({args}); }})'
+        pos = b + 1
+
+
+def build(force=False):
+    os.makedirs(BUILD, exist_ok=True)
+    deps = [os.path.join(CSRC, f) for f in SOURCES] + [os.path.join(CSRC, 'lgr_common.cuh'), os.path.join(CSRC, 'lgr_prof.cuh'),
+                                                       os.path.join(HERE, 'cuda_runtime.h'), os.path.join(HERE, 'emu_api.cpp'),
+                                                       os.path.abspath(__file__), os.path.join(ROOT, 'include', 'log_b200_raster.h')]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    objs = []
+    for f in SOURCES:
+        cpp = os.path.join(BUILD, f.replace('.cu', '.emu.cpp'))
+        with open(cpp, 'w') as fh:
+            fh.write(f'// generated from log_b200/csrc/{f} by tests/emu/build_emu.py -- do not edit\n')
+            fh.write(translate(open(os.path.join(CSRC, f)).read()))
+        objs.append(cpp)
+    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-w', '-I', HERE, '-I', CSRC, '-o', LIB + '.tmp'] + objs + \
+          [os.path.join(HERE, 'emu_api.cpp')]
+    env = dict(os.environ)
+    env.pop('CC', None)
+    env.pop('CXX', None)
+    subprocess.check_call(cmd, env=env)
+    os.replace(LIB + '.tmp', LIB)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force=True))

@@ -1,0 +1,302 @@
+// Minimal SIMT emulation of the CUDA constructs used by the integer / byte kernels of log_b200 (lgr_bin.cu,
+// lgr_shard.cu), so that `-m "not gpu"` tests can execute the REAL kernel source on the CPU.  Test infrastructure only:
+// nothing in the product links against this.
+//
+// Model: one fiber (ucontext) per CUDA thread, CTAs run one after the other on a single OS thread.  A fiber runs until
+// it reaches a barrier (__syncthreads / any *_sync warp collective) or returns; barriers release when every LIVE
+// thread of the scope has arrived (threads that returned no longer count, as on the GPU).  A barrier nobody can
+// complete is reported as a deadlock -- i.e. divergent-barrier bugs fail loudly here.  Scheduling is deterministic;
+// atomics are plain read-modify-writes.  Not modelled: memory-model races, warp-synchronous timing, performance.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <functional>
+#include <type_traits>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __constant__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) alignas(n)
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t*) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+
+namespace emu {
+
+enum State { READY = 0, WAIT_CTA, WAIT_WARP, DONE };
+
+struct Fiber {
+  ucontext_t ctx;
+  char* stack = nullptr;
+  dim3 tid;
+  int state = READY;
+};
+
+struct Cta {
+  std::vector<Fiber> fibers;
+  int nthreads = 0, alive = 0, cta_waiting = 0;
+  int warp_alive[32], warp_waiting[32];
+  unsigned long long scratch[32][32];   // [warp][lane] exchange slots of the warp collectives
+  int cta_acc = 0;                       // __syncthreads_or / _and / _count accumulator
+  int cta_result = 0;
+  std::function<void()> body;
+  dim3 block_idx, block_dim, grid_dim;
+  char* dyn = nullptr;
+};
+
+inline Cta*& cta() { static Cta* c = nullptr; return c; }
+inline Fiber*& cur() { static Fiber* f = nullptr; return f; }
+inline ucontext_t& sched_ctx() { static ucontext_t c; return c; }
+inline void* dyn_smem() { return cta()->dyn; }
+
+inline void yield() { swapcontext(&cur()->ctx, &sched_ctx()); }
+
+inline void release_cta(Cta* c) {
+  for (auto& f : c->fibers) if (f.state == WAIT_CTA) f.state = READY;
+  c->cta_waiting = 0;
+}
+inline void release_warp(Cta* c, int w) {
+  for (int l = 0; l < 32 && w * 32 + l < c->nthreads; l++)
+    if (c->fibers[w * 32 + l].state == WAIT_WARP) c->fibers[w * 32 + l].state = READY;
+  c->warp_waiting[w] = 0;
+}
+
+inline void barrier_cta() {
+  Cta* c = cta();
+  if (++c->cta_waiting == c->alive) { release_cta(c); return; }
+  cur()->state = WAIT_CTA;
+  yield();
+}
+inline void barrier_warp() {
+  Cta* c = cta();
+  const int w = cur()->tid.x >> 5;
+  if (++c->warp_waiting[w] == c->warp_alive[w]) { release_warp(c, w); return; }
+  cur()->state = WAIT_WARP;
+  yield();
+}
+
+inline void fiber_entry() {
+  Cta* c = cta();
+  c->body();
+  Fiber* f = cur();
+  f->state = DONE;
+  const int w = f->tid.x >> 5;
+  c->alive--; c->warp_alive[w]--;
+  if (c->cta_waiting > 0 && c->cta_waiting == c->alive) release_cta(c);
+  if (c->warp_waiting[w] > 0 && c->warp_waiting[w] == c->warp_alive[w]) release_warp(c, w);
+  swapcontext(&f->ctx, &sched_ctx());
+}
+
+constexpr size_t STACK = 192 * 1024;
+
+template <class F>
+inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
+  if (grid.y != 1 || grid.z != 1 || block.y != 1 || block.z != 1) { fprintf(stderr, "emu: 1-D launches only\n"); abort(); }
+  Cta c;
+  c.nthreads = (int)block.x;
+  c.fibers.resize(c.nthreads);
+  for (auto& f : c.fibers) f.stack = (char*)malloc(STACK);
+  std::vector<char> dyn(smem + 64);
+  c.dyn = (char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
+  c.block_dim = block; c.grid_dim = grid;
+  c.body = fn;
+  cta() = &c;
+  for (unsigned b = 0; b < grid.x; b++) {
+    c.block_idx = dim3(b);
+    c.alive = c.nthreads; c.cta_waiting = 0; c.cta_acc = 0;
+    for (int w = 0; w < 32; w++) { c.warp_waiting[w] = 0; c.warp_alive[w] = 0; }
+    for (int t = 0; t < c.nthreads; t++) {
+      Fiber& f = c.fibers[t];
+      f.tid = dim3((unsigned)t); f.state = READY;
+      c.warp_alive[t >> 5]++;
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = STACK; f.ctx.uc_link = nullptr;
+      makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+    }
+    while (c.alive > 0) {
+      bool ran = false;
+      for (int t = 0; t < c.nthreads; t++) {
+        Fiber& f = c.fibers[t];
+        if (f.state != READY) continue;
+        ran = true;
+        cur() = &f;
+        swapcontext(&sched_ctx(), &f.ctx);
+      }
+      if (!ran) {
+        fprintf(stderr, "emu: DEADLOCK in block %u: %d threads alive, %d at __syncthreads", b, c.alive, c.cta_waiting);
+        for (int w = 0; w < 32; w++) if (c.warp_waiting[w]) fprintf(stderr, "; warp %d: %d of %d at a warp collective", w, c.warp_waiting[w], c.warp_alive[w]);
+        fprintf(stderr, "\n");
+        abort();
+      }
+    }
+  }
+  for (auto& f : c.fibers) free(f.stack);
+  cta() = nullptr; cur() = nullptr;
+}
+
+// ---- warp collectives -------------------------------------------------------------------------------------------
+inline int lane_id() { return cur()->tid.x & 31; }
+inline int warp_id() { return cur()->tid.x >> 5; }
+inline bool lane_alive(int l) {
+  Cta* c = cta();
+  const int t = warp_id() * 32 + l;
+  return t < c->nthreads && c->fibers[t].state != DONE;
+}
+template <class T> inline void publish(T v) {
+  static_assert(sizeof(T) <= 8, "collective payload");
+  unsigned long long u = 0; memcpy(&u, &v, sizeof(T));
+  cta()->scratch[warp_id()][lane_id()] = u;
+  barrier_warp();
+}
+template <class T> inline T peek(int l) { T v; memcpy(&v, &cta()->scratch[warp_id()][l], sizeof(T)); return v; }
+}  // namespace emu
+
+#define threadIdx (emu::cur()->tid)
+#define blockIdx (emu::cta()->block_idx)
+#define blockDim (emu::cta()->block_dim)
+#define gridDim (emu::cta()->grid_dim)
+
+inline void __syncthreads() { emu::barrier_cta(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier_warp(); }
+inline void __trap() { fprintf(stderr, "emu: __trap()\n"); abort(); }
+
+inline int __syncthreads_reduce(int pred, int mode) {   // 0 or, 1 and, 2 count
+  emu::Cta* c = emu::cta();
+  // phase 1: everybody contributes
+  if (c->cta_waiting == 0) c->cta_acc = (mode == 1) ? 1 : 0;
+  if (mode == 0) c->cta_acc |= (pred != 0); else if (mode == 1) c->cta_acc &= (pred != 0); else c->cta_acc += (pred != 0);
+  emu::barrier_cta();
+  const int r = c->cta_acc;
+  emu::barrier_cta();          // nobody starts the next reduction before everyone has read this one
+  return r;
+}
+inline int __syncthreads_or(int p) { return __syncthreads_reduce(p, 0); }
+inline int __syncthreads_and(int p) { return __syncthreads_reduce(p, 1); }
+inline int __syncthreads_count(int p) { return __syncthreads_reduce(p, 2); }
+
+inline unsigned __ballot_sync(unsigned, int pred) {
+  emu::publish<unsigned>(pred ? 1u : 0u);
+  unsigned r = 0;
+  for (int l = 0; l < 32; l++) if (emu::lane_alive(l) && emu::peek<unsigned>(l)) r |= 1u << l;
+  emu::barrier_warp();
+  return r;
+}
+inline int __all_sync(unsigned m, int pred) {
+  emu::publish<unsigned>(pred ? 1u : 0u);
+  int r = 1;
+  for (int l = 0; l < 32; l++) if (emu::lane_alive(l) && !emu::peek<unsigned>(l)) r = 0;
+  emu::barrier_warp();
+  return r;
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) {
+  emu::publish<T>(v);
+  const T r = emu::peek<T>(src & 31);
+  emu::barrier_warp();
+  return r;
+}
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+  emu::publish<T>(v);
+  const int l = emu::lane_id();
+  const T r = l >= (int)d ? emu::peek<T>(l - (int)d) : v;
+  emu::barrier_warp();
+  return r;
+}
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d) {
+  emu::publish<T>(v);
+  const int l = emu::lane_id();
+  const T r = l + (int)d < 32 ? emu::peek<T>(l + (int)d) : v;
+  emu::barrier_warp();
+  return r;
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) {
+  emu::publish<T>(v);
+  const T r = emu::peek<T>((emu::lane_id() ^ m) & 31);
+  emu::barrier_warp();
+  return r;
+}
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+  emu::publish<unsigned>(v);
+  unsigned r = 0;
+  for (int l = 0; l < 32; l++) if (emu::lane_alive(l) && emu::peek<unsigned>(l) == v) r |= 1u << l;
+  emu::barrier_warp();
+  return r;
+}
+template <class T> inline T emu_reduce(T v, int op) {
+  emu::publish<T>(v);
+  T r = v; bool first = true;
+  for (int l = 0; l < 32; l++) if (emu::lane_alive(l)) {
+    const T x = emu::peek<T>(l);
+    if (first) { r = x; first = false; } else r = op == 0 ? (T)(r + x) : (x > r ? x : r);
+  }
+  emu::barrier_warp();
+  return r;
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v) { return emu_reduce<unsigned>(v, 0); }
+inline int __reduce_add_sync(unsigned, int v) { return emu_reduce<int>(v, 0); }
+inline unsigned __reduce_max_sync(unsigned, unsigned v) { return emu_reduce<unsigned>(v, 1); }
+inline int __reduce_max_sync(unsigned, int v) { return emu_reduce<int>(v, 1); }
+
+// ---- scalar intrinsics ------------------------------------------------------------------------------------------
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
+inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
+inline float __fdividef(float a, float b) { return a / b; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+
+template <class T> inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }
+inline int atomicAdd(int* p, unsigned v) { const int o = *p; *p = o + (int)v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { const T o = *p; if (v > o) *p = v; return o; }
+
+#define EMU_MINMAX(T)                                   \
+  inline T min(T a, T b) { return b < a ? b : a; }      \
+  inline T max(T a, T b) { return a < b ? b : a; }
+EMU_MINMAX(int)
+EMU_MINMAX(unsigned)
+EMU_MINMAX(long long)
+EMU_MINMAX(unsigned long long)
+EMU_MINMAX(long)
+EMU_MINMAX(unsigned long)
+EMU_MINMAX(float)
+#undef EMU_MINMAX
+inline long long min(long long a, int b) { return a < b ? a : b; }
+inline long long min(int a, long long b) { return a < b ? a : b; }
+inline long min(long a, int b) { return a < b ? a : b; }
+inline long min(int a, long b) { return a < b ? a : b; }
+inline long long max(long long a, int b) { return a < b ? (long long)b : a; }
+inline long max(long a, int b) { return a < b ? (long)b : a; }

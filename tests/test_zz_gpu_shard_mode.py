@@ -7,8 +7,9 @@ ranks produce must equal the ordinary single-GPU call:
     same records in the same (depth, global index) order);
   * gradients: to fp32 summation order (the 2D gradients are accumulated per band and then summed).
 
-STATUS: written at the very end of round 1, after the GPU budget was spent -- it compiles and the host logic is covered
-by tests/test_sharded_cpu.py, but it has not yet run on hardware.  Hence the non-strict xfail (an XPASS is the expected
+STATUS: written at the very end of round 1, after the GPU budget was spent.  The exchange kernels themselves are checked
+bit-exactly on the CPU SIMT emulation (tests/test_emulated_kernels.py::test_shard_exchange_emulated) and the host logic
+by tests/test_sharded_cpu.py, but the path has not yet run on hardware.  Hence the non-strict xfail (an XPASS is the expected
 outcome); the file sorts last so that nothing it does can disturb the verified tests.  `--runxfail` shows real failures.
 """
 import numpy as np
