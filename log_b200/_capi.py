@@ -51,15 +51,8 @@ class LgrError(RuntimeError):
 _lib = None
 
 
-def load():
-    """Load liblog_b200_raster.so; raise (never fall back) if it is absent."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise LgrError(f'{LIB_PATH} not found: run `python -m log_b200.build` (or __graft_entry__.build()). '
-                       'log_b200 has no CPU fallback.')
-    lib = ctypes.CDLL(LIB_PATH)
+def bind(lib):
+    """Declare restype / argtypes of every entry point of include/log_b200_raster.h on a loaded library handle."""
     lib.lgr_abi_version.restype = ctypes.c_int
     lib.lgr_sort_smem_capacity.restype = _i32
     lib.lgr_compute_radius.restype = ctypes.c_int
@@ -96,10 +89,34 @@ def load():
     lib.lgr_profile_collect.argtypes = [_vp, _vp, _i32]
     lib.lgr_profile_kernel_name.restype = ctypes.c_char_p
     lib.lgr_profile_kernel_name.argtypes = [ctypes.c_int]
+    return lib
+
+
+def load():
+    """Load liblog_b200_raster.so; raise (never fall back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LgrError(f'{LIB_PATH} not found: run `python -m log_b200.build` (or __graft_entry__.build()). '
+                       'log_b200 has no CPU fallback.')
+    lib = bind(ctypes.CDLL(LIB_PATH))
     if lib.lgr_abi_version() != LGR_ABI_VERSION:
         raise LgrError('liblog_b200_raster.so ABI version mismatch: rebuild with `python -m log_b200.build --force`')
     _lib = lib
     return lib
+
+
+def current_stream():
+    """The caller's CUDA stream (torch's current stream) as the void* the C ABI takes."""
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name):
+    """Every tensor handed to the C ABI must live on a CUDA device: there is no CPU path in this package."""
+    if not t.is_cuda:
+        raise LgrError(f'{name} is on {t.device}: log_b200 rasterises on CUDA only (no CPU fallback)')
 
 
 def check(rc, what):

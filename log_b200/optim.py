@@ -16,8 +16,7 @@ def sparse_adam_step_(param, grad, exp_avg, exp_avg_sq, index, step, lr, max_exp
     index: (K,) int64 unique rows; grad: (K, ...) gradient of the gathered rows param[index]."""
     lib = _capi.load()
     for name, t in (('param', param), ('grad', grad), ('exp_avg', exp_avg), ('exp_avg_sq', exp_avg_sq)):
-        if not t.is_cuda:
-            raise _capi.LgrError(f'{name} is on {t.device}: log_b200 has no CPU path')
+        _capi.require_cuda(t, name)
         if t.dtype != torch.float32 or not t.is_contiguous():
             raise TypeError(f'{name} must be contiguous float32')
     if index.dtype != torch.int64 or not index.is_contiguous():
@@ -29,5 +28,5 @@ def sparse_adam_step_(param, grad, exp_avg, exp_avg_sq, index, step, lr, max_exp
     p = lambda t: None if t is None or t.numel() == 0 else ctypes.c_void_p(t.data_ptr())
     _capi.check(lib.lgr_sparse_adam(k, c, p(index), p(grad), p(param), p(exp_avg), p(exp_avg_sq), p(max_exp_avg_sq),
                                     int(step), float(lr), float(beta1), float(beta2), float(eps),
-                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'lgr_sparse_adam')
+                                    _capi.current_stream()), 'lgr_sparse_adam')
     return param

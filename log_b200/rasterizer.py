@@ -51,8 +51,7 @@ def _f32c(t: Optional[torch.Tensor], name: str, device=None):
     """float32, contiguous, 16-byte aligned CUDA tensor (what the C ABI requires)."""
     if t is None:
         return None
-    if not t.is_cuda:
-        raise _capi.LgrError(f'{name} is on {t.device}: log_b200 rasterises on CUDA only (no CPU fallback)')
+    _capi.require_cuda(t, name)
     if device is not None and t.device != device:
         raise _capi.LgrError(f'{name} is on {t.device}, expected {device}')
     if t.dtype != torch.float32:
@@ -66,7 +65,7 @@ def _f32c(t: Optional[torch.Tensor], name: str, device=None):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _capi.current_stream()
 
 
 def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep,

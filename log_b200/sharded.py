@@ -54,11 +54,11 @@ def rows_to_shard(rows: torch.Tensor, lo: int, hi: int, shard: torch.Tensor = No
     lib = _capi.load()
     if shard is None:
         shard = torch.zeros((max(hi - lo, 0), _capi.LGR_ROW_FLOATS), dtype=torch.float32, device=rows.device)
-    if rows.shape[0]:
+    if rows.shape[0] and hi > lo:      # an owner past the end of the index range holds no Gaussians: nothing to add
         rows = rows.contiguous()
         _capi.check(lib.lgr_grad_scatter_add(int(rows.shape[0]), ctypes.c_void_p(rows.data_ptr()), int(lo), int(hi),
                                              ctypes.c_void_p(shard.data_ptr()),
-                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'lgr_grad_scatter_add')
+                                             _capi.current_stream()), 'lgr_grad_scatter_add')
     return shard
 
 
@@ -133,7 +133,7 @@ class PeerExchange:
         shard = torch.zeros((self.chunk, _capi.LGR_ROW_FLOATS), dtype=torch.float32, device=self.stage.device)
         _capi.check(lib.lgr_grad_scatter_add_staged(ctypes.c_void_p(self.stage.data_ptr()), self.world, self.chunk, self.lo,
                                                     self.hi, ctypes.c_void_p(shard.data_ptr()),
-                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                                                    _capi.current_stream()),
                     'lgr_grad_scatter_add_staged')
         return shard
 
@@ -202,8 +202,9 @@ class SplatExchange:
         self.band = tile_row_partition(image_height, self.world)[self.rank]
         self.image_height = int(image_height)
         peer_ptrs = [int(p) for p in peer_ptrs]
-        if own_buffer.dtype != torch.float32 or own_buffer.numel() < self.floats or not own_buffer.is_cuda:
-            raise ValueError(f'the exchange buffer must be a float32 CUDA tensor of >= {self.floats} elements')
+        _capi.require_cuda(own_buffer, 'the exchange buffer')
+        if own_buffer.dtype != torch.float32 or own_buffer.numel() < self.floats:
+            raise ValueError(f'the exchange buffer must be a float32 tensor of >= {self.floats} elements')
         if len(peer_ptrs) != self.world or peer_ptrs[self.rank] != own_buffer.data_ptr():
             raise ValueError('peer_ptrs needs one address per rank, entry `rank` being own_buffer')
         self.buf, self.barrier = own_buffer, barrier

@@ -15,7 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'log_b200', 'csrc')
 BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(BUILD, 'libemu.so')
-SOURCES = ['lgr_bin.cu', 'lgr_shard.cu']
+SOURCES = ['lgr_bin.cu', 'lgr_shard.cu', 'lgr_project.cu', 'lgr_blend.cu', 'lgr_optim.cu', 'lgr_capi.cu']
+# inline-PTX helpers of lgr_blend.cu, replaced by tests/emu/emu_blend_helpers.h
+PTX_HELPERS = ['ex2_approx', 'rcp_approx', 'smem_u32', 'lds_f4', 'lds_f2', 'pin_reg', 'red_shared_max_u32', 'red_shared_add_f32']
 
 
 def _split_top(s):
@@ -34,7 +36,27 @@ def _split_top(s):
     return out
 
 
+def drop_ptx_helpers(src: str) -> str:
+    """Remove the definitions of PTX_HELPERS (whole functions) and include the host versions in their place."""
+    first = True
+    for name in PTX_HELPERS:
+        m = re.search(r'^__device__ __forceinline__ [\w ]+? ' + name + r'\(', src, flags=re.M)
+        if not m:
+            continue
+        a = src.index('{', m.end())
+        depth, b = 1, a
+        while depth:
+            b += 1
+            depth += {'{': 1, '}': -1}.get(src[b], 0)
+        repl = '}  // namespace lgr\n#include "emu_blend_helpers.h"\nnamespace lgr {\n' if first else ''
+        first = False
+        src = src[:m.start()] + repl + src[b + 1:]
+    assert 'asm' not in re.sub(r'//.*', '', src), 'inline PTX left in the translated source'
+    return src
+
+
 def translate(src: str) -> str:
+    src = drop_ptx_helpers(src)
     src = re.sub(r'extern\s+__shared__\s+(\w+)\s+(\w+)\[\];', r'\1* \2 = reinterpret_cast<\1*>(emu::dyn_smem());', src)
     out, pos = '', 0
     while True:
@@ -73,7 +95,7 @@ def translate(src: str) -> str:
 def build(force=False):
     os.makedirs(BUILD, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in SOURCES] + [os.path.join(CSRC, 'lgr_common.cuh'), os.path.join(CSRC, 'lgr_prof.cuh'),
-                                                       os.path.join(HERE, 'cuda_runtime.h'), os.path.join(HERE, 'emu_api.cpp'),
+                                                       os.path.join(HERE, 'cuda_runtime.h'), os.path.join(HERE, 'emu_api.cpp'), os.path.join(HERE, 'emu_blend_helpers.h'),
                                                        os.path.abspath(__file__), os.path.join(ROOT, 'include', 'log_b200_raster.h')]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB

@@ -27,7 +27,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
   unsigned x, y, z;
@@ -300,3 +300,16 @@ inline long min(long a, int b) { return a < b ? a : b; }
 inline long min(int a, long b) { return a < b ? a : b; }
 inline long long max(long long a, int b) { return a < b ? (long long)b : a; }
 inline long max(long a, int b) { return a < b ? (long)b : a; }
+
+// ---- float intrinsics (correctly rounded on the host as on the device) --------------------------------------------
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float4 atomicAdd(float4* p, float4 v) {
+  const float4 o = *p;
+  p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
+  return o;
+}

@@ -1,0 +1,73 @@
+"""CPU: the `-m gpu` parity tests of tests/test_gpu_parity.py (and the shard-mode host class) re-run at small sizes with
+the `emulated_backend` fixture: the real host code (log_b200/rasterizer.py autograd function, sharded.py, optim.py)
+drives the real kernel source and C entry points compiled for the SIMT emulation in tests/emu.
+
+These runs check logic without a GPU -- argument plumbing, buffer sizing, autograd wiring, band / shard bookkeeping, the
+kernels' control flow -- with IEEE float32 arithmetic but exact exp2 / division in place of ex2.approx / rcp.approx and
+sequential atomics.  They do NOT replace the hardware runs: the same test functions run unmodified under `-m gpu`.
+"""
+import pytest
+import torch
+
+import shard_checks
+import test_gpu_parity as gp
+import test_sparse_adam as sa
+
+
+@pytest.mark.parametrize('case', [
+    (96, 64, 300, 12.0, 0, 'fork', True, False),       # big splats: many tiles per Gaussian
+    (75, 50, 500, 3.0, 3, 'stock', True, True),        # SH degree 3, rotated camera, image not a multiple of 16
+    (64, 48, 400, 2.0, 2, 'fork', False, False),       # fork with use_filter=False
+])
+def test_public_api_parity(emulated_backend, case):
+    gp.test_forward_backward_parity(True, *case)
+
+
+def test_scale_modifier_background_empty_and_culled(emulated_backend):
+    gp.test_scale_modifier_and_background(True, size=(64, 48, 300))
+    gp.test_empty_input(True)
+    gp.test_all_culled_and_single(True)
+
+
+def test_depth_ties_and_linearity(emulated_backend):
+    gp.test_depth_ties_are_broken_by_index(True, size=(48, 32, 500))
+    gp.test_backward_is_linear_in_the_cotangent(True, size=(64, 48, 400))
+
+
+def test_tile_row_shards(emulated_backend):
+    gp.test_tile_row_shards_sum_to_full(True, size=(48, 80, 500))
+
+
+@pytest.mark.parametrize('ci', [0, 1, 2])
+def test_compute_radius_golden_from_the_reference(emulated_backend, ci):
+    gp.test_compute_radius_matches_reference_golden(True, ci)
+
+
+def test_compute_radius_method_and_point_id_count(emulated_backend):
+    gp.test_fork_rasterizer_compute_radius_method(True, size=(80, 50, 700))
+    gp.test_point_id_count_equals_torch_unique(True, 80, 48, 500, 4.0)
+    gp.test_point_id_count_equals_torch_unique(True, 32, 32, 0, 3.0)
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_band_mode_rows_and_fused_push(emulated_backend, world):
+    gp.test_band_mode_rows_reproduce_dense_gradients(True, world, size=(64, 80, 900))
+    gp.test_fused_push_route_emulated_on_one_gpu(True, world, size=(64, 80, 900))
+
+
+def test_fused_activations(emulated_backend):
+    gp.test_fused_activations_match_torch_activations(True, size=(64, 48, 400))
+
+
+@pytest.mark.parametrize('prefix', sa.CASES[:4])
+def test_sparse_adam_golden_from_the_reference(emulated_backend, prefix):
+    sa.test_kernel_matches_reference(True, prefix)
+
+
+@pytest.mark.parametrize('world,deg,flavour', [(2, 0, 'fork'), (3, 0, 'fork'), (2, 3, 'stock'), (5, 0, 'fork')])
+def test_shard_mode_host_class(emulated_backend, world, deg, flavour):
+    shard_checks.run_two_steps(world, deg, flavour, size=(64, 80, 700))
+
+
+def test_shard_mode_empty_shards_and_bands(emulated_backend):
+    shard_checks.run_empty_shards_and_bands()

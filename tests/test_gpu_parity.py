@@ -20,7 +20,7 @@ import pytest
 import torch
 
 from oracle import c_oracle, torch_dense as O
-from util import f32_camera, rel, run_gpu
+from util import device, f32_camera, rel, run_gpu
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -126,8 +126,8 @@ def test_forward_backward_parity(built, W, H, n, r, deg, flavour, use_filter, ro
     check_all(got, ref, deg, flavour == 'fork', H * W, ref32)
 
 
-def test_scale_modifier_and_background(built):
-    W, H, n = 128, 80, 800
+def test_scale_modifier_and_background(built, size=(128, 80, 800)):
+    W, H, n = size
     cam = f32_camera(O.make_camera(W, H, bg=(1.0, 1.0, 1.0)))._replace(scale_modifier=1.5)
     sc = f32_scene(O.make_scene(n, W, H, 3.0, seed=5))
     G = O.make_cotangent(3, H, W)
@@ -164,10 +164,10 @@ def test_all_culled_and_single(built):
     check_all(got, ref, 0, True, H * W, oracle(cam, sc, G, O.FILTER_MAX, 0, dtype=np.float32))
 
 
-def test_depth_ties_are_broken_by_index(built):
+def test_depth_ties_are_broken_by_index(built, size=(96, 64, 1200)):
     """All Gaussians on one plane z = const seen by an identity camera: every depth key is identical, so the order
     inside a tile must fall back to the Gaussian index (stable sort of index-ordered duplicates)."""
-    W, H, n = 96, 64, 1200
+    W, H, n = size
     cam = f32_camera(O.make_camera(W, H))
     sc = f32_scene(O.make_scene(n, W, H, 4.0, seed=9))
     z = 5.0
@@ -203,10 +203,10 @@ def test_long_tile_lists(built, n):
     check_all(drop(got, gs, ps), drop(ref, gs, ps), 0, True, H * W, drop(ref32, gs, ps))
 
 
-def test_tile_row_shards_sum_to_full(built):
+def test_tile_row_shards_sum_to_full(built, size=(160, 112, 3000)):
     """Multi-GPU sharding primitive: rendering tile rows [0,k) and [k,gy) separately and adding the results
     reproduces the un-sharded image and gradients."""
-    W, H, n = 160, 112, 3000
+    W, H, n = size
     cam = f32_camera(O.make_camera(W, H, bg=(0.2, 0.3, 0.4)))
     sc = f32_scene(O.make_scene(n, W, H, 5.0, seed=21))
     G = O.make_cotangent(3, H, W)
@@ -225,7 +225,7 @@ def test_compute_radius_matches_reference_golden(built, ci):
     """lgr_compute_radius vs the golden radii produced by the reference's geometry.compute_radius."""
     from log_b200 import compute_radius
     p = f'cam{ci}_'
-    dev = torch.device('cuda:0')
+    dev = device()
     W, H = GOLD[p + 'spec'][0], GOLD[p + 'spec'][1]
     fovx, fovy = GOLD[p + 'FoV']
     tx, ty = math.tan(fovx / 2), math.tan(fovy / 2)
@@ -241,22 +241,22 @@ def test_compute_radius_matches_reference_golden(built, ci):
     assert (got[~keep & margin] == 0).all()
 
 
-def test_fork_rasterizer_compute_radius_method(built):
+def test_fork_rasterizer_compute_radius_method(built, size=(320, 200, 4000)):
     """rasterizer.compute_radius(xyz, scaling, rotation) -- level_of_gaussian.py:59."""
     from log_b200 import GaussianRasterizer
     from util import settings_from_camera
-    W, H, n = 320, 200, 4000
+    W, H, n = size
     cam = f32_camera(O.make_camera(W, H))
     sc = f32_scene(O.make_scene(n, W, H, 3.0, seed=3))
-    dev = torch.device('cuda:0')
+    dev = device()
     r = GaussianRasterizer(settings_from_camera(cam, dev))
     got = r.compute_radius(*(sc[k].to(device=dev, dtype=torch.float32) for k in ('means3D', 'scales', 'rotations')))
     want = c_oracle.compute_radius(cam, sc['means3D'], sc['scales'], sc['rotations'])
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=3e-4, atol=1e-5)
 
 
-def test_backward_is_linear_in_the_cotangent(built):
-    W, H, n = 192, 128, 4000
+def test_backward_is_linear_in_the_cotangent(built, size=(192, 128, 4000)):
+    W, H, n = size
     cam = f32_camera(O.make_camera(W, H, bg=(0.3, 0.3, 0.3)))
     sc = f32_scene(O.make_scene(n, W, H, 4.0, seed=17))
     G1, G2 = O.make_cotangent(3, H, W, seed=1), O.make_cotangent(3, H, W, seed=2)
@@ -266,21 +266,21 @@ def test_backward_is_linear_in_the_cotangent(built):
 
 
 @pytest.mark.parametrize('world', [2, 3])
-def test_band_mode_rows_reproduce_dense_gradients(built, world):
+def test_band_mode_rows_reproduce_dense_gradients(built, world, size=(208, 144, 4001)):
     """Multi-GPU band mode, emulated on one GPU: every "rank" renders its tile band with the owner-grouped id lists,
     returns packed gradient rows; adding every rank's rows into the owner shards reproduces the dense gradients of the
     un-sharded run, and the bands add up to the full image."""
     from log_b200 import rasterize_backward, rasterize_forward, sharded
     from log_b200._capi import LGR_FILTER_MAX
     from util import settings_from_camera
-    W, H, n = 208, 144, 4001
+    W, H, n = size
     cam = f32_camera(O.make_camera(W, H, bg=(0.2, 0.3, 0.4)))
     sc = f32_scene(O.make_scene(n, W, H, 5.0, seed=33))
     G = O.make_cotangent(3, H, W)
     full = run_gpu(cam, sc, G)
     dense = sharded.pack_grads((full['dmeans3D'], full['dmeans2D'], full['dopacities'], full['dscales'], full['drotations'],
                                 full['dcolors']))
-    dev = torch.device('cuda:0')
+    dev = device()
     s = settings_from_camera(cam, dev)
     t = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in sc.items()}
     Gd = G.to(device=dev, dtype=torch.float32)
@@ -312,7 +312,7 @@ def test_point_id_count_equals_torch_unique(built, W, H, n, r):
     torch.unique over the H x W id map (renderer.py:156-159)."""
     from log_b200 import GaussianRasterizer, point_id_count
     from util import settings_from_camera
-    dev = torch.device('cuda:0')
+    dev = device()
     cam = f32_camera(O.make_camera(W, H))
     sc = O.make_scene(max(n, 1), W, H, r, seed=8, dtype=torch.float32)
     t = {k: v[:n].to(dev) for k, v in sc.items()}
@@ -329,21 +329,21 @@ def test_point_id_count_equals_torch_unique(built, W, H, n, r):
 
 
 @pytest.mark.parametrize('world', [2, 5])
-def test_fused_push_route_emulated_on_one_gpu(built, world):
+def test_fused_push_route_emulated_on_one_gpu(built, world, size=(224, 160, 6001)):
     """The fused exchange (project_bwd stores packed rows straight into the owners' staging buffers, then
     lgr_grad_scatter_add_staged) exercised on ONE GPU: the "peer" pointers are local buffers, one per virtual rank."""
     import ctypes
     from log_b200 import _capi, rasterize_backward, rasterize_forward, sharded
     from log_b200._capi import LGR_FILTER_MAX
     from util import settings_from_camera
-    W, H, n = 224, 160, 6001
+    W, H, n = size
     cam = f32_camera(O.make_camera(W, H, bg=(0.1, 0.2, 0.3)))
     sc = f32_scene(O.make_scene(n, W, H, 4.0, seed=41))
     G = O.make_cotangent(3, H, W)
     full = run_gpu(cam, sc, G)
     dense = sharded.pack_grads((full['dmeans3D'], full['dmeans2D'], full['dopacities'], full['dscales'], full['drotations'],
                                 full['dcolors']))
-    dev = torch.device('cuda:0')
+    dev = device()
     s = settings_from_camera(cam, dev)
     t = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in sc.items()}
     Gd, op = G.to(device=dev, dtype=torch.float32), t['opacities'].reshape(-1)
@@ -364,7 +364,7 @@ def test_fused_push_route_emulated_on_one_gpu(built, world):
         shard = torch.zeros((chunk, _capi.LGR_ROW_FLOATS), device=dev)
         _capi.check(lib.lgr_grad_scatter_add_staged(ctypes.c_void_p(stages[o].data_ptr()), world, chunk, lo, hi,
                                                     ctypes.c_void_p(shard.data_ptr()),
-                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'staged')
+                                                    _capi.current_stream()), 'staged')
         shards.append(shard[:hi - lo])
     got = torch.cat(shards)
     assert torch.isfinite(got).all()
@@ -372,13 +372,13 @@ def test_fused_push_route_emulated_on_one_gpu(built, world):
     assert torch.equal(got[:, 18].int(), full['radii'])
 
 
-def test_fused_activations_match_torch_activations(built):
+def test_fused_activations_match_torch_activations(built, size=(176, 112, 2500)):
     """with raw_params=True the kernels apply LoG's activations (activation.py:36-44: exp, sigmoid,
     F.normalize, SH2RGB) themselves; image and gradients w.r.t. the RAW parameters equal torch activations followed by
     the ordinary call, and the fp64 oracle differentiated through the same activations."""
     from log_b200 import GaussianRasterizer
     from util import settings_from_camera
-    W, H, n = 176, 112, 2500
+    W, H, n = size
     cam = f32_camera(O.make_camera(W, H, bg=(0.3, 0.2, 0.1)))
     sc = f32_scene(O.make_scene(n, W, H, 4.0, seed=55))
     g = torch.Generator().manual_seed(1)
@@ -387,7 +387,7 @@ def test_fused_activations_match_torch_activations(built):
                  colors=(sc['colors'] - 0.5) / O.C0)
     raw64 = {k: v.to(torch.float32).to(torch.float64) for k, v in raw64.items()}
     G = O.make_cotangent(3, H, W).to(torch.float32)
-    dev = torch.device('cuda:0')
+    dev = device()
     rast = GaussianRasterizer(settings_from_camera(cam, dev))
 
     def run(fused):

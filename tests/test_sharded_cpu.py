@@ -119,7 +119,8 @@ def test_splat_exchange_rejects_cpu_buffers_and_bad_peer_lists():
     from log_b200 import sharded
     _, floats = sharded.shard_layout(1000, 2, 0)
     buf = torch.zeros(floats)
-    with pytest.raises(ValueError):
-        sharded.SplatExchange(1000, 64, 0, 2, buf, [buf.data_ptr(), 0], barrier=lambda: None)      # CPU tensor
+    from log_b200._capi import LgrError
+    with pytest.raises(LgrError):
+        sharded.SplatExchange(1000, 64, 0, 2, buf, [buf.data_ptr(), 0], barrier=lambda: None)      # CPU tensor: no CPU path
     with pytest.raises(ValueError):
         sharded.SplatExchange(1000, 64, 0, 40, buf, [0] * 40, barrier=lambda: None)                # too many ranks

@@ -41,7 +41,8 @@ def test_oracle_matches_reference(prefix):
 def test_kernel_matches_reference(built, prefix):
     from log_b200.optim import sparse_adam_step_
     hyper, ams = case(prefix)
-    dev = torch.device('cuda:0')
+    from util import device
+    dev = device()
     t = lambda k: torch.from_numpy(G[prefix + k]).to(dev)
     p, m, v, vm = t('param_in'), t('m_in'), t('v_in'), t('vmax_in')
     sparse_adam_step_(p, t('grad'), m, v, t('index'), hyper['step'], hyper['lr'], max_exp_avg_sq=vm if ams else None,

@@ -5,6 +5,13 @@ import torch
 from oracle import torch_dense as O
 
 
+DEVICE = ['cuda:0']      # tests/conftest.py:emulated_backend switches this to 'cpu' (SIMT emulation of the kernels)
+
+
+def device():
+    return torch.device(DEVICE[0])
+
+
 def rel(a, b):
     """Norm-wise relative error ||a-b|| / ||b||."""
     a = np.asarray(a.detach().cpu().numpy() if hasattr(a, 'detach') else a, dtype=np.float64)
@@ -28,10 +35,10 @@ def f32_camera(cam):
                         tanfovx=float(np.float32(cam.tanfovx)), tanfovy=float(np.float32(cam.tanfovy)))
 
 
-def run_gpu(cam, scene, G=None, flavour='fork', use_filter=True, sh_degree=0, device='cuda:0', tile_rows=None):
+def run_gpu(cam, scene, G=None, flavour='fork', use_filter=True, sh_degree=0, device=None, tile_rows=None):
     """Forward (+backward if G) through the public GaussianRasterizer API.  scene: dict of float tensors."""
     from log_b200 import GaussianRasterizer, StockGaussianRasterizer
-    dev = torch.device(device)
+    dev = torch.device(device or DEVICE[0])
     s = settings_from_camera(cam, dev, sh_degree)
     rast = (GaussianRasterizer if flavour == 'fork' else StockGaussianRasterizer)(s)
     rast.tile_rows = tile_rows
@@ -58,5 +65,6 @@ def run_gpu(cam, scene, G=None, flavour='fork', use_filter=True, sh_degree=0, de
             res['dshs'] = t['shs'].grad
         else:
             res['dcolors'] = t['colors'].grad
-    torch.cuda.synchronize()
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
     return res
