@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 12
+#define LGR_ABI_VERSION 13
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -204,6 +204,32 @@ int lgr_shard_return_rows(const lgr_shard_layout* layout, const float* exchange_
 int lgr_shard_gather(const lgr_view* view, const lgr_shard_layout* layout, int64_t n_local, const float* splat_d,
                      const int32_t* radii_d, const int32_t* send_scratch_d, const float* exchange_d,
                      float* dsplat_local_d, float* point_weight_d, int32_t* point_count_d, void* stream);
+
+/* ---- Level-of-Gaussian tree traversal ----------------------------------------------------------
+ * Replaces TensorTree.traverse / _query_tree_torch (LoG/model/tensor_tree.py:132-186) and the per-level
+ * model.compute_radius calls inside it (LoG/model/level_of_gaussian.py:64-93: gather + exp / F.normalize activations
+ * + compute_radius_cuda) by level-synchronous kernels with no host synchronisation between levels.
+ *   node_index_d (num_points) int32: row of tree_d holding the children of a point, -1 = leaf
+ *   tree_d (num_nodes, max_child) int32: child point ids, -1 = empty slot
+ *   xyz_d (num_points,3); scaling_raw_d (num_points,3) RAW (scale = exp(raw), the 'exp' activation of activation.py:7);
+ *   rotation_raw_d (num_points,4) RAW (normalised as F.normalize does); matrices / focal / tan_fov as lgr_compute_radius
+ *   root_index_d (num_roots) int64: the visible roots, in the order the reference passes them
+ *   max_depth: the reference's max_depth argument (child levels descended: min(max_level, max_depth))
+ * Output: index_out_d (capacity num_points) int64 = exactly the reference's index_concat (same elements, same order:
+ * kept roots, then the kept nodes of level 1, 2, ... in parent/child-slot order, then the nodes cut off at the depth
+ * limit); *count_out_d their number.  scratch_d: LGR_TREE_SCRATCH_INTS(num_points, S) int32 with
+ * S = max(num_roots, num_nodes * max_child). */
+typedef struct lgr_tree {
+  int64_t num_points, num_nodes;
+  int32_t max_child, max_level;
+  const int32_t* node_index_d;
+  const int32_t* tree_d;
+} lgr_tree;
+#define LGR_TREE_SCRATCH_INTS(p, s) (8 + 2 * (int64_t)(p) + (int64_t)(s) + 2 * (((int64_t)(s) + 255) / 256) + 2 + ((int64_t)(s) + 3) / 4)
+int lgr_tree_traverse(const lgr_tree* tree, const float* xyz_d, const float* scaling_raw_d, const float* rotation_raw_d,
+                      const float* projmatrix_d, const float* viewmatrix_d, float focal_x, float focal_y, float tan_fovx,
+                      float tan_fovy, const int64_t* root_index_d, int64_t num_roots, float min_resolution_pixel,
+                      int32_t max_depth, int32_t* scratch_d, int64_t* index_out_d, int64_t* count_out_d, void* stream);
 
 /* Sorted compaction of the non-zero entries of point_count_d: ids_out_d / counts_out_d (capacity min(N, H*W)) receive the
  * ids in ascending order and their pixel counts, *num_out_d their number.  Equals

@@ -12,14 +12,14 @@ LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
 LGR_TILE_SCRATCH_INTS = 33
-LGR_ABI_VERSION = 12
+LGR_ABI_VERSION = 13
 LGR_STAGE_HEADER_FLOATS = 64
 LGR_ROW_FLOATS = 20
 
 EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
            'lgr_forward_render', 'lgr_backward', 'lgr_grad_scatter_add', 'lgr_grad_scatter_add_staged', 'lgr_point_compact', 'lgr_sparse_adam', 'lgr_profile_enable', 'lgr_profile_collect',
            'lgr_profile_kernel_name', 'lgr_shard_send', 'lgr_shard_recv_bin', 'lgr_blend_backward', 'lgr_shard_return_rows',
-           'lgr_shard_gather')
+           'lgr_shard_gather', 'lgr_tree_traverse')
 LGR_SHARD_MAX_RANKS = 32
 LGR_PROFILE_KERNELS = 8
 
@@ -37,6 +37,17 @@ class LgrShardLayout(ctypes.Structure):
     """struct lgr_shard_layout (multi-GPU shard mode): float offsets into every rank's exchange buffer."""
     _fields_ = [('num_ranks', _i32), ('my_rank', _i32), ('cap', _i64), ('off_count', _i64), ('off_splat', _i64),
                 ('off_radii', _i64), ('off_gid', _i64), ('off_dsplat', _i64), ('off_weight', _i64), ('off_pcount', _i64)]
+
+
+class LgrTree(ctypes.Structure):
+    """struct lgr_tree: the level-of-Gaussian tree tables (LoG/model/tensor_tree.py)."""
+    _fields_ = [('num_points', _i64), ('num_nodes', _i64), ('max_child', _i32), ('max_level', _i32),
+                ('node_index_d', _vp), ('tree_d', _vp)]
+
+
+def tree_scratch_ints(num_points, slots):
+    """LGR_TREE_SCRATCH_INTS."""
+    return 8 + 2 * num_points + slots + 2 * ((slots + 255) // 256) + 2 + (slots + 3) // 4
 
 
 def shard_send_ints(n_local, r):
@@ -83,6 +94,9 @@ def bind(lib):
     lib.lgr_shard_return_rows.argtypes = [lay, _vp, _i64, _vp, _i32, _i64, _vp, _vp]
     lib.lgr_shard_gather.restype = ctypes.c_int
     lib.lgr_shard_gather.argtypes = [ctypes.POINTER(LgrView), lay, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.lgr_tree_traverse.restype = ctypes.c_int
+    lib.lgr_tree_traverse.argtypes = [ctypes.POINTER(LgrTree), _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _f32,
+                                      _i32, _vp, _vp, _vp, _vp]
     lib.lgr_profile_enable.restype = ctypes.c_int
     lib.lgr_profile_enable.argtypes = [ctypes.c_int]
     lib.lgr_profile_collect.restype = ctypes.c_int

@@ -32,6 +32,7 @@ int launch_shard_recv_count(const View&, const ShardLayout&, float*, float*, int
 int launch_shard_return(const ShardLayout&, const float*, int64_t, const void*, int, int64_t, void* const*, cudaStream_t);
 int launch_shard_gather(const View&, const ShardLayout&, int64_t, const float*, const int32_t*, const int32_t*, const float*,
                         float*, float*, int32_t*, cudaStream_t);
+int launch_tree_traverse(const TreeArgs&, int64_t, int64_t, const int64_t*, int64_t, int, int32_t*, int64_t*, int64_t*, cudaStream_t);
 }  // namespace lgr
 
 using namespace lgr;
@@ -251,6 +252,27 @@ int lgr_shard_gather(const lgr_view* view, const lgr_shard_layout* layout, int64
   if (!splat_d || !radii_d || !send_scratch_d || !exchange_d || !dsplat_local_d) return LGR_E_BADARG;
   return launch_shard_gather(make_view(view, n_local), make_layout(layout), n_local, splat_d, radii_d, send_scratch_d, exchange_d,
                              dsplat_local_d, point_weight_d, point_count_d, (cudaStream_t)stream);
+}
+
+/* ---- level-of-Gaussian tree traversal ---- */
+int lgr_tree_traverse(const lgr_tree* tree, const float* xyz_d, const float* scaling_raw_d, const float* rotation_raw_d,
+                      const float* projmatrix_d, const float* viewmatrix_d, float focal_x, float focal_y, float tan_fovx,
+                      float tan_fovy, const int64_t* root_index_d, int64_t num_roots, float min_resolution_pixel,
+                      int32_t max_depth, int32_t* scratch_d, int64_t* index_out_d, int64_t* count_out_d, void* stream) {
+  if (!tree || tree->num_points < 0 || tree->num_nodes < 0 || tree->max_child <= 0 || tree->max_level < 0) return LGR_E_BADARG;
+  if (num_roots < 0 || num_roots > tree->num_points || max_depth < 0 || !scratch_d || !count_out_d) return LGR_E_BADARG;
+  if (!projmatrix_d || !viewmatrix_d) return LGR_E_BADARG;
+  if (tree->num_points > 0 && (!tree->node_index_d || !xyz_d || !scaling_raw_d || !rotation_raw_d || !index_out_d)) return LGR_E_BADARG;
+  if (tree->num_nodes > 0 && !tree->tree_d) return LGR_E_BADARG;
+  if (num_roots > 0 && !root_index_d) return LGR_E_BADARG;
+  if (tree->num_points > 0x7fffffffLL || tree->num_nodes * tree->max_child > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
+  TreeArgs a;
+  a.node_index = tree->node_index_d; a.tree = tree->tree_d; a.C = tree->max_child;
+  a.xyz = xyz_d; a.scaling_raw = scaling_raw_d; a.rotation_raw = rotation_raw_d; a.view = viewmatrix_d; a.proj = projmatrix_d;
+  a.fx = focal_x; a.fy = focal_y; a.tanfovx = tan_fovx; a.tanfovy = tan_fovy; a.min_px = min_resolution_pixel;
+  const int levels = tree->max_level < max_depth ? tree->max_level : max_depth;
+  return launch_tree_traverse(a, tree->num_points, tree->num_nodes, root_index_d, num_roots, levels, scratch_d, index_out_d,
+                              count_out_d, (cudaStream_t)stream);
 }
 
 /* ---- diagnostics: per-kernel CUDA-event timing (used by bench.py for the live roofline numbers) ---- */

@@ -65,6 +65,19 @@ struct ShardLayout {
   int64_t off_count, off_splat, off_radii, off_gid, off_dsplat, off_weight, off_pcount;
 };
 
+// Arguments of the level-of-Gaussian tree traversal (lgr_tree.cu).
+struct TreeArgs {
+  const int32_t* node_index;   // (num_points): row of `tree` holding the children, -1 = leaf
+  const int32_t* tree;         // (num_nodes, C) child point ids, -1 = empty slot
+  int C;
+  const float* xyz;            // (num_points,3)
+  const float* scaling_raw;    // (num_points,3)  scale = exp(raw)                 (activation.py:7, 'exp')
+  const float* rotation_raw;   // (num_points,4)  rotation = raw / max(|raw|, eps)  (activation.py:18, F.normalize)
+  const float* view;
+  const float* proj;
+  float fx, fy, tanfovx, tanfovy, min_px;
+};
+
 // ---- projected splat record: 3 x float4 per Gaussian ---------------------------------------------------
 //   r0 = (px, py, conic_x, conic_y)      r1 = (conic_z, opacity, hx, hy)      r2 = (r, g, b, depth)
 // The conic is stored pre-multiplied by log2(e) so that the blend can use ex2.approx directly.
@@ -147,6 +160,30 @@ __device__ __forceinline__ float radius_from_cov(float a, float b, float c, floa
   const float mid = 0.5f * (a + c);
   const float root = sqrtf(fmaxf(0.1f, mid * mid - det));
   return 3.0f * sqrtf(fmaxf(mid + root, mid - root));
+}
+
+// compute_radius_cuda of the reference (LoG/cuda/compute_radius_kernel.cu:107-156), in two steps so that callers can
+// skip the scale / rotation loads of culled points: the NDC cull at +-1.3 (no near-plane cull), then the radius --
+// quaternion used as given, max(cov, 0.3) filter, 3 sqrt(lambda_max) NOT rounded up; 0 = degenerate.
+// V, P: view / full projection matrices in the reference's transposed storage (16 floats each).
+__device__ __forceinline__ bool ndc_inside(const float p[3], const float* __restrict__ P) {
+  float hom[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) hom[k] = p[0] * P[k] + p[1] * P[4 + k] + p[2] * P[8 + k] + P[12 + k];
+  const float pw = 1.0f / (hom[3] + 0.0000001f);
+  const float nx = hom[0] * pw, ny = hom[1] * pw;
+  return !(nx < -1.3f || nx > 1.3f || ny < -1.3f || ny > 1.3f);
+}
+__device__ __forceinline__ float projected_radius(const float p[3], const float s[3], const float4 q, const float* __restrict__ V,
+                                                  float fx, float fy, float tanfovx, float tanfovy) {
+  float R[9], Sg[9];
+  quat_to_R(q, R);
+  cov3d(s, R, Sg);
+  Cov2D cv;
+  cov2d(V, p, Sg, fx, fy, tanfovx, tanfovy, LGR_FILTER_MAX, cv);
+  float det;
+  const float rad = radius_from_cov(cv.a, cv.b, cv.c, det);
+  return det != 0.0f ? rad : 0.0f;
 }
 
 // Stock tile rectangle from the radius square, clamped to the tile grid.

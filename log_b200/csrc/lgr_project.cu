@@ -29,22 +29,11 @@ compute_radius_kernel(int64_t n, const float* __restrict__ means, const float* _
   if (i >= n) return;
   float p[3];
   load3(means, i, p);
-  float hom[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) hom[k] = p[0] * sP[k] + p[1] * sP[4 + k] + p[2] * sP[8 + k] + sP[12 + k];
-  const float pw = 1.0f / (hom[3] + 0.0000001f);
-  const float nx = hom[0] * pw, ny = hom[1] * pw;
   float out = 0.0f;
-  if (!(nx < -1.3f || nx > 1.3f || ny < -1.3f || ny > 1.3f)) {
-    float s[3], R[9], Sg[9];
+  if (ndc_inside(p, sP)) {
+    float s[3];
     load3(scales, i, s);
-    quat_to_R(ldg4(rots + 4 * i), R);
-    cov3d(s, R, Sg);
-    Cov2D cv;
-    cov2d(sV, p, Sg, fx, fy, tanfovx, tanfovy, LGR_FILTER_MAX, cv);
-    float det;
-    const float rad = radius_from_cov(cv.a, cv.b, cv.c, det);
-    if (det != 0.0f) out = rad;
+    out = projected_radius(p, s, ldg4(rots + 4 * i), sV, fx, fy, tanfovx, tanfovy);
   }
   radii[i] = out;
 }

@@ -1,9 +1,10 @@
-"""Translate the integer / byte CUDA kernels (log_b200/csrc/lgr_bin.cu, lgr_shard.cu) to host C++ on top of the SIMT
-emulation in tests/emu/cuda_runtime.h and build tests/emu/_build/libemu.so.  Test infrastructure only.
+"""Translate the CUDA sources of log_b200/csrc (kernels and the C entry points) to host C++ on top of the SIMT emulation
+in tests/emu/cuda_runtime.h and build tests/emu/_build/libemu.so.  Test infrastructure only.
 
-The translation touches exactly two constructs, mechanically:
+The translation touches exactly three constructs, mechanically:
   kernel<<<grid, block, smem, stream>>>(args);   ->  emu::launch(dim3(grid), dim3(block), smem, [=]() { kernel(args); });
   extern __shared__ T name[];                    ->  T* name = reinterpret_cast<T*>(emu::dyn_smem());
+  the eight inline-PTX helper functions of lgr_blend.cu  ->  host versions in emu_blend_helpers.h
 Everything else (the kernel bodies) is compiled verbatim.
 """
 import os
@@ -15,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'log_b200', 'csrc')
 BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(BUILD, 'libemu.so')
-SOURCES = ['lgr_bin.cu', 'lgr_shard.cu', 'lgr_project.cu', 'lgr_blend.cu', 'lgr_optim.cu', 'lgr_capi.cu']
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))      # every kernel file and the C entry points
 # inline-PTX helpers of lgr_blend.cu, replaced by tests/emu/emu_blend_helpers.h
 PTX_HELPERS = ['ex2_approx', 'rcp_approx', 'smem_u32', 'lds_f4', 'lds_f2', 'pin_reg', 'red_shared_max_u32', 'red_shared_add_f32']
 
@@ -106,7 +107,8 @@ def build(force=False):
             fh.write(f'// generated from log_b200/csrc/{f} by tests/emu/build_emu.py -- do not edit\n')
             fh.write(translate(open(os.path.join(CSRC, f)).read()))
         objs.append(cpp)
-    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-w', '-I', HERE, '-I', CSRC, '-o', LIB + '.tmp'] + objs + \
+    # a 3-CTA grid for the tree walk: every emulated CTA costs 256 fibers, and 3 CTAs make the grid-stride loops iterate
+    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-w', '-DLGR_TREE_GRID=3', '-I', HERE, '-I', CSRC, '-o', LIB + '.tmp'] + objs + \
           [os.path.join(HERE, 'emu_api.cpp')]
     env = dict(os.environ)
     env.pop('CC', None)

@@ -83,6 +83,7 @@ def main():
     out['sh_rgb_deg0'] = ref_sh.SH2RGB(torch.from_numpy(dc)).numpy()
     # sparse Adam (LoG/model/sparse_optimizer.py:41-78 _single_tensor_adam), float32 as LoG runs it
     make_adam_golden()
+    make_tree_golden()
     np.savez_compressed(os.path.join(HERE, 'reference_geometry_sh.npz'), **out)
     print('wrote', os.path.join(HERE, 'reference_geometry_sh.npz'), {k: v.shape for k, v in out.items() if 'cam0' in k or 'sh' in k})
 
@@ -122,6 +123,108 @@ def make_adam_golden():
     np.savez_compressed(os.path.join(HERE, 'reference_sparse_adam.npz'), **out)
     print('wrote reference_sparse_adam.npz', len(out))
     torch.set_default_dtype(torch.float64)
+
+
+def make_tree_golden():
+    """Index lists returned by the reference's own TensorTree.traverse (LoG/model/tensor_tree.py:164-186), on trees built
+    with the reference's own initialize / split / remove, with a model stub whose compute_radius is the reference's
+    PyTorch twin of the CUDA kernel (level_of_gaussian.py:68-69 `if False:` branch -> geometry.compute_radius).  The twin
+    has no NDC cull, so the scenes keep every point inside +-1.25 NDC (checked), and no radius within 1e-3 (relative) of
+    the keep / descend threshold (checked), so that float32 kernels must reproduce the lists exactly."""
+    import importlib.util
+    torch.set_default_dtype(torch.float64)
+    import LoG.dataset.base as ref_base
+    import LoG.model.geometry as ref_geo
+    spec = importlib.util.spec_from_file_location('ref_tensor_tree', os.path.join(REF, 'LoG/model/tensor_tree.py'))
+    tt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tt)
+    out = {}
+    rng = np.random.default_rng(31)
+    W, H, fx = 640, 360, 500.0
+    K = np.array([[fx, 0, W / 2], [0, fx, H / 2], [0, 0, 1.0]])
+    cam = ref_base.prepare_camera(dict(W=W, H=H, K=K, R=np.eye(3), T=np.zeros((3, 1)), center=np.zeros((3, 1))), scale=1, znear=0.01, zfar=100.0)
+    cam_t = {k: (torch.from_numpy(np.asarray(v, dtype=np.float64)) if isinstance(v, np.ndarray) else v) for k, v in cam.items()}
+    out['tree_cam_spec'] = np.array([W, H, fx, fx, W / 2, H / 2], dtype=np.float64)
+    out['tree_world_view_transform'] = np.asarray(cam['world_view_transform'], dtype=np.float64)
+    out['tree_full_proj_transform'] = np.asarray(cam['full_proj_transform'], dtype=np.float64)
+    out['tree_FoV'] = np.array([cam['FoVx'], cam['FoVy']], dtype=np.float64)
+    case = 0
+    for max_child, n_root, rounds in ((2, 70, 4), (4, 40, 3), (3, 1, 5)):
+        tree = tt.TensorTree(max_child=max_child, max_level=20)
+        tree.initialize(torch.zeros(n_root, 3))
+        tree.log_query = False
+
+        def fresh(n, depth):      # points in front of the camera, inside +-1.2 NDC; deeper levels are smaller
+            z = rng.uniform(1.0, 12.0, n)
+            x = rng.uniform(-1.2, 1.2, n) * (W / (2 * fx)) * z
+            y = rng.uniform(-1.2, 1.2, n) * (H / (2 * fx)) * z
+            px = np.exp(rng.normal(np.log(24.0) - 1.1 * depth, 0.9, n))            # pixel radius ~ 3 sigma
+            sig = (px / 3.0) * z / fx
+            scal = np.log(sig[:, None] * rng.uniform(0.3, 1.0, (n, 3)))
+            rot = rng.normal(size=(n, 4)) * rng.uniform(0.2, 3.0, (n, 1))           # un-normalised, as stored
+            return np.stack([x, y, z], -1), scal, rot
+        xyz, scal, rot = fresh(n_root, 0)
+        for rd in range(rounds):
+            leaves = torch.where(tree.is_leaf & (tree.depth == rd))[0]
+            pick = leaves[torch.from_numpy(rng.random(len(leaves)) < (0.7 if n_root > 1 else 0.9 if rd else 1.0))]
+            if len(pick) == 0:
+                break
+            tree.split(pick)
+            a, b, c = fresh(len(pick) * max_child, rd + 1)
+            xyz, scal, rot = np.concatenate([xyz, a]), np.concatenate([scal, b]), np.concatenate([rot, c])
+        # holes in the child table: the reference's remove() compacts every per-point array, do the same to the params
+        cand = torch.where(tree.is_leaf & (~tree.is_root))[0]
+        rm = cand[torch.from_numpy(rng.random(len(cand)) < 0.15)]
+        flag_keep = torch.ones(tree.num_points, dtype=torch.bool)
+        flag_keep[rm] = False
+        tree.remove(rm)
+        xyz, scal, rot = xyz[flag_keep.numpy()], scal[flag_keep.numpy()], rot[flag_keep.numpy()]
+        assert xyz.shape[0] == tree.num_points
+
+        class Stub:      # LoG/model/level_of_gaussian.py:64-93 with the `if False:` (PyTorch twin) branch taken
+            def compute_radius(self, index, camera, level=0):
+                scaling = torch.exp(torch.from_numpy(scal)[index])
+                rotation = torch.nn.functional.normalize(torch.from_numpy(rot)[index])
+                r2d = ref_geo.compute_radius(torch.from_numpy(xyz)[index], scaling, rotation, camera)
+                return scaling.max(dim=-1).values, r2d
+        stub = Stub()
+        for _ in range(20):      # move points whose radius sits within 0.2 % of a threshold used below
+            all_r = ref_geo.compute_radius(torch.from_numpy(xyz), torch.exp(torch.from_numpy(scal)),
+                                           torch.nn.functional.normalize(torch.from_numpy(rot)), cam_t).numpy()
+            near = np.zeros(len(all_r), bool)
+            for thr in (3.0, 1.0, 8.0):
+                near |= np.abs(all_r / thr - 1.0) < 2e-3
+            if not near.any():
+                break
+            scal[near] += 0.03
+        P = np.asarray(cam['full_proj_transform'], dtype=np.float64)
+        hom = xyz @ P[:3] + P[3]
+        assert (np.abs(hom[:, :2] / (hom[:, 3:4] + 1e-7)) < 1.25).all()
+        pre = f'tree{case}_'
+        out[pre + 'node_index'] = tree.node_index.numpy().astype(np.int32)
+        out[pre + 'tree'] = tree.tree.numpy().astype(np.int32)
+        out[pre + 'depth'] = tree.depth.numpy().astype(np.int8)
+        out[pre + 'max_child'] = np.array([max_child, tree.max_level])
+        out[pre + 'xyz'], out[pre + 'scaling_raw'], out[pre + 'rotation_raw'] = xyz, scal, rot
+        out[pre + 'radius'] = all_r
+        roots_all = torch.where(tree.is_root)[0]
+        q = 0
+        for min_px in (3.0, 1.0, 8.0):
+            assert (np.abs(all_r / min_px - 1.0) > 1e-3).all(), 'a radius sits on the threshold: change the seed'
+            for max_depth in (1000, 2, 0):
+                for roots in (roots_all, roots_all[torch.from_numpy(rng.random(len(roots_all)) < 0.6)].flip(0)):
+                    tree.min_resolution_pixel = min_px
+                    idx = tree.traverse(stub, roots.long(), cam_t, max_depth=max_depth)
+                    out[pre + f'q{q}_args'] = np.array([min_px, max_depth], dtype=np.float64)
+                    out[pre + f'q{q}_roots'] = roots.numpy().astype(np.int64)
+                    out[pre + f'q{q}_index'] = idx.numpy().astype(np.int64)
+                    q += 1
+        out[pre + 'num_queries'] = np.array([q])
+        print(pre, tree, 'queries', q, 'last result', len(idx))
+        case += 1
+    out['num_trees'] = np.array([case])
+    np.savez_compressed(os.path.join(HERE, 'reference_tree.npz'), **out)
+    print('wrote reference_tree.npz')
 
 
 if __name__ == '__main__':
