@@ -59,7 +59,11 @@ typedef struct lgr_view {
                             LoG/model/activation.py:36-44 are fused into the projection and its backward:
                             scale = exp(raw), opacity = sigmoid(raw), rotation = raw / max(|raw|, 1e-12),
                             colour = C0 * raw + 0.5 (SH2RGB, sh_utils.py:72-73); gradients are w.r.t. the raw values.
-                            Precomputed colours only. */
+                            Colour sources with raw_params: colors_precomp alone (DC colour), or colors_precomp (raw DC)
+                            TOGETHER with shs = LoG's "rest" coefficients (N, sh_coeffs, 3), sh_coeffs >= (sh_degree+1)^2-1:
+                            then LoG's colour activation (activation.py:27-34) is fused -- SH2RGB(dc) +
+                            eval_sh_wobase(normalize(mean - campos), shs, sh_degree), NOT clamped at 0, direction
+                            detached (no colour gradient into the mean).  Not available in band mode. */
   int32_t* band_ids_d;   /* (256 B) int32, or NULL */
   int32_t* band_blk_d;   /* (2 B + 1) int32 */
   int32_t* band_count_d; /* (num_owners) int32 */

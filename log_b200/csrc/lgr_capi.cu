@@ -68,9 +68,17 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
                         const float* shs_d, float* splat_d, int32_t* radii_d, uint8_t* clamped_d,
                         int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, void* stream) {
   if (!view_ok(view) || n < 0 || !tile_start_d || !tile_cursor_d || !meta_d) return LGR_E_BADARG;
-  if ((colors_precomp_d != nullptr) == (shs_d != nullptr) && n > 0) return LGR_E_BADARG;   // exactly one colour source
-  if (view->raw_params && shs_d) return LGR_E_UNSUPPORTED;   // fused activations: precomputed (DC) colours only
-  if (shs_d) {
+  // colour sources: colors_precomp XOR shs (stock), or -- with raw_params -- raw DC colours + the rest coefficients
+  // (LoG's colour activation fused, activation.py:27-34)
+  const bool log_sh = view->raw_params && colors_precomp_d && shs_d;
+  if (!log_sh && (colors_precomp_d != nullptr) == (shs_d != nullptr) && n > 0) return LGR_E_BADARG;
+  if (view->raw_params && shs_d && !colors_precomp_d) return LGR_E_UNSUPPORTED;   // raw stock-layout SH is not a LoG input
+  if (log_sh) {
+    if (!view->campos_d) return LGR_E_BADARG;
+    if (view->sh_degree < 0 || view->sh_degree > 3) return LGR_E_UNSUPPORTED;
+    if (view->sh_coeffs < (view->sh_degree + 1) * (view->sh_degree + 1) - 1) return LGR_E_BADARG;
+    if (view->num_owners > 0) return LGR_E_UNSUPPORTED;
+  } else if (shs_d) {
     if (!view->campos_d || !clamped_d) return LGR_E_BADARG;
     if (view->sh_degree < 0 || view->sh_degree > 3) return LGR_E_UNSUPPORTED;
     if (view->sh_coeffs < (view->sh_degree + 1) * (view->sh_degree + 1)) return LGR_E_BADARG;
@@ -83,6 +91,7 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
   if (v.num_owners > 0) {
     if (shs_d) return LGR_E_UNSUPPORTED;          // band mode packs 17-float rows: precomputed colours only
   }
+  if (log_sh && view->sh_degree == 0) shs_d = nullptr;      // degree 0: the rest coefficients are not read
   cudaError_t e = cudaMemsetAsync(tile_cursor_d, 0, sizeof(int32_t) * (size_t)ntiles * CSTRIDE, st);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(meta_d, 0, sizeof(int32_t) * LGR_META_INTS, st);
@@ -126,8 +135,10 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
                  int64_t num_rows, void* stream) {
   if (!view_ok(view) || n < 0 || !tile_start_d || !image_d || !dL_dimage_d) return LGR_E_BADARG;
   if (n == 0) return 0;
-  const bool use_sh = shs_d != nullptr;
-  if (use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
+  const bool log_sh = view->raw_params && colors_precomp_d && shs_d;      // LoG-style SH: DC colours + rest coefficients
+  const bool use_sh = shs_d != nullptr && !log_sh;
+  if (!log_sh && use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
+  if (log_sh && (!dshs_d || !view->campos_d || view->num_owners > 0)) return LGR_E_BADARG;
   if (!means3D_d || !scales_d || !rotations_d || !splat_d || !radii_d || !dsplat_d) return LGR_E_BADARG;
   if (view->raw_params && (!opacities_d || use_sh)) return LGR_E_BADARG;
   if (grad_rows_d || peer_stage_d) {
@@ -146,7 +157,7 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   if (num_instances > 0) rc = launch_blend_bwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, dL_dimage_d, dsplat_d, st);
   if (rc) return rc;
   const bool rows_mode = grad_rows_d || peer_stage_d;
-  return launch_project_bwd(v, rows_mode ? num_rows : n, means3D_d, opacities_d, scales_d, rotations_d, shs_d, use_sh, radii_d, clamped_d, dsplat_d,
+  return launch_project_bwd(v, rows_mode ? num_rows : n, means3D_d, opacities_d, scales_d, rotations_d, (use_sh || log_sh) ? shs_d : nullptr, use_sh, radii_d, clamped_d, dsplat_d,
                             dmeans3D_d, dmeans2D_d, dopacities_d, dscales_d, drotations_d, dcolors_d, dshs_d, grad_rows_d, peer_stage_d, my_rank, st);
 }
 

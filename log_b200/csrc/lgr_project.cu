@@ -41,7 +41,10 @@ compute_radius_kernel(int64_t n, const float* __restrict__ means, const float* _
 // ---------------------------------------------------------------------------------------------------------
 // forward projection
 // ---------------------------------------------------------------------------------------------------------
-template <bool USE_SH>
+// LOG_SH (with USE_SH = false and View::raw_params): LoG's colour activation (LoG/model/activation.py:27-34) fused --
+// rgb = SH2RGB(dc) + eval_sh_wobase(dir, rest, degree) with dc = `colors` (N,3) raw and rest = `shs` (N,K,3); unlike the
+// stock SH path there is NO clamp at 0 and the direction comes from the DETACHED position (no gradient to the mean).
+template <bool USE_SH, bool LOG_SH = false>
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ opac,
                    const float* __restrict__ scales, const float* __restrict__ rots,
@@ -58,7 +61,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { const float w = v.view[r * 4 + c]; a += w * w; }
     sWf = a;
   }
-  if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
+  if ((USE_SH || LOG_SH) && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
   int rad_out = 0;
@@ -183,6 +186,18 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) rgb[ch] = fmaf(SH_C0, rgb[ch], 0.5f);
           }
+          if (LOG_SH && v.sh_degree > 0) {      // + eval_sh_wobase (sh_utils.py:31-58): basis functions 1 .. (deg+1)^2 - 1
+            float d[3] = {p[0] - sCam[0], p[1] - sCam[1], p[2] - sCam[2]};
+            const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            float B[16];
+            sh_basis(v.sh_degree, d[0] * inv, d[1] * inv, d[2] * inv, B);
+            const int nb = (v.sh_degree + 1) * (v.sh_degree + 1);
+            const float* sh = shs + (int64_t)i * v.sh_K * 3;
+            for (int k = 1; k < nb; k++) {
+              rgb[0] += B[k] * __ldg(sh + 3 * (k - 1)); rgb[1] += B[k] * __ldg(sh + 3 * (k - 1) + 1);
+              rgb[2] += B[k] * __ldg(sh + 3 * (k - 1) + 2);
+            }
+          }
         }
         // conic pre-multiplied by log2(e): the blend evaluates alpha = o * 2^(-0.5 d^T C' d)
         const float kdet = LOG2E * idet;
@@ -237,7 +252,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
 // ---------------------------------------------------------------------------------------------------------
 // backward projection: dsplat (d/dpx, d/dpy, d/dconic xyz, d/dopacity, d/drgb) -> input gradients
 // ---------------------------------------------------------------------------------------------------------
-template <bool USE_SH, bool ROWS>
+template <bool USE_SH, bool ROWS, bool LOG_SH = false>
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ opac,
                    const float* __restrict__ scales, const float* __restrict__ rots, const float* __restrict__ shs, const int32_t* __restrict__ radii,
@@ -247,7 +262,7 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
                    float* __restrict__ grad_rows, void* const* __restrict__ peer_stage, int my_rank) {
   __shared__ float sV[16], sP[16], sCam[3];
   if (threadIdx.x < 16) { sV[threadIdx.x] = v.view[threadIdx.x]; sP[threadIdx.x] = v.proj[threadIdx.x]; }
-  if (USE_SH && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
+  if ((USE_SH || LOG_SH) && threadIdx.x < 3) sCam[threadIdx.x] = v.campos[threadIdx.x];
   __syncthreads();
   // Fused exchange: rank r starts with the rows of owner r+1, r+2, ... so that the ranks do not all push into the same
   // destination at the same time (rows are grouped by owner in ascending order).
@@ -422,7 +437,28 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     const float dot = qn.x * dq[0] + qn.y * dq[1] + qn.z * dq[2] + qn.w * dq[3];
     dq[0] = (dq[0] - qn.x * dot) * inv; dq[1] = (dq[1] - qn.y * dot) * inv;       // d (r/|r|) = (I - q q^T) / |r|
     dq[2] = (dq[2] - qn.z * dot) * inv; dq[3] = (dq[3] - qn.w * dot) * inv;
+    if (LOG_SH) {      // d rest_k = B_k(dir) * d rgb ; the direction is detached (activation.py:30): nothing flows to the mean
+      float* dsh = dshs + (int64_t)i * K * 3;
+      int nb = 1;
+      if (v.sh_degree > 0) {
+        float p[3];
+        load3(means, i, p);
+        const float d[3] = {p[0] - sCam[0], p[1] - sCam[1], p[2] - sCam[2]};
+        const float inv_d = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        float B[16];
+        sh_basis(v.sh_degree, d[0] * inv_d, d[1] * inv_d, d[2] * inv_d, B);
+        nb = (v.sh_degree + 1) * (v.sh_degree + 1);
+        for (int k = 1; k < nb; k++) {
+          dsh[3 * (k - 1)] = B[k] * drgb[0]; dsh[3 * (k - 1) + 1] = B[k] * drgb[1]; dsh[3 * (k - 1) + 2] = B[k] * drgb[2];
+        }
+      }
+      for (int k = nb - 1; k < K; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+    }
     if (!USE_SH) { drgb[0] *= SH_C0; drgb[1] *= SH_C0; drgb[2] *= SH_C0; }        // d (C0 x + 0.5) = C0
+  }
+  if (LOG_SH && active && !live) {
+    float* dsh = dshs + (int64_t)i * K * 3;
+    for (int k = 0; k < K * 3; k++) dsh[k] = 0.f;
   }
   if (ROWS) {
     // Rows are staged in shared memory and written out by the whole CTA as contiguous 16-byte-per-lane runs: the rows of
@@ -600,7 +636,9 @@ int launch_project_fwd(const View& v, int64_t n, const float* means, const float
   if (n == 0) return 0;
   const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
   ProfScope ps(K_PROJECT_FWD, st);
-  if (colors)
+  if (colors && shs)      // LoG-style SH on top of raw DC colours (checked by the caller: raw_params, no band mode)
+    project_fwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
+  else if (colors)
     project_fwd_kernel<false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
   else
     project_fwd_kernel<true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
@@ -621,6 +659,8 @@ int launch_project_bwd(const View& v, int64_t n, const float* means, const float
   ProfScope ps(K_PROJECT_BWD, st);
   if (grad_rows || peer_stage)
     project_bwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
+  else if (!use_sh && shs)      // LoG-style SH: dcolors (DC) and dshs (rest) both written
+    project_bwd_kernel<false, false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   else if (!use_sh)
     project_bwd_kernel<false, false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   else

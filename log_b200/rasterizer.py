@@ -109,7 +109,9 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     num_owners > 0 (multi-GPU band mode, see log_b200/sharded.py): also compact the ids of the Gaussians reaching the
     band `tile_rows`, grouped by owner rank; the backward then returns packed gradient rows instead of dense tensors.
     raw_params=True: scales / opacities / rotations / colors_precomp are LoG's RAW parameters; exp / sigmoid / normalize /
-    SH2RGB (LoG/model/activation.py:36-44) run inside the projection kernels and the gradients are w.r.t. the raw values."""
+    SH2RGB (LoG/model/activation.py:36-44) run inside the projection kernels and the gradients are w.r.t. the raw values.
+    With raw_params and BOTH colors_precomp (raw DC, (N,3)) and shs (the rest coefficients, (N,K,3)) LoG's whole colour
+    activation is fused: SH2RGB(dc) + eval_sh_wobase(dir, shs, settings.sh_degree), no clamp, direction detached."""
     lib = _capi.load()
     dev = means3D.device
     n = int(means3D.shape[0])
@@ -302,7 +304,8 @@ class GaussianRasterizer(nn.Module):
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None, use_filter=True, raw_params=False):
-        if (shs is None) == (colors_precomp is None):
+        log_sh = raw_params and shs is not None and colors_precomp is not None      # LoG's colour activation fused
+        if (shs is None) == (colors_precomp is None) and not log_sh:
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
         if cov3D_precomp is not None:
             raise NotImplementedError('cov3D_precomp is not supported: LoG always passes None (renderer.py:134,149)')
@@ -313,8 +316,9 @@ class GaussianRasterizer(nn.Module):
             filter_mode = LGR_FILTER_MAX if use_filter else LGR_FILTER_NONE
         else:
             filter_mode = LGR_FILTER_ADD
-        if raw_params and shs is not None:
-            raise NotImplementedError('raw_params (fused activations) supports precomputed colours only')
+        if raw_params and shs is not None and colors_precomp is None:
+            raise NotImplementedError('raw_params with SH: pass the raw DC colours as colors_precomp and the REST coefficients '
+                                      '(LoG layout, activation.py:27-34) as shs')
         out = _RasterizeGaussians.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
                                         self.raster_settings, filter_mode, fork, self.tile_rows, raw_params)
         # fork flavour: per-Gaussian histogram of the per-pixel winners (feeds point_id_count())

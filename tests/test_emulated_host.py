@@ -104,3 +104,8 @@ def test_random_small_configurations(emulated_backend):
             if np.linalg.norm(ref[k]) > 1e-12:
                 assert rel(got[k], ref[k]) < max(1e-4, 4 * rel(ref32[k], ref[k])), (it, (W, H, n, r, deg, flavour, use_filter, rot), k)
         assert (got['radii'].numpy() != ref['radii']).sum() <= 1
+
+
+@pytest.mark.parametrize('deg', [1, 3])
+def test_fused_log_colour_activation_with_sh(emulated_backend, deg):
+    gp.check_fused_log_colour_activation_with_sh(deg, size=(64, 48, 400))

@@ -418,3 +418,59 @@ def test_fused_activations_match_torch_activations(built, size=(176, 112, 2500))
     assert rel(img_f, out['image'].detach()) < 1e-4
     for k in g_t:
         assert rel(g_f[k], leaves[k].grad) < 2e-4, (k, rel(g_f[k], leaves[k].grad))
+
+
+def check_fused_log_colour_activation_with_sh(deg, size=(160, 96, 1800)):
+    """SURVEY 8(f) row 3, colour part: LoG computes colours as SH2RGB(dc) + eval_sh_wobase(normalize(xyz.detach() - campos),
+    shs, degree) with NO clamp (LoG/model/activation.py:27-34, sh_utils.py:31-73).  With raw_params and both raw DC colours
+    and rest coefficients the kernels do that themselves; image and every gradient (incl. d/d rest, and NO colour
+    gradient into the positions) equal torch activations + the ordinary call and the fp64 oracle."""
+    from log_b200 import GaussianRasterizer
+    from util import settings_from_camera
+    W, H, n = size
+    K = 15                                                     # LoG allocates (max_sh_degree+1)^2 - 1 = 15 rest coefficients
+    cam = f32_camera(O.make_camera(W, H, bg=(0.3, 0.2, 0.1), sh_degree=deg, R=[[0.98, 0.0, 0.199], [0, 1, 0], [-0.199, 0, 0.98]],
+                                   T=[0.1, -0.05, 0.3]))
+    sc = f32_scene(O.make_scene(n, W, H, 4.0, seed=56, sh_degree=3))
+    raw64 = dict(means3D=sc['means3D'], scales=torch.log(sc['scales']), opacities=torch.logit(sc['opacities'].clamp(0.02, 0.98)),
+                 rotations=sc['rotations'] * 1.7, colors=(sc['colors'] - 0.5) / O.C0, shs=sc['shs'][:, 1:1 + K] * 3.0)
+    raw64 = {k: v.to(torch.float32).to(torch.float64).contiguous() for k, v in raw64.items()}
+    G = O.make_cotangent(3, H, W).to(torch.float32)
+    dev = device()
+    rast = GaussianRasterizer(settings_from_camera(cam, dev, deg))
+    campos = cam.campos
+
+    def log_colours(t, cp):      # activation.py:27-34 (eval_sh on [dc | rest] is SH2RGB(dc) + eval_sh_wobase(rest), unclamped)
+        d = t['means3D'].detach() - cp[None]
+        d = d / torch.norm(d, dim=-1, keepdim=True)
+        return O.eval_sh(deg, torch.cat([t['colors'][:, None], t['shs']], dim=1), d)
+
+    def run(fused):
+        t = {k: v.to(device=dev, dtype=torch.float32).requires_grad_(True) for k, v in raw64.items()}
+        m2d = torch.zeros(n, 3, device=dev, requires_grad=True)
+        if fused:
+            out = rast(means3D=t['means3D'], means2D=m2d, shs=t['shs'], colors_precomp=t['colors'], opacities=t['opacities'],
+                       scales=t['scales'], rotations=t['rotations'], cov3D_precomp=None, raw_params=True)
+        else:
+            out = rast(means3D=t['means3D'], means2D=m2d, shs=None, colors_precomp=log_colours(t, campos.to(device=dev, dtype=torch.float32)),
+                       opacities=torch.sigmoid(t['opacities']), scales=torch.exp(t['scales']),
+                       rotations=torch.nn.functional.normalize(t['rotations']), cov3D_precomp=None)
+        (out[0] * G.to(dev)).sum().backward()
+        return out[0].detach(), {k: v.grad for k, v in t.items()}, m2d.grad
+
+    img_f, g_f, m2_f = run(True)
+    img_t, g_t, m2_t = run(False)
+    assert rel(img_f, img_t) < 1e-5
+    assert rel(m2_f, m2_t) < 1e-4
+    for k in g_t:
+        assert rel(g_f[k], g_t[k]) < 1e-4, (k, rel(g_f[k], g_t[k]))
+    nb = (deg + 1) ** 2 - 1
+    assert float(g_f['shs'][:, :nb].abs().max()) > 0.0 and (nb == K or float(g_f['shs'][:, nb:].abs().max()) == 0.0)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in raw64.items()}
+    out = O.render(leaves['means3D'], torch.sigmoid(leaves['opacities']), torch.exp(leaves['scales']),
+                   torch.nn.functional.normalize(leaves['rotations']), cam, colors_precomp=log_colours(leaves, campos),
+                   filter_mode=O.FILTER_MAX)
+    (out['image'] * G.to(torch.float64)).sum().backward()
+    assert rel(img_f, out['image'].detach()) < 1e-4
+    for k in g_t:
+        assert rel(g_f[k], leaves[k].grad) < 2e-4, (k, rel(g_f[k], leaves[k].grad))
