@@ -63,3 +63,108 @@ def test_reference_render_reaches_our_forward_with_its_own_kwargs(renderer_modul
     rast = R.BaseRender.prepare(camera(), torch.zeros(3))
     with pytest.raises(LgrError, match='no CPU fallback'):
         rr.render(camera(), rast, _Model())
+
+
+@pytest.mark.parametrize('origin,training', [(False, True), (False, False), (True, True)])
+def test_reference_render_end_to_end_on_the_emulated_backend(renderer_module, emulated_backend, origin, training):
+    """LoG's own render() (renderer.py:117-205), unmodified, with this repo's rasteriser behind it and the kernels running
+    on the CPU SIMT emulation: the image, radii, point_id / point_count / point_weight it returns equal the oracle's for
+    the flavour and filter it selects (fork + filter in training, fork without filter in eval :151-152, stock with
+    use_origin_render), and loss.backward() fills viewspace_points.grad (read at counter.py:40)."""
+    import numpy as np
+    from oracle import c_oracle, torch_dense as O
+    from util import f32_camera, rel
+    R = renderer_module
+    W, H, n = 64, 48, 300
+    cam = f32_camera(O.make_camera(W, H, bg=(0.0, 0.0, 0.0)))
+    sc = {k: v.to(torch.float32) for k, v in O.make_scene(n, W, H, 4.0, seed=12).items()}
+    camera = {'FoVx': 2 * np.arctan(cam.tanfovx), 'FoVy': 2 * np.arctan(cam.tanfovy), 'image_height': H, 'image_width': W,
+              'world_view_transform': cam.viewmatrix.float(), 'full_proj_transform': cam.projmatrix.float(),
+              'camera_center': cam.campos.float(), 'K': torch.eye(3)}
+
+    class Model:
+        visibility_flag = None
+        empty_xyz = torch.zeros((0, 3))
+
+        def get_all(self, camera, rasterizer, **kw):
+            self.leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+            return {'xyz': self.leaves['means3D'], 'opacity': self.leaves['opacities'], 'colors': self.leaves['colors'],
+                    'scaling': self.leaves['scales'], 'rotation': self.leaves['rotations']}
+    model = Model()
+    model.training = training
+    rr = R.NaiveRendererAndLoss(use_origin_render=origin)
+    rast = R.BaseRender.prepare(camera, torch.zeros(3))
+    ret, _ = rr.render(camera, rast, model)
+    fm = c_oracle.FILTER_ADD if origin else (c_oracle.FILTER_MAX if training else c_oracle.FILTER_NONE)
+    G = O.make_cotangent(3, H, W).to(torch.float32)
+    d64 = {k: v.to(torch.float64) for k, v in sc.items()}
+    ref = c_oracle.render(cam, d64['means3D'], d64['opacities'], d64['scales'], d64['rotations'], colors_precomp=d64['colors'],
+                          filter_mode=fm, dL_dimage=G.to(torch.float64), dtype=np.float64)
+    assert ret['render'].shape == (3, H, W) and rel(ret['render'], ref['image']) < 1e-4
+    assert (ret['radii'].numpy() != ref['radii']).sum() <= 1
+    if not origin:
+        ids, cnt = np.unique(ref['point_id_pixel'], return_counts=True)
+        keep = ids >= 0
+        assert (ret['point_id'].numpy() != ids[keep]).sum() <= 2 if ret['point_id'].numel() == keep.sum() else False
+        assert abs(int(ret['point_count'].sum()) - int(cnt[keep].sum())) <= 3
+        assert rel(ret['point_weight'], ref['point_weight']) < 1e-4
+    (ret['render'] * G).sum().backward()
+    assert rel(ret['viewspace_points'].grad, ref['dmeans2D']) < 2e-4
+    assert rel(model.leaves['means3D'].grad, ref['dmeans3D']) < 2e-4
+    assert rel(model.leaves['colors'].grad, ref['dcolors']) < 1e-4
+
+
+def test_fused_tree_walk_equals_the_reference_traverse_call_path(emulated_backend):
+    """The reference's own `TensorTree.traverse` driving its own `Gaussian.compute_radius` (level_of_gaussian.py:64-93, with
+    dropin/LoG_cuda/compute_radius.py in place of the JIT module, i.e. this repo's lgr_compute_radius underneath) against
+    `log_b200.tree.traverse` on the same objects: identical index tensors, also when many nodes are culled (radius 0)."""
+    import importlib.util
+    import numpy as np
+    from log_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    from log_b200.tree import traverse
+    from oracle import torch_dense as O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('LoG.cuda.compute_radius', os.path.join(root, 'dropin', 'LoG_cuda', 'compute_radius.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    saved = sys.modules.get('LoG.cuda.compute_radius')
+    sys.modules['LoG.cuda.compute_radius'] = mod
+    sys.path.insert(0, REF)
+    try:
+        import LoG.model.level_of_gaussian as L
+        from LoG.model.tensor_tree import TensorTree
+    finally:
+        sys.path.remove(REF)
+        if saved is not None:
+            sys.modules['LoG.cuda.compute_radius'] = saved
+    rng = np.random.default_rng(3)
+    cam = O.make_camera(160, 96)
+    settings = GaussianRasterizationSettings(
+        image_height=96, image_width=160, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.zeros(3), scale_modifier=1.0,
+        viewmatrix=cam.viewmatrix.float(), projmatrix=cam.projmatrix.float(), sh_degree=0, campos=cam.campos.float(),
+        prefiltered=False, debug=False)
+    rast = GaussianRasterizer(settings)
+    for max_child, n_root in ((2, 120), (4, 50)):
+        tree = TensorTree(max_child=max_child, max_level=20)
+        tree.initialize(torch.zeros(n_root, 3))
+        for rd in range(4):
+            leaves = torch.where(tree.is_leaf & (tree.depth == rd))[0]
+            tree.split(leaves[torch.from_numpy(rng.random(len(leaves)) < 0.6)])
+        P = tree.num_points
+        depth = tree.depth.numpy().astype(np.float64)
+        z = rng.uniform(0.5, 10.0, P)
+        g = L.Gaussian()
+        g.xyz = torch.from_numpy(np.stack([rng.uniform(-2.0, 2.0, P) * cam.tanfovx * z, rng.uniform(-2.0, 2.0, P) * cam.tanfovy * z, z], -1)).float()
+        sig = np.exp(rng.normal(np.log(12.0) - 1.0 * depth, 1.0)) / 3.0 * z / (160 / (2 * cam.tanfovx))
+        g.scaling = torch.from_numpy(np.log(sig[:, None] * rng.uniform(0.3, 1.0, (P, 3)))).float()
+        g.rotation = torch.from_numpy(rng.normal(size=(P, 4))).float()
+        roots = torch.where(tree.is_root)[0]
+        for min_px, max_depth in ((3.0, 1000), (6.0, 2), (1.5, 1000)):
+            tree.min_resolution_pixel = min_px
+            want = tree.traverse(g, roots.long(), rast, max_depth=max_depth)
+            got = traverse(tree, g, roots.long(), rast, max_depth=max_depth)
+            r2d = g.compute_radius(want, rast)[1]
+            assert (r2d == 0).sum() > 10                               # culled nodes are part of the case
+            if (torch.abs(r2d[r2d > 0] / min_px - 1) < 1e-4).any():     # a radius within fp32 noise of the threshold: skip it
+                continue
+            assert torch.equal(got, want), (max_child, min_px, max_depth)
