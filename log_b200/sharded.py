@@ -381,3 +381,33 @@ class SplatExchange:
         self.blend_backward_and_return(s, grad_image)
         self.barrier()          # all returned rows have landed
         return self.gather_and_project_backward(s)
+
+
+class _ShardRasterize(torch.autograd.Function):
+    """Autograd plumbing around SplatExchange.forward / backward: differentiable w.r.t. the rank's OWN Gaussians."""
+
+    @staticmethod
+    def forward(ctx, xch, settings, kw, means3D, means2D, opacities, scales, rotations, colors_precomp, shs):
+        image, radii, pid, pwp, step = xch.forward(settings, means3D, opacities.reshape(-1), scales, rotations, colors_precomp, shs, **kw)
+        ctx.xch, ctx.step, ctx.opacity_shape = xch, step, opacities.shape
+        outs = (image, radii) if pid is None else (image, radii, pid, pwp)
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, grad_image, *unused):
+        (dm3, dm2, dop, dsc, drot, dcol, dsh), pw, pc = ctx.xch.backward(ctx.step, grad_image)
+        ctx.xch.last_point_weight, ctx.xch.last_point_count = pw, pc
+        return None, None, None, dm3, dm2, dop.reshape(ctx.opacity_shape), dsc, drot, dcol, dsh
+
+
+def _rasterize(self, settings, means3D, means2D, opacities, scales, rotations, colors_precomp=None, shs=None, **kw):
+    """`GaussianRasterizer.__call__` for a rank of the shard-mode exchange: inputs are the rank's own Gaussians, the image
+    holds the rank's tile-row band (zero elsewhere), and `.backward()` of a loss on that band fills the `.grad` of the
+    rank's own tensors -- complete, no reduction needed.  Returns (image, radii[, point_id_pixel, point_weight_pixel]);
+    the per-Gaussian point_weight / point_count of the step are in `last_point_weight` / `last_point_count` after the
+    backward (they travel back with the gradients)."""
+    return _ShardRasterize.apply(self, settings, kw, means3D, means2D, opacities, scales, rotations, colors_precomp, shs)
+
+
+SplatExchange.rasterize = _rasterize

@@ -109,3 +109,28 @@ def test_random_small_configurations(emulated_backend):
 @pytest.mark.parametrize('deg', [1, 3])
 def test_fused_log_colour_activation_with_sh(emulated_backend, deg):
     gp.check_fused_log_colour_activation_with_sh(deg, size=(64, 48, 400))
+
+
+def test_shard_mode_autograd_wrapper_single_rank(emulated_backend):
+    """World size 1 (the only size one process can run through the barriers): SplatExchange.rasterize + loss.backward()
+    equal the ordinary rasteriser's image and .grad, means2D.grad included."""
+    from log_b200 import sharded
+    from oracle import torch_dense as O
+    from util import f32_camera, rel, run_gpu, settings_from_camera
+    W, H, n = 64, 48, 300
+    cam = f32_camera(O.make_camera(W, H, bg=(0.1, 0.2, 0.3)))
+    sc = O.make_scene(n, W, H, 4.0, seed=21)
+    G = O.make_cotangent(3, H, W).to(torch.float32)
+    full = run_gpu(cam, sc, G)
+    _, floats = sharded.shard_layout(n, 1, 0)
+    buf = torch.zeros(floats)
+    xch = sharded.SplatExchange(n, H, 0, 1, buf, [buf.data_ptr()], barrier=lambda: None)
+    t = {k: v.to(torch.float32).requires_grad_(True) for k, v in sc.items()}
+    m2d = torch.zeros(n, 3, requires_grad=True)
+    out = xch.rasterize(settings_from_camera(cam, torch.device('cpu')), t['means3D'], m2d, t['opacities'], t['scales'], t['rotations'],
+                        colors_precomp=t['colors'])
+    assert torch.equal(out[0], full['image']) and torch.equal(out[1], full['radii']) and torch.equal(out[2], full['point_id_pixel'])
+    (out[0] * G).sum().backward()
+    assert rel(m2d.grad, full['dmeans2D']) < 1e-5 and rel(t['means3D'].grad, full['dmeans3D']) < 1e-5
+    assert rel(t['opacities'].grad.reshape(-1), full['dopacities']) < 1e-5 and rel(t['colors'].grad, full['dcolors']) < 1e-5
+    assert torch.equal(xch.last_point_weight, full['point_weight'])
