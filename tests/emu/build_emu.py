@@ -93,7 +93,14 @@ def translate(src: str) -> str:
         pos = b + 1
 
 
-def build(force=False):
+def build(force=False, asan=None):
+    """asan=True (or LGR_EMU_ASAN=1 in the environment): AddressSanitizer build, libemu_asan.so -- run the emulated tests
+    with it as  LGR_EMU_ASAN=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python -m pytest
+    tests/test_emulated_kernels.py tests/test_emulated_pipeline.py tests/test_emulated_host.py tests/test_tree_traverse.py
+    (a CPU stand-in for compute-sanitizer memcheck: out-of-bounds accesses of global buffers and of __shared__ arrays)."""
+    global LIB
+    asan = bool(int(os.environ.get('LGR_EMU_ASAN', '0'))) if asan is None else asan
+    LIB = os.path.join(BUILD, 'libemu_asan.so' if asan else 'libemu.so')
     os.makedirs(BUILD, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in SOURCES] + [os.path.join(CSRC, 'lgr_common.cuh'), os.path.join(CSRC, 'lgr_prof.cuh'),
                                                        os.path.join(HERE, 'cuda_runtime.h'), os.path.join(HERE, 'emu_api.cpp'), os.path.join(HERE, 'emu_blend_helpers.h'),
@@ -108,7 +115,8 @@ def build(force=False):
             fh.write(translate(open(os.path.join(CSRC, f)).read()))
         objs.append(cpp)
     # a 3-CTA grid for the tree walk: every emulated CTA costs 256 fibers, and 3 CTAs make the grid-stride loops iterate
-    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-w', '-DLGR_TREE_GRID=3', '-I', HERE, '-I', CSRC, '-o', LIB + '.tmp'] + objs + \
+    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-w', '-DLGR_TREE_GRID=3'] + \
+          (['-fsanitize=address', '-fno-omit-frame-pointer'] if asan else []) + ['-I', HERE, '-I', CSRC, '-o', LIB + '.tmp'] + objs + \
           [os.path.join(HERE, 'emu_api.cpp')]
     env = dict(os.environ)
     env.pop('CC', None)
