@@ -200,12 +200,9 @@ __device__ __forceinline__ void sort_tile(uint32_t* kA, uint32_t* vA, uint32_t* 
   };
   // does any depth repeat?  (checked after the depth sort; almost never true)
   for (int s = 0; s < 32; s += RADIX_BITS) run(s, false);
-  __shared__ int tie;
-  if (threadIdx.x == 0) tie = 0;
-  __syncthreads();
-  for (int i = threadIdx.x + 1; i < len; i += SORT_THREADS) if (ki[i] == ki[i - 1]) tie = 1;
-  __syncthreads();
-  if (tie) {   // full (depth, id) order: ids first (LSD), then the depth passes again
+  int my_tie = 0;
+  for (int i = threadIdx.x + 1; i < len; i += SORT_THREADS) if (ki[i] == ki[i - 1]) my_tie = 1;
+  if (__syncthreads_or(my_tie)) {      // barrier + vote (no shared flag written by several threads)   // full (depth, id) order: ids first (LSD), then the depth passes again
     for (int s = 0; s < id_bits; s += RADIX_BITS) run(s, true);
     for (int s = 0; s < 32; s += RADIX_BITS) run(s, false);
   }

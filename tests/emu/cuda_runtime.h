@@ -19,6 +19,28 @@
 #include <type_traits>
 #include <vector>
 
+// ---- optional ThreadSanitizer build (EMU_TSAN): every WARP is a TSan fiber (TSan tracks at most ~250 live threads, fewer than
+// the CUDA threads of one CTA, so lanes of a warp share an identity), barriers / kernel boundaries are the only
+// happens-before edges, atomics are real atomics -> TSan reports data races between the warps of a CTA (shared AND global
+// memory), i.e. a CPU stand-in for compute-sanitizer racecheck (minus intra-warp hazards).  Fiber switches are "no-sync".
+#ifdef EMU_TSAN
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+#define EMU_NOTSAN __attribute__((no_sanitize("thread")))
+#define EMU_TSAN_ACQUIRE(p) __tsan_acquire((void*)(p))
+#define EMU_TSAN_RELEASE(p) __tsan_release((void*)(p))
+#else
+#define EMU_NOTSAN
+#define EMU_TSAN_ACQUIRE(p) ((void)0)
+#define EMU_TSAN_RELEASE(p) ((void)0)
+#endif
+
 #define __global__
 #define __device__
 #define __host__
@@ -60,14 +82,19 @@ struct Fiber {
   char* stack = nullptr;
   dim3 tid;
   int state = READY;
+  void* tsan = nullptr;
 };
 
 struct Cta {
-  std::vector<Fiber> fibers;
+  Fiber* fibers = nullptr;
   int nthreads = 0, alive = 0, cta_waiting = 0;
   int warp_alive[32], warp_waiting[32];
   unsigned long long scratch[32][32];   // [warp][lane] exchange slots of the warp collectives
   int cta_acc = 0;                       // __syncthreads_or / _and / _count accumulator
+  int cta_gen = 0, warp_gen[32];         // barrier generations (TSan: alternating sync objects)
+  char cta_sync[2], warp_sync[32][2], launch_sync, done_sync;
+  void* sched_tsan = nullptr;
+  void* warp_tsan[32];
   int cta_result = 0;
   std::function<void()> body;
   dim3 block_idx, block_dim, grid_dim;
@@ -79,62 +106,83 @@ inline Fiber*& cur() { static Fiber* f = nullptr; return f; }
 inline ucontext_t& sched_ctx() { static ucontext_t c; return c; }
 inline void* dyn_smem() { return cta()->dyn; }
 
-inline void yield() { swapcontext(&cur()->ctx, &sched_ctx()); }
+EMU_NOTSAN inline void yield() {
+#ifdef EMU_TSAN
+  __tsan_switch_to_fiber(cta()->sched_tsan, 1);
+#endif
+  swapcontext(&cur()->ctx, &sched_ctx());
+}
 
-inline void release_cta(Cta* c) {
-  for (auto& f : c->fibers) if (f.state == WAIT_CTA) f.state = READY;
+EMU_NOTSAN inline void release_cta(Cta* c) {
+  for (int t = 0; t < c->nthreads; t++) if (c->fibers[t].state == WAIT_CTA) c->fibers[t].state = READY;
   c->cta_waiting = 0;
 }
-inline void release_warp(Cta* c, int w) {
+EMU_NOTSAN inline void release_warp(Cta* c, int w) {
   for (int l = 0; l < 32 && w * 32 + l < c->nthreads; l++)
     if (c->fibers[w * 32 + l].state == WAIT_WARP) c->fibers[w * 32 + l].state = READY;
   c->warp_waiting[w] = 0;
 }
 
-inline void barrier_cta() {
+EMU_NOTSAN inline void barrier_cta() {
   Cta* c = cta();
-  if (++c->cta_waiting == c->alive) { release_cta(c); return; }
+  char* sync = &c->cta_sync[c->cta_gen & 1];
+  EMU_TSAN_RELEASE(sync);
+  if (++c->cta_waiting == c->alive) { c->cta_gen++; release_cta(c); EMU_TSAN_ACQUIRE(sync); return; }
   cur()->state = WAIT_CTA;
   yield();
+  EMU_TSAN_ACQUIRE(sync);
 }
-inline void barrier_warp() {
+EMU_NOTSAN inline void barrier_warp() {
   Cta* c = cta();
   const int w = cur()->tid.x >> 5;
-  if (++c->warp_waiting[w] == c->warp_alive[w]) { release_warp(c, w); return; }
+  char* sync = &c->warp_sync[w][c->warp_gen[w] & 1];
+  EMU_TSAN_RELEASE(sync);
+  if (++c->warp_waiting[w] == c->warp_alive[w]) { c->warp_gen[w]++; release_warp(c, w); EMU_TSAN_ACQUIRE(sync); return; }
   cur()->state = WAIT_WARP;
   yield();
+  EMU_TSAN_ACQUIRE(sync);
 }
 
-inline void fiber_entry() {
+EMU_NOTSAN inline void fiber_entry() {
   Cta* c = cta();
+  EMU_TSAN_ACQUIRE(&c->launch_sync);
   c->body();
+  EMU_TSAN_RELEASE(&c->done_sync);
   Fiber* f = cur();
   f->state = DONE;
   const int w = f->tid.x >> 5;
   c->alive--; c->warp_alive[w]--;
-  if (c->cta_waiting > 0 && c->cta_waiting == c->alive) release_cta(c);
-  if (c->warp_waiting[w] > 0 && c->warp_waiting[w] == c->warp_alive[w]) release_warp(c, w);
+  if (c->cta_waiting > 0 && c->cta_waiting == c->alive) { c->cta_gen++; release_cta(c); }
+  if (c->warp_waiting[w] > 0 && c->warp_waiting[w] == c->warp_alive[w]) { c->warp_gen[w]++; release_warp(c, w); }
+#ifdef EMU_TSAN
+  __tsan_switch_to_fiber(c->sched_tsan, 1);
+#endif
   swapcontext(&f->ctx, &sched_ctx());
 }
 
 constexpr size_t STACK = 192 * 1024;
 
 template <class F>
-inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
+EMU_NOTSAN inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
   if (grid.y != 1 || grid.z != 1 || block.y != 1 || block.z != 1) { fprintf(stderr, "emu: 1-D launches only\n"); abort(); }
   Cta c;
   c.nthreads = (int)block.x;
-  c.fibers.resize(c.nthreads);
-  for (auto& f : c.fibers) f.stack = (char*)malloc(STACK);
+  std::vector<Fiber> storage(c.nthreads);
+  c.fibers = storage.data();
+  for (int t = 0; t < c.nthreads; t++) c.fibers[t].stack = (char*)malloc(STACK);
   std::vector<char> dyn(smem + 64);
   c.dyn = (char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
   c.block_dim = block; c.grid_dim = grid;
   c.body = fn;
   cta() = &c;
+#ifdef EMU_TSAN
+  c.sched_tsan = __tsan_get_current_fiber();
+#endif
+  EMU_TSAN_RELEASE(&c.launch_sync);
   for (unsigned b = 0; b < grid.x; b++) {
     c.block_idx = dim3(b);
-    c.alive = c.nthreads; c.cta_waiting = 0; c.cta_acc = 0;
-    for (int w = 0; w < 32; w++) { c.warp_waiting[w] = 0; c.warp_alive[w] = 0; }
+    c.alive = c.nthreads; c.cta_waiting = 0; c.cta_acc = 0; c.cta_gen = 0;
+    for (int w = 0; w < 32; w++) { c.warp_waiting[w] = 0; c.warp_alive[w] = 0; c.warp_gen[w] = 0; }
     for (int t = 0; t < c.nthreads; t++) {
       Fiber& f = c.fibers[t];
       f.tid = dim3((unsigned)t); f.state = READY;
@@ -143,6 +191,10 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
       f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = STACK; f.ctx.uc_link = nullptr;
       makecontext(&f.ctx, (void (*)())fiber_entry, 0);
     }
+#ifdef EMU_TSAN
+    for (int w = 0; w * 32 < c.nthreads; w++) c.warp_tsan[w] = __tsan_create_fiber(0);
+    for (int t = 0; t < c.nthreads; t++) c.fibers[t].tsan = c.warp_tsan[t >> 5];
+#endif
     while (c.alive > 0) {
       bool ran = false;
       for (int t = 0; t < c.nthreads; t++) {
@@ -150,6 +202,9 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
         if (f.state != READY) continue;
         ran = true;
         cur() = &f;
+#ifdef EMU_TSAN
+        __tsan_switch_to_fiber(f.tsan, 1);
+#endif
         swapcontext(&sched_ctx(), &f.ctx);
       }
       if (!ran) {
@@ -159,26 +214,34 @@ inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
         abort();
       }
     }
+#ifdef EMU_TSAN
+    for (int w = 0; w * 32 < c.nthreads; w++) __tsan_destroy_fiber(c.warp_tsan[w]);
+    // The next CTA reuses the same __shared__ storage, so it is ordered after this one.  Consequence: races BETWEEN CTAs on
+    // global memory are not reported (compute-sanitizer racecheck does not look at global memory either).
+    EMU_TSAN_ACQUIRE(&c.done_sync);
+    EMU_TSAN_RELEASE(&c.launch_sync);
+#endif
   }
-  for (auto& f : c.fibers) free(f.stack);
+  EMU_TSAN_ACQUIRE(&c.done_sync);
+  for (int t = 0; t < c.nthreads; t++) free(c.fibers[t].stack);
   cta() = nullptr; cur() = nullptr;
 }
 
 // ---- warp collectives -------------------------------------------------------------------------------------------
-inline int lane_id() { return cur()->tid.x & 31; }
-inline int warp_id() { return cur()->tid.x >> 5; }
-inline bool lane_alive(int l) {
+EMU_NOTSAN inline int lane_id() { return cur()->tid.x & 31; }
+EMU_NOTSAN inline int warp_id() { return cur()->tid.x >> 5; }
+EMU_NOTSAN inline bool lane_alive(int l) {
   Cta* c = cta();
   const int t = warp_id() * 32 + l;
   return t < c->nthreads && c->fibers[t].state != DONE;
 }
-template <class T> inline void publish(T v) {
+template <class T> EMU_NOTSAN inline void publish(T v) {
   static_assert(sizeof(T) <= 8, "collective payload");
   unsigned long long u = 0; memcpy(&u, &v, sizeof(T));
   cta()->scratch[warp_id()][lane_id()] = u;
   barrier_warp();
 }
-template <class T> inline T peek(int l) { T v; memcpy(&v, &cta()->scratch[warp_id()][l], sizeof(T)); return v; }
+template <class T> EMU_NOTSAN inline T peek(int l) { T v; memcpy(&v, &cta()->scratch[warp_id()][l], sizeof(T)); return v; }
 }  // namespace emu
 
 #define threadIdx (emu::cur()->tid)
@@ -190,7 +253,7 @@ inline void __syncthreads() { emu::barrier_cta(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier_warp(); }
 inline void __trap() { fprintf(stderr, "emu: __trap()\n"); abort(); }
 
-inline int __syncthreads_reduce(int pred, int mode) {   // 0 or, 1 and, 2 count
+EMU_NOTSAN inline int __syncthreads_reduce(int pred, int mode) {   // 0 or, 1 and, 2 count
   emu::Cta* c = emu::cta();
   // phase 1: everybody contributes
   if (c->cta_waiting == 0) c->cta_acc = (mode == 1) ? 1 : 0;
@@ -279,9 +342,22 @@ inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f;
 inline float __fdividef(float a, float b) { return a / b; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 
-template <class T> inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }
-inline int atomicAdd(int* p, unsigned v) { const int o = *p; *p = o + (int)v; return o; }
-template <class T> inline T atomicMax(T* p, T v) { const T o = *p; if (v > o) *p = v; return o; }
+// relaxed atomics, like the device's: no ordering of other data
+template <class T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float* p, float v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(p);
+  uint32_t o = __atomic_load_n(u, __ATOMIC_RELAXED), n;
+  float f;
+  do { memcpy(&f, &o, 4); f += v; memcpy(&n, &f, 4); } while (!__atomic_compare_exchange_n(u, &o, n, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  memcpy(&f, &o, 4);
+  return f;
+}
+inline int atomicAdd(int* p, unsigned v) { return __atomic_fetch_add(p, (int)v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicMax(T* p, T v) {
+  T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return o;
+}
 
 #define EMU_MINMAX(T)                                   \
   inline T min(T a, T b) { return b < a ? b : a; }      \
@@ -309,7 +385,7 @@ inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline float4 atomicAdd(float4* p, float4 v) {
-  const float4 o = *p;
-  p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
+  float4 o;
+  o.x = atomicAdd(&p->x, v.x); o.y = atomicAdd(&p->y, v.y); o.z = atomicAdd(&p->z, v.z); o.w = atomicAdd(&p->w, v.w);
   return o;
 }

@@ -12,9 +12,6 @@ inline float rcp_approx(float x) { return 1.0f / x; }
 inline float4 lds_f4(uint32_t a) { return *reinterpret_cast<const float4*>(emu_shared_ptr(a)); }
 inline float2 lds_f2(uint32_t a) { return *reinterpret_cast<const float2*>(emu_shared_ptr(a)); }
 inline uint32_t pin_reg(uint32_t v) { return v; }
-inline void red_shared_max_u32(uint32_t a, unsigned v) {
-  unsigned* p = reinterpret_cast<unsigned*>(emu_shared_ptr(a));
-  if (v > *p) *p = v;
-}
-inline void red_shared_add_f32(uint32_t a, float v) { *reinterpret_cast<float*>(emu_shared_ptr(a)) += v; }
+inline void red_shared_max_u32(uint32_t a, unsigned v) { atomicMax(reinterpret_cast<unsigned*>(emu_shared_ptr(a)), v); }
+inline void red_shared_add_f32(uint32_t a, float v) { atomicAdd(reinterpret_cast<float*>(emu_shared_ptr(a)), v); }
 }  // namespace lgr
