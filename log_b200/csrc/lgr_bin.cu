@@ -202,7 +202,9 @@ __device__ __forceinline__ void sort_tile(uint32_t* kA, uint32_t* vA, uint32_t* 
   for (int s = 0; s < 32; s += RADIX_BITS) run(s, false);
   int my_tie = 0;
   for (int i = threadIdx.x + 1; i < len; i += SORT_THREADS) if (ki[i] == ki[i - 1]) my_tie = 1;
-  if (__syncthreads_or(my_tie)) {      // barrier + vote (no shared flag written by several threads)   // full (depth, id) order: ids first (LSD), then the depth passes again
+  // barrier + vote (no shared flag written by several threads); on a tie: full (depth, id) order -- ids first (LSD),
+  // then the depth passes again
+  if (__syncthreads_or(my_tie)) {
     for (int s = 0; s < id_bits; s += RADIX_BITS) run(s, true);
     for (int s = 0; s < 32; s += RADIX_BITS) run(s, false);
   }
