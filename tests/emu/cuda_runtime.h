@@ -216,10 +216,14 @@ EMU_NOTSAN inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
     }
 #ifdef EMU_TSAN
     for (int w = 0; w * 32 < c.nthreads; w++) __tsan_destroy_fiber(c.warp_tsan[w]);
-    // The next CTA reuses the same __shared__ storage, so it is ordered after this one.  Consequence: races BETWEEN CTAs on
-    // global memory are not reported (compute-sanitizer racecheck does not look at global memory either).
+    // The next CTA reuses the same __shared__ storage, so by default it is ordered after this one; races BETWEEN CTAs on
+    // global memory are then not reported (compute-sanitizer racecheck does not look at global memory either).
+    // EMU_TSAN_UNORDERED_CTAS leaves the CTAs of a launch concurrent: global-memory races between CTAs are reported, and so
+    // is every reuse of the emulated shared storage -- filter those reports by location (tests/emu/README.md).
+#ifndef EMU_TSAN_UNORDERED_CTAS
     EMU_TSAN_ACQUIRE(&c.done_sync);
     EMU_TSAN_RELEASE(&c.launch_sync);
+#endif
 #endif
   }
   EMU_TSAN_ACQUIRE(&c.done_sync);
