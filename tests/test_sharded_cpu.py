@@ -3,6 +3,7 @@ gradient packing and the reduce-to-owners exchange.  The per-rank partial gradie
 only its band of tile rows is NOT needed here: the exchange is linear, so random partials test it exactly."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -124,3 +125,97 @@ def test_splat_exchange_rejects_cpu_buffers_and_bad_peer_lists():
         sharded.SplatExchange(1000, 64, 0, 2, buf, [buf.data_ptr(), 0], barrier=lambda: None)      # CPU tensor: no CPU path
     with pytest.raises(ValueError):
         sharded.SplatExchange(1000, 64, 0, 40, buf, [0] * 40, barrier=lambda: None)                # too many ranks
+
+
+# ---- shard mode as real processes: gloo barriers, exchange buffers in POSIX shared memory, kernels on the CPU emulation ----
+def _shard_worker(rank, world, port, tag, n, W, H, steps, out):
+    """One rank of SplatExchange.forward()/backward() (through the autograd wrapper) with the real barrier structure."""
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, 'tests'), os.path.join(root, 'tests', 'emu')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import build_emu
+    import util
+    from log_b200 import _capi
+    from oracle import torch_dense as O
+    from util import f32_camera, rel, run_gpu, settings_from_camera
+    _capi._lib = _capi.bind(ctypes.CDLL(build_emu.build()))          # TEST ONLY: the emulated kernels (tests/emu)
+    _capi.current_stream = lambda: None
+    _capi.require_cuda = lambda t, name: None
+    util.DEVICE = ['cpu']
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    _, floats = sharded.shard_layout(n, world, rank)
+    maps = [torch.from_file(f'/dev/shm/lgr_xch_{tag}_{r}', shared=True, size=floats, dtype=torch.float32) for r in range(world)]
+    if True:      # every rank initialises its own buffer, then everybody waits
+        maps[rank].fill_(float('nan'))
+    dist.barrier()
+    xch = sharded.SplatExchange(n, H, rank, world, maps[rank], [m.data_ptr() for m in maps], barrier=dist.barrier)
+    dist.barrier()
+    cam = f32_camera(O.make_camera(W, H, bg=(0.1, 0.2, 0.3)))
+    ok = True
+    for step in range(steps):
+        sc = O.make_scene(n, W, H, 4.0 if step % 2 == 0 else 1.5, seed=70 + step)
+        G = O.make_cotangent(3, H, W, seed=step).to(torch.float32)
+        full = run_gpu(cam, sc, G)                                     # single-rank reference, computed by every process
+        t = {k: v[xch.lo:xch.hi].to(torch.float32).clone().requires_grad_(True) for k, v in sc.items()}
+        m2d = torch.zeros(xch.hi - xch.lo, 3, requires_grad=True)
+        image, radii, pid, pwp = xch.rasterize(settings_from_camera(cam, torch.device('cpu')), t['means3D'], m2d, t['opacities'],
+                                               t['scales'], t['rotations'], colors_precomp=t['colors'])
+        (image * G).sum().backward()                                    # loss on this rank's band only (zero elsewhere)
+        a, b = xch.band[0] * 16, min(xch.band[1] * 16, H)
+        ok &= torch.equal(image[:, a:b], full['image'][:, a:b]) and float(image[:, :a].abs().sum() + image[:, b:].abs().sum()) == 0.0
+        ok &= torch.equal(radii, full['radii'][xch.lo:xch.hi]) and torch.equal(pid[a:b], full['point_id_pixel'][a:b])
+        ok &= torch.equal(xch.last_point_weight, full['point_weight'][xch.lo:xch.hi])
+        for k, g in (('dmeans3D', t['means3D'].grad), ('dmeans2D', m2d.grad), ('dopacities', t['opacities'].grad.reshape(-1)),
+                     ('dscales', t['scales'].grad), ('drotations', t['rotations'].grad), ('dcolors', t['colors'].grad)):
+            want = full[k][xch.lo:xch.hi]
+            ok &= bool(torch.isfinite(g).all()) and (rel(g, want) < 2e-5 or float(want.abs().max()) == 0.0)
+    out.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_shard_mode_as_separate_processes_with_real_barriers(world):
+    """What the single-process emulation cannot exercise: SplatExchange.forward()/backward() as written, i.e. with their
+    barriers, run by `world` concurrent processes (gloo) whose exchange buffers live in POSIX shared memory mapped at
+    different addresses in every process -- exactly how NVLink peer mappings are addressed.  Two steps through the same
+    buffers; every rank checks its band and its own Gaussians' gradients against the single-rank result."""
+    import uuid
+    n, W, H, steps = 500, 64, 80, 2
+    emu_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu')
+    if emu_dir not in sys.path:
+        sys.path.insert(0, emu_dir)
+    import build_emu
+    build_emu.build()                      # once, here: the workers must not race to rebuild it
+    tag = uuid.uuid4().hex[:8]
+    _, floats = sharded.shard_layout(n, world, 0)
+    files = [f'/dev/shm/lgr_xch_{tag}_{r}' for r in range(world)]
+    for f in files:
+        with open(f, 'wb') as fh:
+            fh.truncate(floats * 4)
+    try:
+        port = _free_port()
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_shard_worker, args=(r, world, port, tag, n, W, H, steps, q)) for r in range(world)]
+        [p.start() for p in procs]
+        res, waited = {}, 0.0
+        while len(res) < world and waited < 240:
+            try:
+                r, ok = q.get(timeout=2)
+                res[r] = ok
+            except Exception:
+                waited += 2
+                if any(p.exitcode not in (None, 0) for p in procs):      # a worker died: do not wait for the others
+                    break
+        [p.join(30) for p in procs]
+        [p.kill() for p in procs if p.is_alive()]
+        assert all(p.exitcode == 0 for p in procs)
+        assert res == {r: True for r in range(world)}, res
+    finally:
+        for f in files:
+            if os.path.exists(f):
+                os.remove(f)
