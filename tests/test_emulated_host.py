@@ -134,3 +134,9 @@ def test_shard_mode_autograd_wrapper_single_rank(emulated_backend):
     assert rel(m2d.grad, full['dmeans2D']) < 1e-5 and rel(t['means3D'].grad, full['dmeans3D']) < 1e-5
     assert rel(t['opacities'].grad.reshape(-1), full['dopacities']) < 1e-5 and rel(t['colors'].grad, full['dcolors']) < 1e-5
     assert torch.equal(xch.last_point_weight, full['point_weight'])
+
+
+def test_baseline_config0_shape(emulated_backend):
+    """BASELINE.json configs[0] -- 1k synthetic Gaussians, 256x256 -- through the public API on the emulated kernels, against
+    the oracle (the same case runs on hardware as the first entry of test_gpu_parity.CASES)."""
+    gp.test_forward_backward_parity(True, *gp.CASES[0])
