@@ -11,7 +11,7 @@ run() {  # $1 = label, env in front
 }
 LGR_MULTI=band run band
 LGR_MULTI=shard run shard
-timeout 900 python -m pytest tests/test_gpu_multirank.py -q -m gpu -x -p no:cacheprovider > gpurun_out/next/multirank.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_multirank.py tests/test_zz_gpu_shard_multirank.py -q -m gpu --runxfail -p no:cacheprovider > gpurun_out/next/multirank.log 2>&1
 echo "multirank rc=$?" >> gpurun_out/next/summary.txt
 python - <<'PY'
 import json, glob
