@@ -140,3 +140,10 @@ def test_baseline_config0_shape(emulated_backend):
     """BASELINE.json configs[0] -- 1k synthetic Gaussians, 256x256 -- through the public API on the emulated kernels, against
     the oracle (the same case runs on hardware as the first entry of test_gpu_parity.CASES)."""
     gp.test_forward_backward_parity(True, *gp.CASES[0])
+
+
+@pytest.mark.parametrize('n', [3500, 15000])
+def test_long_tile_lists(emulated_backend, n):
+    """Lists beyond the main sort launch (the long-tile launch) and beyond the shared-memory capacity (LSD fallback over
+    global scratch), through the public API, with thousands of splats per pixel."""
+    gp.test_long_tile_lists(True, n)
