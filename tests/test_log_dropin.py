@@ -168,3 +168,85 @@ def test_fused_tree_walk_equals_the_reference_traverse_call_path(emulated_backen
             if (torch.abs(r2d[r2d > 0] / min_px - 1) < 1e-4).any():     # a radius within fp32 noise of the threshold: skip it
                 continue
             assert torch.equal(got, want), (max_child, min_px, max_depth)
+
+
+def test_log_training_loop_in_miniature(emulated_backend, monkeypatch):
+    """BASELINE config 3 in miniature: LoG's OWN classes -- `LoG` / `GaussianPoint` / `TensorTree` / `Counter` /
+    `SparseOptimizer` (LoG/model/level_of_gaussian.py) and `NaiveRendererAndLoss` (LoG/render/renderer.py) -- drive a few
+    training iterations exactly as `Trainer.training_step` does (LoG/utils/trainer.py:144-166: render, loss.backward(),
+    update_by_output, step) with this repo's rasteriser and compute_radius behind them (kernels on the CPU emulation).
+    Checked: the first loss equals LoG's own loss applied to the ORACLE's image of the same parameters, the loss goes down,
+    the parameters move, the counters fill.  Test-only stand-ins: simple_knn.distCUDA2 (a CUDA-only third party, used once
+    for the initial scales) and Tensor.cuda()."""
+    import importlib.util
+    import types
+    import numpy as np
+    from oracle import c_oracle, torch_dense as O
+    from util import rel
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def dist2(x):                                  # mean squared distance to the 3 nearest neighbours, as distCUDA2
+        d = torch.cdist(x, x)
+        d.fill_diagonal_(float('inf'))
+        return (d.topk(3, largest=False).values ** 2).mean(-1)
+    knn, knn_c = types.ModuleType('simple_knn'), types.ModuleType('simple_knn._C')
+    knn_c.distCUDA2, knn._C = dist2, knn_c
+    monkeypatch.setitem(sys.modules, 'simple_knn', knn)
+    monkeypatch.setitem(sys.modules, 'simple_knn._C', knn_c)
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    spec = importlib.util.spec_from_file_location('LoG.cuda.compute_radius', os.path.join(root, 'dropin', 'LoG_cuda', 'compute_radius.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setitem(sys.modules, 'LoG.cuda.compute_radius', mod)
+    monkeypatch.syspath_prepend(REF)
+    import LoG.model.level_of_gaussian as L
+    import LoG.render.renderer as R
+
+    class AD(dict):
+        __getattr__ = dict.__getitem__
+
+    rng = np.random.default_rng(0)
+    W, H, n = 64, 48, 300
+    cam = O.make_camera(W, H)
+    z = rng.uniform(2, 6, n)
+    xyz = np.stack([rng.uniform(-1, 1, n) * cam.tanfovx * z, rng.uniform(-1, 1, n) * cam.tanfovy * z, z], -1).astype(np.float32)
+    colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    model = L.LoG(gaussian=dict(init_ply=dict(filename={'xyz': xyz, 'colors': colors}, scale3d=1., init_opacity=0.5), sh_degree=1, xyz_scale=1.),
+                  tree=AD(max_child=2, max_level=5),
+                  optimizer=AD(optimize_keys=['xyz', 'colors', 'scaling', 'opacity', 'rotation', 'shs'], opt_all_levels=True,
+                               lr_dict=dict(xyz=0.00016, xyz_final=0.0000016, xyz_scale=1., colors=0.0025, shs=0.000125, scaling=0.005,
+                                            opacity=0.05, rotation=0.001, max_steps=100)),
+                  densify_and_remove=AD(upgrade_sh_iter=10, densify_from_iter=1, densify_every_iter=1, upgrade_repeat=50),
+                  use_view_correction=False)
+    model.base_iter = 1
+    model.training_setup()
+    model.train()
+    rend = R.NaiveRendererAndLoss(split='train')
+    batch = {'camera': {'camera_center': cam.campos.float()[None], 'world_view_transform': cam.viewmatrix.float()[None],
+                        'full_proj_transform': cam.projmatrix.float()[None], 'image_width': torch.tensor([W]), 'image_height': torch.tensor([H]),
+                        'FoVx': torch.tensor([2 * np.arctan(cam.tanfovx)]), 'FoVy': torch.tensor([2 * np.arctan(cam.tanfovy)]),
+                        'K': torch.eye(3)[None], 'R': torch.eye(3)[None], 'T': torch.zeros(1, 3, 1)},
+             'image': torch.rand(1, H, W, 3, generator=torch.Generator().manual_seed(1)), 'index': torch.tensor([0])}
+    g = model.gaussian
+    act = g.activation
+    start = {k: getattr(g, k).clone() for k in ('xyz', 'scaling', 'opacity', 'rotation', 'colors')}
+    ref = c_oracle.render(cam, g.xyz.double(), act.opacity_activation(g.opacity).double(), act.scaling_activation(g.scaling).double(),
+                          act.rotation_activation(g.rotation).double(), colors_precomp=(g.colors * O.C0 + 0.5).double(),
+                          filter_mode=c_oracle.FILTER_MAX, dtype=np.float64)
+    losses = []
+    for it in range(5):
+        model.clear()
+        out = rend(batch, model)                       # Trainer.training_step, trainer.py:144-166
+        out['loss'].backward()
+        model.update_by_output(out)
+        model.step()
+        losses.append(float(out['loss'].detach()))
+        if it == 0:
+            first = {}
+            rend.calculate_loss(batch['image'].permute(0, 3, 1, 2), torch.from_numpy(ref['image']).float()[None], first)
+            assert abs(losses[0] - float(first['loss'])) < 1e-5 * max(1.0, abs(losses[0]))
+            assert rel(out['render'][0], ref['image']) < 1e-4
+    assert all(b < a for a, b in zip(losses, losses[1:])), losses
+    assert all(float((getattr(g, k) - start[k]).abs().max()) > 0 for k in start)       # SparseOptimizer moved every parameter group
+    assert int(model.counter.visible_count.sum()) > 0 and float(model.counter.weights_max.max()) > 0
+    assert int(model.optimizer.global_steps.item()) == 5
