@@ -170,14 +170,8 @@ def test_fused_tree_walk_equals_the_reference_traverse_call_path(emulated_backen
             assert torch.equal(got, want), (max_child, min_px, max_depth)
 
 
-def test_log_training_loop_in_miniature(emulated_backend, monkeypatch):
-    """BASELINE config 3 in miniature: LoG's OWN classes -- `LoG` / `GaussianPoint` / `TensorTree` / `Counter` /
-    `SparseOptimizer` (LoG/model/level_of_gaussian.py) and `NaiveRendererAndLoss` (LoG/render/renderer.py) -- drive a few
-    training iterations exactly as `Trainer.training_step` does (LoG/utils/trainer.py:144-166: render, loss.backward(),
-    update_by_output, step) with this repo's rasteriser and compute_radius behind them (kernels on the CPU emulation).
-    Checked: the first loss equals LoG's own loss applied to the ORACLE's image of the same parameters, the loss goes down,
-    the parameters move, the counters fill.  Test-only stand-ins: simple_knn.distCUDA2 (a CUDA-only third party, used once
-    for the initial scales) and Tensor.cuda()."""
+def _miniature_log(monkeypatch, densify=None):
+    """LoG's own model / renderer / batch for a 64x48 view of 300 points (see test_log_training_loop_in_miniature)."""
     import importlib.util
     import types
     import numpy as np
@@ -216,7 +210,7 @@ def test_log_training_loop_in_miniature(emulated_backend, monkeypatch):
                   optimizer=AD(optimize_keys=['xyz', 'colors', 'scaling', 'opacity', 'rotation', 'shs'], opt_all_levels=True,
                                lr_dict=dict(xyz=0.00016, xyz_final=0.0000016, xyz_scale=1., colors=0.0025, shs=0.000125, scaling=0.005,
                                             opacity=0.05, rotation=0.001, max_steps=100)),
-                  densify_and_remove=AD(upgrade_sh_iter=10, densify_from_iter=1, densify_every_iter=1, upgrade_repeat=50),
+                  densify_and_remove=AD(dict(upgrade_sh_iter=10, densify_from_iter=1, densify_every_iter=1, upgrade_repeat=50), **(densify or {})),
                   use_view_correction=False)
     model.base_iter = 1
     model.training_setup()
@@ -227,6 +221,21 @@ def test_log_training_loop_in_miniature(emulated_backend, monkeypatch):
                         'FoVx': torch.tensor([2 * np.arctan(cam.tanfovx)]), 'FoVy': torch.tensor([2 * np.arctan(cam.tanfovy)]),
                         'K': torch.eye(3)[None], 'R': torch.eye(3)[None], 'T': torch.zeros(1, 3, 1)},
              'image': torch.rand(1, H, W, 3, generator=torch.Generator().manual_seed(1)), 'index': torch.tensor([0])}
+    return model, rend, batch, cam
+
+
+def test_log_training_loop_in_miniature(emulated_backend, monkeypatch):
+    """BASELINE config 3 in miniature: LoG's OWN classes -- `LoG` / `GaussianPoint` / `TensorTree` / `Counter` /
+    `SparseOptimizer` (LoG/model/level_of_gaussian.py) and `NaiveRendererAndLoss` (LoG/render/renderer.py) -- drive a few
+    training iterations exactly as `Trainer.training_step` does (LoG/utils/trainer.py:144-166: render, loss.backward(),
+    update_by_output, step) with this repo's rasteriser and compute_radius behind them (kernels on the CPU emulation).
+    Checked: the first loss equals LoG's own loss applied to the ORACLE's image of the same parameters, the loss goes down,
+    the parameters move, the counters fill.  Test-only stand-ins: simple_knn.distCUDA2 (a CUDA-only third party, used once
+    for the initial scales) and Tensor.cuda()."""
+    import numpy as np
+    from oracle import c_oracle, torch_dense as O
+    from util import rel
+    model, rend, batch, cam = _miniature_log(monkeypatch)
     g = model.gaussian
     act = g.activation
     start = {k: getattr(g, k).clone() for k in ('xyz', 'scaling', 'opacity', 'rotation', 'colors')}
@@ -250,3 +259,43 @@ def test_log_training_loop_in_miniature(emulated_backend, monkeypatch):
     assert all(float((getattr(g, k) - start[k]).abs().max()) > 0 for k in start)       # SparseOptimizer moved every parameter group
     assert int(model.counter.visible_count.sum()) > 0 and float(model.counter.weights_max.max()) > 0
     assert int(model.optimizer.global_steps.item()) == 5
+
+
+def test_log_training_loop_with_tree_nodes_and_the_fused_walk(emulated_backend, monkeypatch):
+    """The same loop taken into LoG's depth stage: `upgrade_tree`, `update_depth_stage` (LoG's own Splitter creates child
+    nodes), then training continues through `LoG.prepare` -> `render_to_check` -> `TensorTree.traverse`
+    (level_of_gaussian.py:223-257).  `tree.traverse` is replaced by `log_b200.tree.traverse`; in every call the fused walk
+    returns exactly the tensor LoG's own traverse returns, and the loss keeps falling."""
+    from log_b200.tree import traverse as fused
+    model, rend, batch, cam = _miniature_log(monkeypatch, densify=dict(
+        split_grad_thres=0.0, radius2d_thres=0, min_steps_split=0, remove_weights_thres=0.005, max_split_points=20000,
+        sort_method='radii', scaling_decay=0.9))
+
+    def train(iters):
+        out_losses = []
+        for _ in range(iters):
+            model.clear()
+            out = rend(batch, model)
+            out['loss'].backward()
+            model.update_by_output(out)
+            model.step()
+            out_losses.append(float(out['loss'].detach()))
+        return out_losses, out
+    train(3)
+    model.set_stage('depth')
+    model.upgrade_tree()                       # level_of_gaussian.py:527-533
+    train(3)
+    model.update_depth_stage(10)               # :454-525 -> tree.split_and_remove + Splitter
+    assert model.tree.num_nodes > 0 and model.num_points > 300
+    reference_traverse, agree = model.tree.traverse, []
+
+    def both(g, root_index, rasterizer, max_depth=1000):
+        want = reference_traverse(g, root_index, rasterizer, max_depth=max_depth)
+        got = fused(model.tree, g, root_index, rasterizer, max_depth=max_depth)
+        agree.append(bool(torch.equal(got, want)))
+        return got
+    model.tree.traverse = both
+    losses, out = train(4)
+    assert agree == [True] * 4
+    assert losses[-1] < losses[0], losses
+    assert out['visibility_flag'][0]['index_node'].numel() > 0       # parents and leaves are both in play
