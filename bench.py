@@ -112,6 +112,25 @@ def make_inputs(workload, dtype=torch.float32):
     return cam, sc, G
 
 
+def morton_order(cam, sc, W, H):
+    """Permute the scene so that neighbours in memory are neighbours on screen (Morton order of the projected centre, 4-pixel
+    cells): a diagnostic for the same-address atomics of binning, which a spatially random order never stresses."""
+    m = sc['means3D'].double()
+    P = cam.projmatrix.double()
+    hom = m @ P[:3] + P[3]
+    ndc = hom[:, :2] / (hom[:, 3:4] + 1e-7)
+    px = (((ndc[:, 0] + 1) * W - 1) * 0.5).clamp(0, W - 1).long() >> 2
+    py = (((ndc[:, 1] + 1) * H - 1) * 0.5).clamp(0, H - 1).long() >> 2
+
+    def spread(v):
+        v = (v | (v << 8)) & 0x00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F
+        v = (v | (v << 2)) & 0x33333333
+        return (v | (v << 1)) & 0x55555555
+    perm = torch.argsort(spread(px) | (spread(py) << 1))
+    return {k: v[perm].contiguous() for k, v in sc.items()}
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port (C, OpenMP, all host threads) on a bounded sample of the workload."""
     if rank != 0:
@@ -153,6 +172,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--order', default='random', choices=['random', 'morton'],
+                    help='order of the synthetic Gaussians in memory: random (SURVEY 8d, the default and the reported metric) or '
+                         'sorted along a Morton curve of their screen position (spatially coherent, like tree-ordered LoG data)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -177,6 +199,8 @@ def main():
 
     n, W, H, r, deg = WORKLOADS[args.workload]
     cam, sc, G = make_inputs(args.workload)
+    if args.order == 'morton':
+        sc = morton_order(cam, sc, W, H)
     host = {k: v.pin_memory() for k, v in sc.items()}
     host_G = G.pin_memory()
     settings = GaussianRasterizationSettings(
@@ -395,7 +419,7 @@ def main():
         'metric': 'gaussians_per_s_fwd_bwd', 'value': n / (ms_step * 1e-3), 'unit': 'Gaussians/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / (ms_step * 1e-3) / 1e6,
-        'config': {'workload': workload_name(args.workload),
+        'config': {'workload': workload_name(args.workload) + ('' if args.order == 'random' else f' [memory order: {args.order}]'),
                    'parallelism': (f'Gaussians sharded x{world} + tile-row bands x{world}: splat records pushed to the band owners, 2D gradients returned, over NVLink peer memory (shard mode)') if shard is not None else (f'tile-row bands x{world}, gradient rows ' + ('pushed to owner ranks over NVLink peer memory (fused in the backward kernel)' if peer is not None else 'NCCL all-to-all to owner ranks')) if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
                    'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible']},
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
