@@ -197,7 +197,19 @@ EMU_NOTSAN inline void launch(dim3 grid, dim3 block, size_t smem, F fn) {
 #endif
     while (c.alive > 0) {
       bool ran = false;
-      for (int t = 0; t < c.nthreads; t++) {
+      // EMU_SCHED_SEED=<n> in the environment: visit the runnable threads in a different pseudo-random order on every pass
+      // (default: ascending thread id).  Results must not depend on it beyond floating-point summation order.
+      static const char* seed_env = getenv("EMU_SCHED_SEED");
+      static unsigned long long rng = seed_env ? 0x9E3779B97F4A7C15ull * (1 + strtoull(seed_env, nullptr, 10)) : 0;
+      unsigned start = 0, stride = 1;
+      if (seed_env) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        start = (unsigned)(rng % (unsigned)c.nthreads);
+        stride = 1 + 2 * (unsigned)((rng >> 32) % 64);                 // odd stride: a permutation of a power-of-two thread count
+        if (c.nthreads & (c.nthreads - 1)) stride = 1;                 // not a power of two: just rotate
+      }
+      for (int k = 0; k < c.nthreads; k++) {
+        const int t = (int)((start + (unsigned long long)k * stride) % (unsigned)c.nthreads);
         Fiber& f = c.fibers[t];
         if (f.state != READY) continue;
         ran = true;
