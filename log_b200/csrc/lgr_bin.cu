@@ -123,6 +123,63 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
     }
 }
 
+// Variant with warp-aggregated slot requests (compile with -DLGR_AGG_ATOMICS=1; not band mode): lanes of a warp that ask
+// for a slot in the SAME tile are found with match.any, one lane reserves all their slots with a single returning atomic
+// and the others take consecutive offsets.  With spatially random input almost no two lanes share a tile and this only
+// costs the match; with spatially coherent input (tree-ordered LoG data, `bench.py --order morton`) it turns up to 32
+// same-address atomics -- which the L2 serialises -- into one.  Every lane stays in the kernel to the end (no early
+// return) so that the collectives are convergent.
+#ifndef LGR_AGG_ATOMICS
+#define LGR_AGG_ATOMICS 0
+#endif
+__global__ void __launch_bounds__(SCATTER_THREADS)
+bin_scatter_agg_kernel(View v, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
+                       const int32_t* __restrict__ tile_start, int32_t* __restrict__ cursor, uint32_t* __restrict__ inst_key,
+                       uint32_t* __restrict__ inst_val) {
+  const int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  uint32_t key = 0;
+  bool live = false;
+  if (i < n) {
+    const int rad = radii[i];
+    if (rad > 0) {
+      const float4 r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);
+      const float4 r1 = ldg4(splat + i * LGR_SPLAT_FLOATS + 4);
+      if (r1.z > 0.f) {
+        key = __float_as_uint(__ldg(splat + i * LGR_SPLAT_FLOATS + 11));
+        tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
+        live = true;
+      }
+    }
+  }
+  const int w = x1 - x0, cnt = live ? w * (y1 - y0) : 0;
+  const bool small = cnt <= 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int t = -1 - lane;                                   // idle lanes: distinct keys, a group of one that does nothing
+    if (small && k < cnt) t = (y0 + k / max(w, 1) - v.row0) * v.gx + x0 + k % max(w, 1);
+    const unsigned peers = __match_any_sync(0xffffffffu, t);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (t >= 0 && lane == leader) base = atomicAdd(cursor + t * CSTRIDE, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (t >= 0) {
+      const int pos = __ldg(tile_start + t) + base + __popc(peers & ((1u << lane) - 1u));
+      inst_key[pos] = key;
+      inst_val[pos] = (uint32_t)i;
+    }
+  }
+  if (!small)                                            // big splats: one request per tile, not aggregated
+    for (int ty = y0; ty < y1; ty++)
+      for (int tx = x0; tx < x1; tx++) {
+        const int t = (ty - v.row0) * v.gx + tx;
+        const int pos = tile_start[t] + atomicAdd(cursor + t * CSTRIDE, 1);
+        inst_key[pos] = key;
+        inst_val[pos] = (uint32_t)i;
+      }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // stable LSD radix sort (fallback for lists longer than the shared-memory capacity; operates on global scratch)
 // ---------------------------------------------------------------------------------------------------------
@@ -466,6 +523,11 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
   const unsigned blocks = (unsigned)((n + SCATTER_THREADS - 1) / SCATTER_THREADS);
   {
     ProfScope ps(K_BIN_SCATTER, st);
+#if LGR_AGG_ATOMICS
+    if (v.num_owners == 0)
+      bin_scatter_agg_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val);
+    else
+#endif
     bin_scatter_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val);
   }
   LGR_CHECK_LAUNCH();

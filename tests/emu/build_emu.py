@@ -101,7 +101,9 @@ def build(force=False, asan=None):
     global LIB
     asan = bool(int(os.environ.get('LGR_EMU_ASAN', '0'))) if asan is None else asan
     tsan = int(os.environ.get('LGR_EMU_TSAN', '0'))      # ThreadSanitizer build (2: CTAs of a launch left unordered), see cuda_runtime.h
-    LIB = os.path.join(BUILD, ('libemu_tsan%d.so' % tsan) if tsan else 'libemu_asan.so' if asan else 'libemu.so')
+    extra = os.environ.get('LGR_EMU_EXTRA', '').split()      # e.g. -DLGR_AGG_ATOMICS=1: compile-time knobs of the kernels
+    tag = ('_' + ''.join(ch for ch in ''.join(extra) if ch.isalnum())) if extra else ''
+    LIB = os.path.join(BUILD, (('libemu_tsan%d' % tsan) if tsan else 'libemu_asan' if asan else 'libemu') + tag + '.so')
     os.makedirs(BUILD, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in SOURCES] + [os.path.join(CSRC, 'lgr_common.cuh'), os.path.join(CSRC, 'lgr_prof.cuh'),
                                                        os.path.join(HERE, 'cuda_runtime.h'), os.path.join(HERE, 'emu_api.cpp'), os.path.join(HERE, 'emu_blend_helpers.h'),
@@ -116,7 +118,7 @@ def build(force=False, asan=None):
             fh.write(translate(open(os.path.join(CSRC, f)).read()))
         objs.append(cpp)
     # a 3-CTA grid for the tree walk: every emulated CTA costs 256 fibers, and 3 CTAs make the grid-stride loops iterate
-    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-w', '-DLGR_TREE_GRID=3'] + \
+    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-w', '-DLGR_TREE_GRID=3'] + extra + \
           (['-fsanitize=thread', '-DEMU_TSAN'] + (['-DEMU_TSAN_UNORDERED_CTAS'] if tsan == 2 else []) if tsan else ['-fsanitize=address', '-fno-omit-frame-pointer'] if asan else []) + ['-I', HERE, '-I', CSRC, '-o', LIB + '.tmp'] + objs + \
           [os.path.join(HERE, 'emu_api.cpp')]
     env = dict(os.environ)
