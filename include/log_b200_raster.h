@@ -69,7 +69,8 @@ typedef struct lgr_view {
   int32_t* band_count_d; /* (num_owners) int32 */
   int32_t* band_rows_d;  /* (N) int32: dense packed-row -> id map, written by lgr_forward_render */
   float* band_dsplat_d;  /* (N,12) or NULL: the backward's dsplat_d; lgr_forward_render zeroes the rows of listed
-                            Gaussians so that the caller need not zero-fill all N rows */
+                            Gaussians so that the caller need not zero-fill all N rows.  Also honoured with num_owners = 0:
+                            the rows of all Gaussians with radius > 0 are zeroed (the only rows lgr_backward reads) */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */

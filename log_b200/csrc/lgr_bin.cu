@@ -86,6 +86,10 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
   }
   const int rad = radii[i];
   if (rad <= 0) return;
+  if (v.num_owners == 0 && v.band_dsplat) {      // optional: zero the backward's accumulator row of every visible Gaussian here,
+    float4* z = reinterpret_cast<float4*>(v.band_dsplat + i * LGR_GRAD_FLOATS);      // instead of a separate full-size memset
+    z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const float4 r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);
   const float4 r1 = ldg4(splat + i * LGR_SPLAT_FLOATS + 4);
   if (!(r1.z > 0.f)) return;     // hx == 0: opacity below 1/255, contributes nowhere

@@ -24,6 +24,7 @@ import torch.nn as nn
 from . import _capi
 from ._capi import LGR_FILTER_ADD, LGR_FILTER_MAX, LGR_FILTER_NONE, LgrView
 
+PREZERO_DSPLAT = bool(int(__import__('os').environ.get('LGR_PREZERO_DSPLAT', '0')))      # see rasterize_forward
 FLAVOUR_STOCK = 'stock'   # diff_gaussian_rasterization            (graphdeco-inria)   -> 2-tuple, cov += 0.3
 FLAVOUR_FORK = 'fork'     # diff_gaussian_rasterization_wodilate   (chingswy antialias) -> 5-tuple, cov = max(cov, 0.3)
 
@@ -118,6 +119,10 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     keep = []
     K = 0 if shs is None else int(shs.shape[1])
     band_ids = band_count = band_blk = band_rows = band_dsplat = None
+    if num_owners == 0 and PREZERO_DSPLAT and torch.is_grad_enabled():
+        # experiment (LGR_PREZERO_DSPLAT=1): the scatter kernel zeroes the accumulator rows the backward will read, instead of a
+        # 48 N-byte memset at the start of the backward
+        band_dsplat = torch.empty((max(n, 1), _capi.LGR_GRAD_FLOATS), dtype=torch.float32, device=dev)
     if num_owners > 0:
         band_rows = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
         band_dsplat = torch.empty((max(n, 1), _capi.LGR_GRAD_FLOATS), dtype=torch.float32, device=dev)
@@ -186,8 +191,8 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
     n = state.n
     f32 = dict(dtype=torch.float32, device=dev)
     g = _f32c(grad_image, 'grad_image', dev)
-    if state.num_owners > 0 and state.band_ids[3] is not None:
-        dsplat = state.band_ids[3]          # rows of listed Gaussians were zeroed by the forward's scatter kernel
+    if state.band_ids[3] is not None:
+        dsplat = state.band_ids[3]          # rows the backward reads were zeroed by the forward's scatter kernel
         state.band_ids = state.band_ids[:3] + (None,)      # one backward per forward
     else:
         dsplat = torch.zeros((n, _capi.LGR_GRAD_FLOATS), **f32)
