@@ -218,6 +218,20 @@ class SplatExchange:
         self.dsplat_rows = torch.empty((rows, _capi.LGR_GRAD_FLOATS), dtype=torch.float32, device=dev)
         self.count.zero_()
         self.recv_radii.zero_()
+        self._cache = {}
+
+    def _scratch(self, name: str, shape, dtype):
+        """Grow-only scratch tensors that live as long as the exchange (one step is in flight at a time, like the exchange
+        buffers themselves): at ~1 ms per step the ~20 allocator calls of a step are a visible share of the host time that
+        sits between the forward's one synchronisation and the next kernel launch."""
+        need = 1
+        for d in shape:
+            need *= int(d)
+        t = self._cache.get(name)
+        if t is None or t.numel() < need or t.dtype != dtype:
+            t = torch.empty((max(need, 1) * 5 // 4 + 64,), dtype=dtype, device=self.buf.device)
+            self._cache[name] = t
+        return t[:need].view(*shape)
 
     @classmethod
     def over_symmetric_memory(cls, num_gaussians: int, image_height: int, group=None):
@@ -259,17 +273,17 @@ class SplatExchange:
             raise ValueError('image height differs from the one the bands were cut for')
         gx, gy = (W + 15) // 16, (H + 15) // 16
         i32 = dict(dtype=torch.int32, device=dev)
-        s.splat = torch.empty((n, _capi.LGR_SPLAT_FLOATS), dtype=torch.float32, device=dev)
-        s.radii = torch.empty((n,), **i32)
-        s.clamped = torch.empty((n,), dtype=torch.uint8, device=dev) if sh is not None else None
-        s.tile_start_full = torch.empty((gx * gy + 1,), **i32)
-        cursor = torch.empty((_capi.LGR_TILE_SCRATCH_INTS * gx * gy,), **i32)
-        meta = torch.empty((_capi.LGR_META_INTS,), **i32)
+        s.splat = self._scratch('splat', (n, _capi.LGR_SPLAT_FLOATS), torch.float32)
+        s.radii = torch.empty((n,), **i32)                                   # returned to the caller: never recycled
+        s.clamped = self._scratch('clamped', (n,), torch.uint8) if sh is not None else None
+        s.tile_start_full = self._scratch('tile_start_full', (gx * gy + 1,), torch.int32)
+        cursor = self._scratch('cursor_full', (_capi.LGR_TILE_SCRATCH_INTS * gx * gy,), torch.int32)
+        meta = self._scratch('meta_full', (_capi.LGR_META_INTS,), torch.int32)
         st = _stream()
         _capi.check(lib.lgr_forward_project(ctypes.byref(s.view_full), n, _ptr(m), _ptr(o), _ptr(sc), _ptr(r), _ptr(c), _ptr(sh),
                                             _ptr(s.splat), _ptr(s.radii), _ptr(s.clamped), _ptr(s.tile_start_full), _ptr(cursor),
                                             _ptr(meta), st), 'lgr_forward_project')
-        s.send_scratch = torch.empty((_capi.shard_send_ints(n, self.world),), **i32)
+        s.send_scratch = self._scratch('send', (_capi.shard_send_ints(n, self.world),), torch.int32)
         _capi.check(lib.lgr_shard_send(ctypes.byref(s.view_full), ctypes.byref(self.layout), n, self.lo, _ptr(s.splat),
                                        _ptr(s.radii), _ptr(s.send_scratch), ctypes.c_void_p(self.peer_ptrs.data_ptr()), st),
                     'lgr_shard_send')
@@ -289,9 +303,9 @@ class SplatExchange:
         ntiles = gx * (self.band[1] - self.band[0])
         rows = self.world * self.cap
         i32, f32 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.float32, device=dev)
-        s.tile_start = torch.empty((ntiles + 1,), **i32)
-        cursor = torch.empty((_capi.LGR_TILE_SCRATCH_INTS * max(ntiles, 1),), **i32)
-        meta = torch.empty((_capi.LGR_META_INTS,), **i32)
+        s.tile_start = self._scratch('tile_start', (ntiles + 1,), torch.int32)
+        cursor = self._scratch('cursor', (_capi.LGR_TILE_SCRATCH_INTS * max(ntiles, 1),), torch.int32)
+        meta = self._scratch('meta', (_capi.LGR_META_INTS,), torch.int32)
         st = _stream()
         _capi.check(lib.lgr_shard_recv_bin(ctypes.byref(v), ctypes.byref(self.layout), _ptr(self.buf), _ptr(self.dsplat_rows),
                                            _ptr(s.tile_start), _ptr(cursor), _ptr(meta), st), 'lgr_shard_recv_bin')
@@ -299,19 +313,19 @@ class SplatExchange:
         D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
         s.num_instances, s.max_tile_len, s.num_rows = D, max_len, int(sum(m[_capi.LGR_META_INTS:]))
         s.stock_instances = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
-        inst_key = torch.empty((D,), **i32)
-        inst_val = torch.empty((D,), **i32)
-        inst_tmp = torch.empty((2 * D,), **i32) if max_len > lib.lgr_sort_smem_capacity() else None
-        s.sorted_ids = torch.empty((D,), **i32)
-        s.image = torch.zeros((3, H, W), **f32)
-        final_T = torch.ones((H, W), **f32)
-        n_contrib = torch.zeros((H, W), **i32)
+        inst_key = self._scratch('inst_key', (D,), torch.int32)
+        inst_val = self._scratch('inst_val', (D,), torch.int32)
+        inst_tmp = self._scratch('inst_tmp', (2 * D,), torch.int32) if max_len > lib.lgr_sort_smem_capacity() else None
+        s.sorted_ids = self._scratch('sorted_ids', (D,), torch.int32)
+        s.image = torch.zeros((3, H, W), **f32)                              # outputs: fresh every step
+        final_T = self._scratch('final_T', (H, W), torch.float32)            # written for the band's pixels, read by nobody
+        n_contrib = self._scratch('n_contrib', (H, W), torch.int32)
         pid = pwp = s.pw_rows = s.pc_rows = None
         if s.want_aux:
             pid = torch.full((H, W), -1, **i32)
             pwp = torch.zeros((H, W), **f32)
-            s.pw_rows = torch.zeros((rows,), **f32)
-            s.pc_rows = torch.zeros((rows,), **i32)
+            s.pw_rows = self._scratch('pw_rows', (rows,), torch.float32).zero_()
+            s.pc_rows = self._scratch('pc_rows', (rows,), torch.int32).zero_()
         _capi.check(lib.lgr_forward_render(ctypes.byref(v), rows, D, max_len, num_long, _ptr(self.recv_splat), _ptr(self.recv_radii),
                                            _ptr(s.tile_start), _ptr(cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
                                            _ptr(s.sorted_ids), _ptr(s.image), _ptr(final_T), _ptr(n_contrib), _ptr(pid), _ptr(pwp),
@@ -351,7 +365,7 @@ class SplatExchange:
         n = s.n
         m, o, sc, r, c, sh = s.inputs
         f32 = dict(dtype=torch.float32, device=dev)
-        dsplat = torch.empty((n, _capi.LGR_GRAD_FLOATS), **f32)
+        dsplat = self._scratch('dsplat_local', (n, _capi.LGR_GRAD_FLOATS), torch.float32)
         pw = torch.empty((n,), **f32) if s.want_aux else None
         pc = torch.empty((n,), dtype=torch.int32, device=dev) if s.want_aux else None
         st = _stream()
