@@ -330,8 +330,9 @@ class SplatExchange:
                                            _ptr(s.tile_start), _ptr(cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
                                            _ptr(s.sorted_ids), _ptr(s.image), _ptr(final_T), _ptr(n_contrib), _ptr(pid), _ptr(pwp),
                                            _ptr(s.pw_rows), _ptr(s.pc_rows), st), 'lgr_forward_render')
-        if pid is not None:                                          # rows -> global Gaussian indices
-            pid = torch.where(pid >= 0, self.recv_gid[pid.clamp_min(0).long()], pid)
+        if pid is not None and self.band[1] > self.band[0]:         # rows -> global Gaussian indices (band rows only)
+            sub = pid[self.band[0] * 16:min(self.band[1] * 16, H)]
+            sub.copy_(torch.where(sub >= 0, self.recv_gid[sub.clamp_min(0).long()], sub))
         return s.image, s.radii, pid, pwp
 
     def blend_backward_and_return(self, s: ShardStep, grad_image):
