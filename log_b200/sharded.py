@@ -212,6 +212,9 @@ class SplatExchange:
         self.peer_ptrs = torch.tensor(peer_ptrs, dtype=torch.int64, device=dev)
         L, rows = self.layout, self.world * self.cap
         self.count = self.buf[L.off_count:L.off_count + self.world].view(torch.int32)
+        # header words [32, 40) of the own buffer double as the owner side's `meta`, so that one D2H copy brings the counts and D
+        self.header = self.buf[L.off_count:L.off_count + 40].view(torch.int32)
+        self.meta = self.header[32:40]
         self.recv_splat = self.buf[L.off_splat:L.off_splat + rows * 12].view(rows, 12)
         self.recv_radii = self.buf[L.off_radii:L.off_radii + rows].view(torch.int32)
         self.recv_gid = self.buf[L.off_gid:L.off_gid + rows].view(torch.int32)
@@ -305,13 +308,14 @@ class SplatExchange:
         i32, f32 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.float32, device=dev)
         s.tile_start = self._scratch('tile_start', (ntiles + 1,), torch.int32)
         cursor = self._scratch('cursor', (_capi.LGR_TILE_SCRATCH_INTS * max(ntiles, 1),), torch.int32)
-        meta = self._scratch('meta', (_capi.LGR_META_INTS,), torch.int32)
+        meta = self.meta
         st = _stream()
         _capi.check(lib.lgr_shard_recv_bin(ctypes.byref(v), ctypes.byref(self.layout), _ptr(self.buf), _ptr(self.dsplat_rows),
                                            _ptr(s.tile_start), _ptr(cursor), _ptr(meta), st), 'lgr_shard_recv_bin')
-        m = torch.cat([meta, self.count]).tolist()                 # the one host sync of the forward
+        h = self.header.tolist()                                     # the one host sync of the forward (160 bytes)
+        m = h[32:40]
         D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
-        s.num_instances, s.max_tile_len, s.num_rows = D, max_len, int(sum(m[_capi.LGR_META_INTS:]))
+        s.num_instances, s.max_tile_len, s.num_rows = D, max_len, int(sum(h[:self.world]))
         s.stock_instances = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
         inst_key = self._scratch('inst_key', (D,), torch.int32)
         inst_val = self._scratch('inst_val', (D,), torch.int32)
