@@ -222,6 +222,7 @@ class SplatExchange:
         self.count.zero_()
         self.recv_radii.zero_()
         self._cache = {}
+        self._in_flight = False      # a forward() whose backward() has not run yet (see forward())
 
     def _scratch(self, name: str, shape, dtype):
         """Grow-only scratch tensors that live as long as the exchange (one step is in flight at a time, like the exchange
@@ -391,14 +392,21 @@ class SplatExchange:
 
     # ---- the calls a training loop makes -----------------------------------------------------------------------
     def forward(self, settings, means3D, opacities, scales, rotations, colors_precomp=None, shs=None, **kw):
-        self.barrier()          # every rank is done with the previous step's buffers
+        # Entry barrier: nobody may overwrite exchange buffers a peer is still reading.  After a completed backward() its
+        # barrier already guarantees that (every owner's last read of the received rows precedes it, and a rank's own
+        # gather precedes, in stream order, its arrival at the next step's post-send barrier), so a training loop pays two
+        # barriers per step; two forwards in a row (evaluation) need the third.
+        if self._in_flight:
+            self.barrier()
+        self._in_flight = True
         s = self.project_and_send(settings, means3D, opacities, scales, rotations, colors_precomp, shs, **kw)
         self.barrier()          # all records have landed
         return self.receive_and_render(s) + (s,)
 
     def backward(self, s: ShardStep, grad_image):
         self.blend_backward_and_return(s, grad_image)
-        self.barrier()          # all returned rows have landed
+        self.barrier()          # all returned rows have landed; all owners are done with this step's received rows
+        self._in_flight = False
         return self.gather_and_project_backward(s)
 
 

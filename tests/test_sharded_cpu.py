@@ -172,6 +172,15 @@ def _shard_worker(rank, world, port, tag, n, W, H, steps, out):
                      ('dscales', t['scales'].grad), ('drotations', t['rotations'].grad), ('dcolors', t['colors'].grad)):
             want = full[k][xch.lo:xch.hi]
             ok &= bool(torch.isfinite(g).all()) and (rel(g, want) < 2e-5 or float(want.abs().max()) == 0.0)
+    # evaluation: two forwards in a row without a backward (the entry barrier of forward() is needed here)
+    for step in range(2):
+        sc = O.make_scene(n, W, H, 3.0, seed=90 + step)
+        full = run_gpu(cam, sc, None)
+        t = {k: v[xch.lo:xch.hi].to(torch.float32) for k, v in sc.items()}
+        image, radii, pid, pwp, _ = xch.forward(settings_from_camera(cam, torch.device('cpu')), t['means3D'], t['opacities'].reshape(-1),
+                                                t['scales'], t['rotations'], colors_precomp=t['colors'])
+        a, b = xch.band[0] * 16, min(xch.band[1] * 16, H)
+        ok &= torch.equal(image[:, a:b], full['image'][:, a:b]) and torch.equal(pid[a:b], full['point_id_pixel'][a:b])
     out.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
