@@ -245,10 +245,8 @@ def main():
                                                      loc['colors'] if deg == 0 else None, loc['shs'] if deg > 0 else None,
                                                      filter_mode=LGR_FILTER_MAX, want_aux=True)
             ev[1].record()
-            shard.blend_backward_and_return(st, dG)
+            g = shard.backward(st, dG)          # sweep + return, barrier, gather + per-Gaussian backward
             ev[2].record()
-            shard.barrier()
-            g = shard.gather_and_project_backward(st)
             ev[3].record()
             phase_ev.append(ev)
             stats['rows'] = st.num_rows
