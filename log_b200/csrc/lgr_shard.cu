@@ -69,7 +69,7 @@ __device__ __forceinline__ void count_owner_hits(bool valid, int o0, int o1, int
 __global__ void __launch_bounds__(SHARD_THREADS)
 shard_count_kernel(View v, int R, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
                    int32_t* __restrict__ send_blk, int B) {
-  __shared__ int sW[SHARD_MAX_RANKS][SHARD_WARPS];
+  __shared__ __align__(16) int sW[SHARD_MAX_RANKS][SHARD_WARPS];      // 16-byte aligned: a vectorised load of a row never covers a neighbour
   const int64_t i = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x;
   int o0, o1;
   const bool valid = owner_range(v, R, splat, radii, i, n, o0, o1);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(SHARD_THREADS)
 shard_push_kernel(View v, ShardLayout L, int64_t n, int64_t gid_base, const float* __restrict__ splat,
                   const int32_t* __restrict__ radii, const int32_t* __restrict__ send_blk, int B,
                   void* const* __restrict__ peer_base) {
-  __shared__ int sW[SHARD_MAX_RANKS][SHARD_WARPS];
+  __shared__ __align__(16) int sW[SHARD_MAX_RANKS][SHARD_WARPS];      // 16-byte aligned: a vectorised load of a row never covers a neighbour
   __shared__ float4 sRows[SHARD_THREADS * 3];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x;
@@ -174,8 +174,8 @@ shard_push_kernel(View v, ShardLayout L, int64_t n, int64_t gid_base, const floa
 __global__ void __launch_bounds__(SHARD_THREADS)
 shard_recv_count_kernel(View v, ShardLayout L, float* __restrict__ xbuf, float* __restrict__ dsplat,
                         int32_t* __restrict__ tile_count, int32_t* __restrict__ meta) {
-  __shared__ unsigned sStock[SHARD_WARPS];
-  __shared__ int sVis[SHARD_WARPS];
+  __shared__ __align__(16) unsigned sStock[SHARD_WARPS];
+  __shared__ __align__(16) int sVis[SHARD_WARPS];
   const int64_t slot = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x;
   const int64_t total = (int64_t)L.R * L.cap;
   const int32_t* count = reinterpret_cast<const int32_t*>(xbuf + L.off_count);
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(SHARD_THREADS)
 shard_gather_kernel(View v, ShardLayout L, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
                     const int32_t* __restrict__ send_blk, int B, const float* __restrict__ xbuf,
                     float* __restrict__ dsplat_out, float* __restrict__ weight_out, int32_t* __restrict__ pcount_out) {
-  __shared__ int sW[SHARD_MAX_RANKS][SHARD_WARPS];
+  __shared__ __align__(16) int sW[SHARD_MAX_RANKS][SHARD_WARPS];      // 16-byte aligned: a vectorised load of a row never covers a neighbour
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x;
   int o0, o1;

@@ -81,7 +81,7 @@ tree_classify_kernel(TreeArgs a, const int64_t* __restrict__ roots, const int32_
 // exclusive scan of the (kept, descending) chunk counts in place; totals into state[2], state[3]
 __global__ void __launch_bounds__(1024)
 tree_scan_kernel(int C_or_one, int32_t* __restrict__ state, int32_t* __restrict__ chunk_cnt) {
-  __shared__ int wsum[2][32];
+  __shared__ __align__(16) int wsum[2][32];
   __shared__ int carry[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t nslots = (int64_t)state[ST_FRONT] * C_or_one;
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(TREE_THREADS)
 tree_scatter_kernel(int C_or_one, const int32_t* __restrict__ state, const int32_t* __restrict__ cand,
                     const uint8_t* __restrict__ flags, const int32_t* __restrict__ chunk_pre, int64_t* __restrict__ out,
                     int32_t* __restrict__ next_front) {
-  __shared__ int wk[TREE_THREADS / 32], wn[TREE_THREADS / 32];
+  __shared__ __align__(16) int wk[TREE_THREADS / 32];
+  __shared__ __align__(16) int wn[TREE_THREADS / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t nslots = (int64_t)state[ST_FRONT] * C_or_one;
   const int64_t nchunks = (nslots + TREE_THREADS - 1) / TREE_THREADS;
