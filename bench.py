@@ -10,6 +10,11 @@ through the public GaussianRasterizer autograd API with HOST (pinned) inputs cop
 step.  N > 1: tile rows are sharded over ranks (strong scaling of ONE view), per-Gaussian gradients are reduced to
 owner ranks with NCCL; time = max over ranks.
 
+N > 1 default: shard mode (log_b200/sharded.py:SplatExchange: Gaussians AND tile-row bands sharded, splat records pushed to
+the band owners over NVLink peer memory, 2D gradients returned, no reduction); `LGR_MULTI=band` selects the round-1
+layout (Gaussians replicated, gradient rows reduced to owner ranks).  Every N > 1 line carries `parity`: outside the timed
+region each rank repeats the step on ONE GPU and compares its band of the image and its own Gaussians' gradients.
+
 `--impl reference` times the CPU implementation of the same path (the oracle port: the reference's rasteriser is an
 un-vendored CUDA package that cannot be built or run on a CPU) on the box's host cores.
 """
@@ -141,6 +146,8 @@ def run_reference(args, rank, world):
     cam, sc, G = make_inputs(args.workload)
     sub = {k: v[:ns].numpy() for k, v in sc.items()}
     kw = dict(colors_precomp=sub['colors']) if deg == 0 else dict(shs=sub['shs'])
+    # torchrun exports OMP_NUM_THREADS=1 to its children: size the OpenMP team explicitly from the box's cores
+    c_oracle.set_num_threads(os.cpu_count() or 1)
     cores = c_oracle.num_threads()
 
     def step():
@@ -224,7 +231,7 @@ def main():
     # LGR_MULTI=shard: Gaussian-sharded ranks exchanging splat records / 2D gradients (log_b200/sharded.py:SplatExchange)
     # instead of replicated Gaussians + gradient rows.  Opt-in until its first hardware run has been checked in.
     shard = None
-    if world > 1 and os.environ.get('LGR_MULTI', 'band') == 'shard':
+    if world > 1 and os.environ.get('LGR_MULTI', 'shard') == 'shard':
         shard = sharded.SplatExchange.over_symmetric_memory(n, H)
         lo_, hi_ = shard.lo, shard.hi
         loc = {k: v[lo_:hi_].contiguous() for k, v in d.items()}
@@ -310,78 +317,134 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
 
+    # ---- parity of the multi-GPU result (outside the timed region): the same step on ONE GPU, compared on every rank ----
+    parity = None
+    if world > 1:
+        def relerr(got, want):
+            d = (got.double() - want.double()).norm()
+            return float(d / want.double().norm().clamp_min(1e-30))
+        img1, rad1, pid1, pwp1, pw1, st1 = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs, LGR_FILTER_MAX, True, None)
+        g1 = rasterize_backward(st1, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
+        names = ('dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations', 'dcolors')
+        errs = {}
+        if shard is not None:
+            imgN, radN, pidN, pwpN, stN = shard.forward(settings, loc['means3D'], loc_op, loc['scales'], loc['rotations'],
+                                                        loc['colors'] if deg == 0 else None, loc['shs'] if deg > 0 else None,
+                                                        filter_mode=LGR_FILTER_MAX, want_aux=True)
+            gN, pwN, pcN = shard.backward(stN, dG)
+            y0, y1 = shard.band[0] * 16, min(shard.band[1] * 16, H)
+            errs['image'] = relerr(imgN[:, y0:y1], img1[:, y0:y1]) if y1 > y0 else 0.0
+            errs['point_id_pixel_mismatch'] = float((pidN[y0:y1] != pid1[y0:y1]).float().mean()) if y1 > y0 else 0.0
+            for k, name in enumerate(names):
+                errs[name] = relerr(gN[k].reshape(hi_ - lo_, -1), g1[k][lo_:hi_].reshape(hi_ - lo_, -1)) if hi_ > lo_ else 0.0
+            errs['radii_mismatch'] = float((radN != rad1[lo_:hi_]).float().mean()) if hi_ > lo_ else 0.0
+            errs['point_weight'] = relerr(pwN, pw1[lo_:hi_]) if hi_ > lo_ else 0.0
+        else:
+            imgN, radN, pidN, pwpN, pwN, stN = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
+                                                                 LGR_FILTER_MAX, True, tile_rows, num_owners=world)
+            if peer is not None:
+                gsh = peer.backward(stN, dG, d['means3D'], opac, d['scales'], d['rotations'], col)
+            else:
+                gsh = sharded.exchange_rows_to_owners(rasterize_backward(stN, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs),
+                                                      stN.band_counts_host, n)
+            lo_b, hi_b = sharded.owner_partition(n, world)[rank]
+            y0, y1 = tile_rows[0] * 16, min(tile_rows[1] * 16, H)
+            errs['image'] = relerr(imgN[:, y0:y1], img1[:, y0:y1]) if y1 > y0 else 0.0
+            want = sharded.pack_grads((g1[0], g1[1], g1[2], g1[3], g1[4], g1[5]))[lo_b:hi_b]
+            for k, name in enumerate(names):
+                sl = sharded.unpack_grads(gsh[:hi_b - lo_b, :17])[k], sharded.unpack_grads(want)[k]
+                errs[name] = relerr(sl[0].reshape(hi_b - lo_b, -1), sl[1].reshape(hi_b - lo_b, -1)) if hi_b > lo_b else 0.0
+        keys = sorted(errs)
+        te = torch.tensor([errs[k] for k in keys], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        parity = {k: float(v) for k, v in zip(keys, te.tolist())}
+        parity['bound'] = 2e-5
+        parity['what'] = ('max over ranks of the norm-wise relative error between the N-rank result (each rank: its band of the image, '
+                          'the gradients of the Gaussians it owns) and the same step on one GPU')
+        parity['ok'] = all(v <= 2e-5 for k, v in parity.items() if k not in ('bound', 'what', 'point_id_pixel_mismatch', 'radii_mismatch')) and \
+            parity.get('radii_mismatch', 0.0) == 0.0 and parity.get('point_id_pixel_mismatch', 0.0) <= 1e-5
+        del img1, rad1, pid1, pwp1, pw1, st1, g1, imgN, stN
+        torch.cuda.empty_cache()
+
     # ---- end to end through the public API: pinned host inputs in, loss out, every step ----
+    # Two preallocated device input sets; every step copies ALL of its inputs from pinned host memory into one of them
+    # (copy stream, no allocation and no record_stream inside the timed loop) and reads its loss back.  N = 1: the
+    # reference-facing GaussianRasterizer + autograd.  N > 1 (shard mode): SplatExchange.rasterize + autograd, and a rank
+    # copies only the Gaussians it owns.
     e2e = None
     if not args.no_e2e:
-        rast = GaussianRasterizer(settings)
-        rast.tile_rows = tile_rows
-        h2d_bytes = sum(v.numel() * 4 for k, v in host.items() if not (k == 'colors' and deg > 0)) + host_G.numel() * 4
-
+        use_sh = deg > 0
+        if shard is not None:
+            host = {k: v[shard.lo:shard.hi].contiguous().pin_memory() for k, v in sc.items()}
+        in_keys = [k for k in host if not (k == 'colors' and use_sh)]
+        h2d_bytes = sum(host[k].numel() * 4 for k in in_keys) + host_G.numel() * 4
+        sets = []
+        for _ in range(2):
+            t_ = {k: torch.empty_like(host[k], device=dev).requires_grad_(True) for k in in_keys}
+            sets.append((t_, torch.empty_like(host_G, device=dev), torch.zeros(host['means3D'].shape[0], 3, device=dev, requires_grad=True)))
         copy_stream = torch.cuda.Stream(device=dev)
+        rast = GaussianRasterizer(settings)
 
-        if shard is not None:      # a rank only ever needs its own Gaussians
-            host = {k: v[shard.lo:shard.hi] for k, v in host.items()}
-            h2d_bytes = sum(v.numel() * 4 for k, v in host.items() if not (k == 'colors' and deg > 0)) + host_G.numel() * 4
-
-        def h2d():
-            """Issue this step's host->device copies on the copy stream; returns (tensors, cotangent, event)."""
-            with torch.cuda.stream(copy_stream):
-                t_ = {k: v.to(dev, non_blocking=True) for k, v in host.items() if not (k == 'colors' and deg > 0)}
-                Gd = host_G.to(dev, non_blocking=True)
+        def h2d(which):
+            """Issue one step's host->device copies into input set `which` on the copy stream; returns the event that follows them."""
+            t_, Gd, _ = sets[which]
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                for k in in_keys:
+                    t_[k].copy_(host[k], non_blocking=True)
+                Gd.copy_(host_G, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return t_, Gd, ev
+            return ev
 
-        def compute(t_, Gd, ev):
+        def compute(which, ev):
+            t_, Gd, m2d = sets[which]
             torch.cuda.current_stream().wait_event(ev)
-            for v_ in list(t_.values()) + [Gd]:
-                v_.record_stream(torch.cuda.current_stream())
+            for v_ in list(t_.values()) + [m2d]:
+                v_.grad = None
             if shard is not None:
-                img, radii, pid, pwp, st = shard.forward(settings, t_['means3D'], t_['opacities'].reshape(-1), t_['scales'],
-                                                         t_['rotations'], t_['colors'] if deg == 0 else None,
-                                                         t_.get('shs') if deg > 0 else None, filter_mode=LGR_FILTER_MAX, want_aux=True)
-                loss = (img * Gd).sum()
-                shard.backward(st, Gd)
-                return loss
-            if world > 1:
-                o_ = t_['opacities'].reshape(-1)
-                img, radii, pid, pwp, pw, st = rasterize_forward(settings, t_['means3D'], o_, t_['scales'], t_['rotations'],
-                                                                 t_['colors'], None, LGR_FILTER_MAX, True, tile_rows, num_owners=world)
+                out = shard.rasterize(settings, t_['means3D'], m2d, t_['opacities'], t_['scales'], t_['rotations'],
+                                      t_['colors'] if not use_sh else None, t_.get('shs') if use_sh else None,
+                                      filter_mode=LGR_FILTER_MAX, want_aux=True)
+            elif world > 1:      # band mode has no autograd front end: the C-ABI wrappers directly (round-1 path)
+                o_ = t_['opacities'].detach().reshape(-1)
+                dt = {k: v.detach() for k, v in t_.items()}
+                img, radii, pid, pwp, pw, st = rasterize_forward(settings, dt['means3D'], o_, dt['scales'], dt['rotations'],
+                                                                 dt['colors'], None, LGR_FILTER_MAX, True, tile_rows, num_owners=world)
                 loss = (img * Gd).sum()
                 if peer is not None:
-                    peer.backward(st, Gd, t_['means3D'], o_, t_['scales'], t_['rotations'], t_['colors'])
+                    peer.backward(st, Gd, dt['means3D'], o_, dt['scales'], dt['rotations'], dt['colors'])
                 else:
-                    rows = rasterize_backward(st, Gd, t_['means3D'], o_, t_['scales'], t_['rotations'], t_['colors'], None)
+                    rows = rasterize_backward(st, Gd, dt['means3D'], o_, dt['scales'], dt['rotations'], dt['colors'], None)
                     sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
                 return loss
-            for v_ in t_.values():
-                v_.requires_grad_(True)
-            m2d = torch.zeros(n, 3, device=dev, requires_grad=True)
-            out = rast(means3D=t_['means3D'], means2D=m2d, shs=t_.get('shs') if deg > 0 else None,
-                       colors_precomp=t_['colors'] if deg == 0 else None, opacities=t_['opacities'], scales=t_['scales'],
-                       rotations=t_['rotations'], cov3D_precomp=None)
+            else:
+                out = rast(means3D=t_['means3D'], means2D=m2d, shs=t_.get('shs') if use_sh else None,
+                           colors_precomp=t_['colors'] if not use_sh else None, opacities=t_['opacities'], scales=t_['scales'],
+                           rotations=t_['rotations'], cov3D_precomp=None)
             loss = (out[0] * Gd).sum()
             loss.backward()
             return loss
 
         def run_e2e(steps, prefetch):
-            """Every step copies all of its inputs from pinned host memory and reads its loss back.  prefetch=True issues
-            the copies of step k+1 on a copy stream before step k's loss is read (double buffering)."""
-            nxt, val = h2d(), 0.0
+            """prefetch=True: the copies of step k+1 (other input set) are issued before step k's loss is read (double buffering);
+            False: copy, compute, read back, strictly in turn."""
+            ev, val = h2d(0), 0.0
             for k in range(steps):
-                cur = nxt
+                cur = k & 1
+                nxt = None
                 if prefetch and k + 1 < steps:
-                    nxt = h2d()
-                loss = compute(*cur)
-                val = float(loss.item())           # D2H read of the step's result
+                    nxt = h2d(cur ^ 1)          # set cur^1 was last used by step k-1, whose loss has been read: free
+                loss = compute(cur, ev)
+                val = float(loss.item())        # D2H read of the step's result
                 if not prefetch and k + 1 < steps:
-                    nxt = h2d()
+                    nxt = h2d(cur ^ 1)
+                ev = nxt
             return val
 
         ne = max(3, min(args.steps, 10))
         res = {}
         for mode in (False, True):
-            run_e2e(6, mode)                        # allocator growth settles after ~5 iterations
+            run_e2e(4, mode)                        # warm-up (the caching allocator reaches its steady state)
             barrier()
             t0 = time.perf_counter()
             run_e2e(ne, mode)
@@ -392,7 +455,11 @@ def main():
             res[mode] = float(te.item())
         e2e = {'value': n / res[True], 'unit': 'Gaussians/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                'ms_per_step': res[True] * 1e3, 'steps': ne,
-               'h2d': 'all inputs copied every step from pinned host memory on a copy stream, double-buffered against the previous step',
+               'api': ('SplatExchange.rasterize + autograd (each rank copies the Gaussians it owns)' if shard is not None else
+                       'rasterize_forward / rasterize_backward (band mode has no autograd front end)' if world > 1 else
+                       'GaussianRasterizer(...) + loss.backward()'),
+               'h2d': 'every step copies all of its inputs from pinned host memory into one of two preallocated device sets on a copy '
+                      'stream (double-buffered against the previous step) and reads the loss back; max over ranks, wall clock',
                'ms_per_step_serial_copy': res[False] * 1e3}
 
     if rank != 0:
@@ -402,7 +469,8 @@ def main():
 
     peak, peak_src = peaks()
     D_stock, D_bin = stats['D_stock'], stats['D']
-    kb, b_min, b_model = algorithmic_bytes(n, H, W, D_stock, deg)
+    kb, b_min, b_model = algorithmic_bytes(n, H, W, D_bin, deg)             # what the launches actually process
+    kb_stock, _, b_model_stock = algorithmic_bytes(n, H, W, D_stock, deg)   # SURVEY 8(d)'s stock radius-square rule, beside it
     kms = {'project_fwd': prof['project_fwd'][0], 'bin_sort': prof['tile_scan'][0] + prof['bin_scatter'][0] + prof['tile_sort'][0],
            'blend_fwd': prof['blend_fwd'][0], 'blend_bwd': prof['blend_bwd'][0], 'project_bwd': prof['project_bwd'][0]}
     kms = {k: v / args.steps for k, v in kms.items()}
@@ -421,22 +489,34 @@ def main():
                    'parallelism': (f'Gaussians sharded x{world} + tile-row bands x{world}: splat records pushed to the band owners, 2D gradients returned, over NVLink peer memory (shard mode)') if shard is not None else (f'tile-row bands x{world}, gradient rows ' + ('pushed to owner ranks over NVLink peer memory (fused in the backward kernel)' if peer is not None else 'NCCL all-to-all to owner ranks')) if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
                    'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible']},
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                     'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes': kb[dom], 'kernel_ms': kms[dom]},
+                     'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes': kb[dom], 'kernel_ms': kms[dom],
+                     'instances': 'binned (instances_binned): the (Gaussian, tile) pairs the launch processes',
+                     'frac_stock_rule_instances': (kb_stock[dom] / (kms[dom] * 1e-3) / 1e9 / peak) if kms[dom] > 0 else 0.0},
         'roofline_step': {'b_model_bytes': b_model, 'b_min_bytes': b_min, 'achieved': b_model / (ms_step * 1e-3) / 1e9,
-                          'frac': b_model / (ms_step * 1e-3) / 1e9 / peak, 'b_min_frac': b_min / (ms_step * 1e-3) / 1e9 / peak},
+                          'frac': b_model / (ms_step * 1e-3) / 1e9 / peak, 'b_min_frac': b_min / (ms_step * 1e-3) / 1e9 / peak,
+                          'frac_stock_rule_instances': b_model_stock / (ms_step * 1e-3) / 1e9 / peak},
         'kernel_ms': kms, 'phase_ms_rank0': phases, 'gpu_launches': launches, 'clocks': clk, 'e2e': e2e,
     }
+    if world > 1:
+        line['parity'] = parity
+        line['kernel_ms_exchange'] = {k: prof[k][0] / args.steps for k in ('shard_send', 'shard_recv', 'shard_return', 'shard_gather') if k in prof}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle          # the checker, timed as the CPU baseline (bounded sample)
         ns = min(n, CPU_SAMPLE[args.workload])
         sub = {k: v[:ns].numpy() for k, v in sc.items()}
         kw = dict(colors_precomp=sub['colors']) if deg == 0 else dict(shs=sub['shs'])
-        t0 = time.perf_counter()
-        c_oracle.render(cam, sub['means3D'], sub['opacities'], sub['scales'], sub['rotations'], filter_mode=c_oracle.FILTER_MAX,
-                        dL_dimage=G.numpy(), dtype=np.float32, want_aux=True, **kw)
-        dt = time.perf_counter() - t0
+        c_oracle.set_num_threads(os.cpu_count() or 1)
+        times = []
+        for rep in range(4):                       # one warm-up + three timed repetitions
+            t0 = time.perf_counter()
+            c_oracle.render(cam, sub['means3D'], sub['opacities'], sub['scales'], sub['rotations'], filter_mode=c_oracle.FILTER_MAX,
+                            dL_dimage=G.numpy(), dtype=np.float32, want_aux=True, **kw)
+            if rep:
+                times.append(time.perf_counter() - t0)
+        dt = float(np.median(times))
         line['cpu_baseline'] = {'value': ns / dt, 'unit': 'Gaussians/s', 'cores': c_oracle.num_threads(), 'kind': 'port',
-                                'sample': f'first {ns} of {n} Gaussians, {W}x{H}, fwd+bwd, fp32 C oracle, 1 repetition', 'seconds': dt}
+                                'sample': f'first {ns} of {n} Gaussians, {W}x{H}, fwd+bwd, fp32 C oracle, {c_oracle.num_threads()} OpenMP threads, '
+                                          'median of 3 repetitions after one warm-up', 'seconds': dt, 'seconds_all': times}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 13
+#define LGR_ABI_VERSION 14
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -71,6 +71,12 @@ typedef struct lgr_view {
   float* band_dsplat_d;  /* (N,12) or NULL: the backward's dsplat_d; lgr_forward_render zeroes the rows of listed
                             Gaussians so that the caller need not zero-fill all N rows.  Also honoured with num_owners = 0:
                             the rows of all Gaussians with radius > 0 are zeroed (the only rows lgr_backward reads) */
+  int32_t* tile_rank_d;  /* (rows,4) int32 or NULL.  When set, the counting pass (lgr_forward_project / lgr_shard_recv_bin)
+                            takes the tile slots of every splat that covers <= 4 tiles with RETURNING atomics and stores
+                            the 4 ranks here (row = Gaussian index); lgr_forward_render then places those instances at
+                            tile_start + rank without touching an atomic again.  Splats covering more tiles are counted
+                            in a second per-tile counter and still take their slots in lgr_forward_render.  NULL: every
+                            slot is taken in lgr_forward_render (two atomic passes over the instances). */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */
@@ -256,7 +262,7 @@ int lgr_sparse_adam(int64_t rows, int32_t row_floats, const int64_t* index_d, co
 /* Diagnostics (not on the data path): per-kernel CUDA-event timing on the launching stream.
  * lgr_profile_enable(1) starts recording; lgr_profile_collect() synchronises the recorded events, writes the summed
  * milliseconds and the launch counts per kernel id (LGR_PROFILE_KERNELS entries) and resets the counters. */
-#define LGR_PROFILE_KERNELS 8
+#define LGR_PROFILE_KERNELS 12
 int lgr_profile_enable(int on);
 int lgr_profile_collect(double* ms_out, int32_t* launches_out, int32_t capacity);
 const char* lgr_profile_kernel_name(int kernel_id);

@@ -12,7 +12,7 @@ LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
 LGR_TILE_SCRATCH_INTS = 33
-LGR_ABI_VERSION = 13
+LGR_ABI_VERSION = 14
 LGR_STAGE_HEADER_FLOATS = 64
 LGR_ROW_FLOATS = 20
 
@@ -21,7 +21,7 @@ EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'l
            'lgr_profile_kernel_name', 'lgr_shard_send', 'lgr_shard_recv_bin', 'lgr_blend_backward', 'lgr_shard_return_rows',
            'lgr_shard_gather', 'lgr_tree_traverse')
 LGR_SHARD_MAX_RANKS = 32
-LGR_PROFILE_KERNELS = 8
+LGR_PROFILE_KERNELS = 12
 
 
 class LgrView(ctypes.Structure):
@@ -29,7 +29,7 @@ class LgrView(ctypes.Structure):
     _fields_ = [('image_height', _i32), ('image_width', _i32), ('tanfovx', _f32), ('tanfovy', _f32),
                 ('scale_modifier', _f32), ('sh_degree', _i32), ('sh_coeffs', _i32), ('filter_mode', _i32),
                 ('want_aux', _i32), ('tile_row_begin', _i32), ('tile_row_end', _i32),
-                ('num_owners', _i32), ('raw_params', _i32), ('band_ids_d', _vp), ('band_blk_d', _vp), ('band_count_d', _vp), ('band_rows_d', _vp), ('band_dsplat_d', _vp),
+                ('num_owners', _i32), ('raw_params', _i32), ('band_ids_d', _vp), ('band_blk_d', _vp), ('band_count_d', _vp), ('band_rows_d', _vp), ('band_dsplat_d', _vp), ('tile_rank_d', _vp),
                 ('viewmatrix_d', _vp), ('projmatrix_d', _vp), ('campos_d', _vp), ('bg_d', _vp)]
 
 

@@ -20,9 +20,10 @@ constexpr int SORT_CAP_SMALL_FWD = 4096;   // lists up to this length are sorted
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* out: starts[0..ntiles] */,
-                 int32_t* __restrict__ cursor /* [0,CSTRIDE*ntiles): padded counts in, zeroed cursors out ;
-                                                 then ntiles ints: ids of long tiles */,
-                 int32_t* __restrict__ meta, int small_cap) {
+                 int32_t* __restrict__ cursor /* [0,CSTRIDE*ntiles): per tile [0] = small-splat count, [1] = big-splat count
+                                                 in; out: ranked ? ([0] kept = offset of the big splats, [1] = 0 their
+                                                 cursor) : ([0] = 0 the cursor) ; then ntiles ints: ids of long tiles */,
+                 int32_t* __restrict__ meta, int small_cap, int ranked) {
   __shared__ int warp_sum[SCAN_THREADS / 32];
   __shared__ int carry_s, maxl_s, nbig_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -31,7 +32,7 @@ tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* out: starts[0..
   int local_max = 0;
   for (int base = 0; base < ntiles; base += SCAN_THREADS) {
     const int i = base + tid;
-    const int c = (i < ntiles) ? cursor[i * CSTRIDE] : 0;
+    const int c = (i < ntiles) ? cursor[i * CSTRIDE] + cursor[i * CSTRIDE + 1] : 0;
     local_max = max(local_max, c);
     int x = c;
 #pragma unroll
@@ -48,7 +49,7 @@ tile_scan_kernel(int ntiles, int32_t* __restrict__ tile_start /* out: starts[0..
     const int carry = carry_s;
     const int excl = carry + (wid ? warp_sum[wid - 1] : 0) + x - c;
     if (i < ntiles) {
-      tile_start[i] = excl; cursor[i * CSTRIDE] = 0;
+      tile_start[i] = excl; cursor[i * CSTRIDE + ranked] = 0;
       if (c > small_cap) cursor[CSTRIDE * ntiles + atomicAdd(&nbig_s, 1)] = i;   // tiles the main sort launch cannot hold
     }
     __syncthreads();
@@ -99,16 +100,21 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
   const uint32_t key = __float_as_uint(depth);   // depth > 0.2 : IEEE bits are order preserving
   const int w = x1 - x0, cnt = w * (y1 - y0);
   if (cnt <= 4) {
-    // the common case (small splats): all slot requests are issued before any dependent store, so the returning
-    // atomics overlap instead of forming a serial chain of L2 round trips
     int t[4], slot[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int ty = y0 + k / max(w, 1), tx = x0 + k % max(w, 1);
       t[k] = k < cnt ? (ty - v.row0) * v.gx + tx : -1;
     }
+    if (v.tile_rank) {      // the counting pass already took the slots: a streaming kernel, no atomics
+      const int4 r = __ldg(reinterpret_cast<const int4*>(v.tile_rank + 4 * i));
+      slot[0] = r.x; slot[1] = r.y; slot[2] = r.z; slot[3] = r.w;
+    } else {
+      // all slot requests are issued before any dependent store, so the returning atomics overlap instead of forming a
+      // serial chain of L2 round trips
 #pragma unroll
-    for (int k = 0; k < 4; k++) slot[k] = t[k] >= 0 ? atomicAdd(cursor + t[k] * CSTRIDE, 1) : 0;
+      for (int k = 0; k < 4; k++) slot[k] = t[k] >= 0 ? atomicAdd(cursor + t[k] * CSTRIDE, 1) : 0;
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++)
       if (t[k] >= 0) {
@@ -118,70 +124,14 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
       }
     return;
   }
+  const int big = v.tile_rank ? 1 : 0;      // ranked: big splats sit behind the cursor[t][0] small ones, slots from cursor[t][1]
   for (int ty = y0; ty < y1; ty++)
     for (int tx = x0; tx < x1; tx++) {
       const int t = (ty - v.row0) * v.gx + tx;
-      const int pos = tile_start[t] + atomicAdd(cursor + t * CSTRIDE, 1);
+      const int pos = tile_start[t] + (big ? cursor[t * CSTRIDE] : 0) + atomicAdd(cursor + t * CSTRIDE + big, 1);
       inst_key[pos] = key;
       inst_val[pos] = (uint32_t)i;
     }
-}
-
-// Variant with warp-aggregated slot requests (compile with -DLGR_AGG_ATOMICS=1; not band mode): lanes of a warp that ask
-// for a slot in the SAME tile are found with match.any, one lane reserves all their slots with a single returning atomic
-// and the others take consecutive offsets.  With spatially random input almost no two lanes share a tile and this only
-// costs the match; with spatially coherent input (tree-ordered LoG data, `bench.py --order morton`) it turns up to 32
-// same-address atomics -- which the L2 serialises -- into one.  Every lane stays in the kernel to the end (no early
-// return) so that the collectives are convergent.
-#ifndef LGR_AGG_ATOMICS
-#define LGR_AGG_ATOMICS 0
-#endif
-__global__ void __launch_bounds__(SCATTER_THREADS)
-bin_scatter_agg_kernel(View v, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
-                       const int32_t* __restrict__ tile_start, int32_t* __restrict__ cursor, uint32_t* __restrict__ inst_key,
-                       uint32_t* __restrict__ inst_val) {
-  const int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-  uint32_t key = 0;
-  bool live = false;
-  if (i < n) {
-    const int rad = radii[i];
-    if (rad > 0) {
-      const float4 r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);
-      const float4 r1 = ldg4(splat + i * LGR_SPLAT_FLOATS + 4);
-      if (r1.z > 0.f) {
-        key = __float_as_uint(__ldg(splat + i * LGR_SPLAT_FLOATS + 11));
-        tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
-        live = true;
-      }
-    }
-  }
-  const int w = x1 - x0, cnt = live ? w * (y1 - y0) : 0;
-  const bool small = cnt <= 4;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    int t = -1 - lane;                                   // idle lanes: distinct keys, a group of one that does nothing
-    if (small && k < cnt) t = (y0 + k / max(w, 1) - v.row0) * v.gx + x0 + k % max(w, 1);
-    const unsigned peers = __match_any_sync(0xffffffffu, t);
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (t >= 0 && lane == leader) base = atomicAdd(cursor + t * CSTRIDE, __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (t >= 0) {
-      const int pos = __ldg(tile_start + t) + base + __popc(peers & ((1u << lane) - 1u));
-      inst_key[pos] = key;
-      inst_val[pos] = (uint32_t)i;
-    }
-  }
-  if (!small)                                            // big splats: one request per tile, not aggregated
-    for (int ty = y0; ty < y1; ty++)
-      for (int tx = x0; tx < x1; tx++) {
-        const int t = (ty - v.row0) * v.gx + tx;
-        const int pos = tile_start[t] + atomicAdd(cursor + t * CSTRIDE, 1);
-        inst_key[pos] = key;
-        inst_val[pos] = (uint32_t)i;
-      }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -512,9 +462,9 @@ int launch_point_compact(int64_t n, const int32_t* count, int32_t* blk, int32_t*
   return 0;
 }
 
-int launch_tile_scan(int ntiles, int32_t* tile_start, int32_t* cursor, int32_t* meta, cudaStream_t st) {
+int launch_tile_scan(int ntiles, int32_t* tile_start, int32_t* cursor, int32_t* meta, bool ranked, cudaStream_t st) {
   ProfScope ps(K_TILE_SCAN, st);
-  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(ntiles, tile_start, cursor, meta, SORT_CAP_SMALL_FWD);
+  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(ntiles, tile_start, cursor, meta, SORT_CAP_SMALL_FWD, ranked ? 1 : 0);
   LGR_CHECK_LAUNCH();
   return 0;
 }
@@ -527,21 +477,14 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
   const unsigned blocks = (unsigned)((n + SCATTER_THREADS - 1) / SCATTER_THREADS);
   {
     ProfScope ps(K_BIN_SCATTER, st);
-#if LGR_AGG_ATOMICS
-    if (v.num_owners == 0)
-      bin_scatter_agg_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val);
-    else
-#endif
     bin_scatter_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val);
   }
   LGR_CHECK_LAUNCH();
   int id_bits = 8;
   while (id_bits < 32 && (n - 1) >> id_bits) id_bits += 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {      // per device / context and cheap: set on every call (a process may drive several GPUs)
     cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SORT_CAP_LARGE);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   ProfScope ps(K_TILE_SORT, st, 1 + (num_long > 0) + (max_len > SORT_CAP_LARGE));
   const int cap_main = max(256, min(max_len, SORT_CAP_SMALL));

@@ -2,12 +2,14 @@
 //
 // One CTA of 256 threads per 16x16 tile; warp w owns the 8x4 pixel sub-tile ((w&1)*8, (w>>1)*4), one pixel per
 // lane.  The tile's depth-sorted list is staged through shared memory 256 splats at a time (coalesced id read,
-// 3 x 16-byte gather per splat, 48-byte staged record).  Each warp then tests 32 staged splats at once against its
-// sub-tile (lane = splat, conservative alpha>=1/255 box), ballots, and only walks the hits (lane = pixel, broadcast
-// LDS).  With small splats this skips ~90 % of the (pixel, splat) pairs the classic per-thread loop evaluates.
-// Backward: the same front-to-back walk (closed form of the published recurrence, see below); per hit every lane
-// publishes two scalars and 27 lanes reduce them against fixed weights held in registers (pixel-coordinate moments
-// and cotangent-weighted sums); the moments become gradients once per staged splat, then 3 vector atomics per splat.
+// 3 x 16-byte gather per splat, 48-byte staged record).  The staging thread also tests its splat's conservative
+// alpha>=1/255 box against the eight sub-tiles and publishes one byte of hit bits, so a warp finds its hits among 32
+// staged splats with one byte load and a ballot, and only walks the hits (lane = pixel, broadcast LDS).  With small
+// splats this skips ~90 % of the (pixel, splat) pairs the classic per-thread loop evaluates.
+// Backward: the same front-to-back walk (closed form of the published recurrence, see below).  Per contributing hit every
+// lane publishes two scalars; every 8 hits the warp contracts them against fixed per-pixel weights (pixel-coordinate
+// moments and cotangent-weighted sums) on the tensor cores (mma.sync m16n8k8, split TF32 = fp32 accuracy); the moments
+// become gradients once per staged splat, then 3 vector atomics per splat.
 #include "lgr_common.cuh"
 #include "lgr_prof.cuh"
 
@@ -27,7 +29,6 @@ constexpr unsigned FULL = 0xffffffffu;
 struct SubTile {
   int x, y;          // this lane's pixel
   bool inside;
-  float x0, x1, y0, y1;   // pixel-centre bounds of the warp's 8x4 sub-tile (clipped to the image)
 };
 
 __device__ __forceinline__ SubTile make_subtile(const View& v, int tile, int lane, int warp) {
@@ -36,13 +37,21 @@ __device__ __forceinline__ SubTile make_subtile(const View& v, int tile, int lan
   const int sx = tx * TILE + (warp & 1) * 8, sy = ty * TILE + (warp >> 1) * 4;
   s.x = sx + (lane & 7); s.y = sy + (lane >> 3);
   s.inside = s.x < v.W && s.y < v.H;
-  s.x0 = (float)sx; s.x1 = (float)min(sx + 7, v.W - 1);
-  s.y0 = (float)sy; s.y1 = (float)min(sy + 3, v.H - 1);
   return s;
 }
 
-__device__ __forceinline__ bool box_hits(const float4 r0, const float4 r1, const SubTile& s) {
-  return (r0.x + r1.z >= s.x0) && (r0.x - r1.z <= s.x1) && (r0.y + r1.w >= s.y0) && (r0.y - r1.w <= s.y1);
+// Which of the tile's eight 8x4 sub-tiles (bit w = warp w) can the conservative {alpha >= 1/255} box of a splat reach?
+// (tx0, ty0) = pixel coordinates of the tile's corner.  Conservative (never misses a contributing pair), so skipping on
+// it never changes a result.
+__device__ __forceinline__ unsigned subtile_bits(const float4 r0, const float4 r1, float tx0, float ty0) {
+  const float xlo = r0.x - r1.z, xhi = r0.x + r1.z, ylo = r0.y - r1.w, yhi = r0.y + r1.w;
+  unsigned xm = 0u, m = 0u;
+  if (xhi >= tx0 && xlo <= tx0 + 7.0f) xm |= 1u;
+  if (xhi >= tx0 + 8.0f && xlo <= tx0 + 15.0f) xm |= 2u;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    if (yhi >= ty0 + 4.0f * r && ylo <= ty0 + 4.0f * r + 3.0f) m |= xm << (2 * r);
+  return m;
 }
 
 // The skip decisions (power > 0, alpha < 1/255, T < 1e-4) must come out IDENTICAL in the forward and the backward
@@ -82,19 +91,50 @@ __device__ __forceinline__ void red_shared_max_u32(uint32_t addr, unsigned v) {
 __device__ __forceinline__ void red_shared_add_f32(uint32_t addr, float v) {
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-
-// Staged splat: three consecutive float4 per list entry (48-byte stride: conflict-free for 128-bit accesses),
-//   [0] = (px, py, conic_x', conic_y')   [1] = (conic_z', opacity, hx, hy)   [2] = (r, g, b, id as int bits)
-__device__ __forceinline__ void stage_splat(float4* s_rec, int slot, const float* __restrict__ splat, int id) {
-  const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
-  float4 r2 = ldg4(rec + 8);
-  r2.w = __int_as_float(id);
-  s_rec[3 * slot] = ldg4(rec); s_rec[3 * slot + 1] = ldg4(rec + 4); s_rec[3 * slot + 2] = r2;
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// pull the 128-byte line(s) of a record the NEXT batch will gather into L2 while this batch is walked
+__device__ __forceinline__ void prefetch_l2(const float* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// TF32 split of an fp32 value.  The tensor core reads only sign, exponent and the upper 10 mantissa bits of a .tf32
+// operand, i.e. it multiplies with trunc(x) when handed the raw fp32 bits; tf32_lo(x) = x - trunc(x) is exact in fp32 and
+// |lo| < 2^-10 |x|, so trunc(x) + trunc(lo) carries x to ~2^-20 relative.  (cvt.rna.tf32 costs 4 SASS instructions per
+// value on sm_100a -- a range check, an integer add, a select and a mask; this is one LOP3 and one FADD.)
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// Four 8x8 b16 matrices = four blocks of 8 rows x 4 fp32: lane l supplies the address of row l%8 of block l/8 and
+// receives, per block, the fp32 at (row l/4, column l%4) -- exactly the B fragment of mma.m16n8k8.tf32 when a row is
+// one hit and the columns are pixels.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate.  Lane (g = l/4, t = l%4) holds
+// a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];  b0 = B[t][g], b1 = B[t+4][g];
+// d0 = D[g][2t], d1 = D[g][2t+1], d2 = D[g+8][2t], d3 = D[g+8][2t+1].
+__device__ __forceinline__ void mma_tf32(float& d0, float& d1, float& d2, float& d3, uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Staged splat: three consecutive float4 per list entry (48-byte stride: conflict-free for 128-bit accesses),
+//   [0] = (px, py, conic_x', conic_y')   [1] = (conic_z', opacity, hx, hy)   [2] = (r, g, b, id as int bits)
+// plus one byte of sub-tile hit bits.
+__device__ __forceinline__ void stage_splat(float4* s_rec, unsigned char* s_bits, int slot, const float* __restrict__ splat,
+                                            int id, float tx0, float ty0) {
+  const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
+  const float4 r0 = ldg4(rec), r1 = ldg4(rec + 4);
+  float4 r2 = ldg4(rec + 8);
+  r2.w = __int_as_float(id);
+  s_rec[3 * slot] = r0; s_rec[3 * slot + 1] = r1; s_rec[3 * slot + 2] = r2;
+  s_bits[slot] = (unsigned char)subtile_bits(r0, r1, tx0, ty0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -108,37 +148,41 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
                  unsigned* __restrict__ point_weight_bits, int32_t* __restrict__ point_count) {
   __shared__ float4 s_rec[BATCH * 3];
   __shared__ unsigned s_w[AUX ? BATCH : 1];
+  __shared__ unsigned char s_bits[BATCH];
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SubTile st = make_subtile(v, tile, lane, warp);
   const float pxf = (float)st.x, pyf = (float)st.y;
+  const float tx0 = (float)((tile % v.gx) * TILE), ty0 = (float)((v.row0 + tile / v.gx) * TILE);
   const int beg = tile_start[tile], len = tile_start[tile + 1] - beg;
   const uint32_t s_w_addr = smem_u32(s_w);
+  const uint32_t s_rec_addr = pin_reg(smem_u32(s_rec));
 
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, wmax = 0.f;
   int last = 0, wid = -1;
   int done = st.inside ? 0 : 1;
+  int id_next = tid < len ? sorted_ids[beg + tid] : -1;
 
   for (int base = 0; base < len; base += BATCH) {
     if (__syncthreads_and(done)) break;      // also orders smem reuse between batches
     const int cnt = min(BATCH, len - base);
-    if (tid < cnt) {
-      stage_splat(s_rec, tid, splat, sorted_ids[beg + base + tid]);
-      if (AUX) s_w[tid] = 0u;
-    }
+    const int id = id_next;
+    if (tid < cnt) stage_splat(s_rec, s_bits, tid, splat, id, tx0, ty0);
+    else s_bits[tid] = 0;
+    if (AUX) s_w[tid] = 0u;
+    id_next = base + BATCH + tid < len ? sorted_ids[beg + base + BATCH + tid] : -1;
+    if (id_next >= 0) prefetch_l2(splat + (int64_t)id_next * LGR_SPLAT_FLOATS);
     __syncthreads();
     if (!__all_sync(FULL, done)) {
       for (int c0 = 0; c0 < cnt; c0 += 32) {
         const int e_l = c0 + lane;
-        bool hit = false;
-        if (e_l < cnt) hit = box_hits(s_rec[3 * e_l], s_rec[3 * e_l + 1], st);
-        unsigned mask = __ballot_sync(FULL, hit);
+        unsigned mask = __ballot_sync(FULL, (s_bits[e_l] >> warp) & 1u);
         unsigned own_w = 0u;                 // max weight of the splat this lane tested, over this warp's pixels
         while (mask) {
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
-          const float4* rec = s_rec + 3 * (c0 + j);
-          const float4 r0 = rec[0];
-          const float2 r1 = *reinterpret_cast<const float2*>(rec + 1);    // (conic_z, opacity)
+          const uint32_t rec = s_rec_addr + 48u * (uint32_t)(c0 + j);
+          const float4 r0 = lds_f4(rec);
+          const float2 r1 = lds_f2(rec + 16u);                              // (conic_z, opacity)
           const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
           const float power = eval_power2(r0, r1.x, dx, dy);
           const float alpha = eval_alpha(r1.y, ex2_approx(power));
@@ -148,7 +192,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
             if (test_T < T_STOP) done = 1;
             else {
               w = alpha * T;
-              const float4 r2 = rec[2];
+              const float4 r2 = lds_f4(rec + 32u);
               C0 = fmaf(r2.x, w, C0); C1 = fmaf(r2.y, w, C1); C2 = fmaf(r2.z, w, C2);
               T = test_T;
               last = base + c0 + j + 1;
@@ -187,87 +231,112 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
 // backward
 // ---------------------------------------------------------------------------------------------------------
 // The sweep runs FRONT TO BACK, exactly like the forward: T_j comes from the same multiplications (no division
-// chain), the colour in front of j is the running prefix P_j, and the colour behind j follows from the rendered
-// pixel:  S_j = image - P_j - c_j a_j T_j  (= sum_{k>j} c_k a_k T_k + bg T_final).  Then
-//   dL/da_j = sum_c dL/dC_c * ( c_j T_j - S_j / (1 - a_j) )
+// chain).  With R_j = sum_c dL/dC_c * (colour of everything from splat j on, incl. bg T_final) -- a scalar that starts at
+// sum_c dL/dC_c * pixel_c and loses (c_j . dL/dC) a_j T_j at every contributing splat --
+//   dL/da_j = (c_j . dL/dC) T_j - R_{j+1} / (1 - a_j)
 // which is the published back-to-front recurrence written in closed form.
 //
 // Reduction over the warp's pixels.  Every one of the 9 per-splat outputs is a FIXED-weight linear functional of two
 // per-lane scalars of the hit, wG = dL/dG * G and w = alpha * T:
 //     M00, M10, M01, M20, M11, M02 = sum_l wG_l * {1, u, v, u^2, uv, v^2}_l      (u, v: tile-centred pixel coordinates)
 //     C0, C1, C2                   = sum_l w_l * dL/dC_{0,1,2; l}
-// so each lane publishes just (wG, w) to a per-warp shared scratch (two 4-byte stores, SoA), 27 lanes -- 9 outputs
-// x 3 row groups -- each accumulate 12 rows (3 x LDS.128) against weights they keep in registers, the 3 partials are
-// combined with two shuffles and 9 lanes add into the per-splat accumulators.  The moments are turned into
-// d/dmean2D, d/dconic, d/dopacity once per staged splat when the batch is flushed (X = splat centre, same coordinates):
+// i.e. a [hits x 32] x [32 x 9] contraction.  Each lane publishes (wG, w) of a contributing hit as one row element of two
+// [8 hits][32 pixels] shared-memory blocks; when 8 hits are pending (or the batch ends) the warp runs the contraction
+// on the tensor cores: A (16 rows = 8 wG rows + 8 w rows) straight from the blocks with ldmatrix, B = the weights (moment
+// weights are small half-integers and their products: exact in TF32; the cotangent weights are split hi + lo once per
+// kernel), every A value split hi + lo, fp32 accumulation -- 8 + 12 mma.m16n8k8 per 8 hits, error ~2^-20 relative.
+// The D fragments (hit x output) are added into per-splat shared accumulators.  The moments are turned
+// into d/dmean2D, d/dconic, d/dopacity once per staged splat when the batch is flushed (X = splat centre, same
+// coordinates):
 //     sum wG dx = X M00 - M10,   sum wG dx^2 = X^2 M00 - 2 X M10 + M20,   sum wG dx dy = XY M00 - X M01 - Y M10 + M11 ...
+constexpr int HITS = 8;          // hits per contraction (half the m of mma.m16n8k8: 8 wG rows + 8 w rows)
+constexpr int XROW = 36;         // floats per published row: 32 pixels + 4 pad, so the 8 rows of an ldmatrix block hit 8 bank groups
+constexpr int BWD_SMEM = BATCH * 48 + BATCH * 36 + (BLEND_THREADS / 32) * (2 * HITS * XROW + 192 + 192) * 4 + BATCH;
+
 __global__ void __launch_bounds__(BLEND_THREADS, LGR_BWD_MIN_CTAS)
 blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
                  const float* __restrict__ splat, const float* __restrict__ image,
                  const float* __restrict__ dL_dimage, float* __restrict__ dsplat) {
-  __shared__ float4 s_rec[BATCH * 3];
-  __shared__ float s_g[BATCH * 9];
-  __shared__ __align__(16) float s_x[(BLEND_THREADS / 32) * 64];     // per warp: wG[32] | w[32]
+  extern __shared__ float4 smem_f4[];
+  float4* s_rec = smem_f4;                                                        // [BATCH * 3]
+  float* s_g = reinterpret_cast<float*>(s_rec + BATCH * 3);                       // [BATCH * 9]
+  float* s_x = s_g + BATCH * 9;                                                   // per warp: wG[8][36] | w[8][36]
+  float* s_cw = s_x + (BLEND_THREADS / 32) * 2 * HITS * XROW;                     // per warp: cotangent weights, hi/lo, A-fragment order
+  float* s_mw = s_cw + (BLEND_THREADS / 32) * 192;                                // per warp: moment weights, A-fragment order
+  unsigned char* s_bits = reinterpret_cast<unsigned char*>(s_mw + (BLEND_THREADS / 32) * 192);      // [BATCH]
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SubTile st = make_subtile(v, tile, lane, warp);
   const float pxf = (float)st.x, pyf = (float)st.y;
+  const float tx0 = (float)((tile % v.gx) * TILE), ty0 = (float)((v.row0 + tile / v.gx) * TILE);
   const int beg = tile_start[tile], len = tile_start[tile + 1] - beg;
-  float* xg = s_x + warp * 64;
-  const uint32_t s_g_lane = pin_reg(smem_u32(s_g) + 4u * (uint32_t)lane);   // this lane's column of the accumulators
+  const uint32_t s_g_addr = pin_reg(smem_u32(s_g));
   const uint32_t s_rec_addr = pin_reg(smem_u32(s_rec));
-  const float tcx = (float)((tile % v.gx) * TILE) + 7.5f, tcy = (float)((v.row0 + tile / v.gx) * TILE) + 7.5f;
+  const uint32_t xg_addr = pin_reg(smem_u32(s_x) + (uint32_t)warp * (2 * HITS * XROW * 4));
+  const uint32_t xlane_addr = pin_reg(xg_addr + 4u * (uint32_t)lane);
+  // ldmatrix row address of this lane: row lane%8 of block lane/8; blocks = (wG, chunk 2s), (w, chunk 2s), (wG, chunk 2s+1), (w, chunk 2s+1)
+  const uint32_t xrow = pin_reg(xg_addr + (uint32_t)(lane & 7) * (XROW * 4) + (uint32_t)((lane >> 3) & 1) * (HITS * XROW * 4) +
+                                (uint32_t)(lane >> 4) * 16u);
+  const float tcx = tx0 + 7.5f, tcy = ty0 + 7.5f;
+  const int g = lane >> 2, t = lane & 3;        // mma fragment coordinates of this lane
 
-  float I0 = 0.f, I1 = 0.f, I2 = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+  float Rd = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
   if (st.inside) {
     const int64_t pix = (int64_t)st.y * v.W + st.x, HW = (int64_t)v.H * v.W;
-    I0 = image[pix]; I1 = image[HW + pix]; I2 = image[2 * HW + pix];
     dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix];
+    Rd = image[pix] * dp0 + image[HW + pix] * dp1 + image[2 * HW + pix] * dp2;
   }
-  // fixed reduction weights of this lane: output red_k, rows 12 red_s .. 12 red_s + 11 (clipped to 32)
-  const int red_k = lane % 9, red_s = min(lane / 9, 2);
-  float wt[12];
+  // B fragments of the moment weights, per warp in shared memory: s_mw[((g*4 + t)*4 + s)*2 + {0,1}] = weight of output g at
+  // the pixel of k-step s with k = t (column t, row s of the sub-tile) / k = t + 4 (column t + 4).  |values| <= 56.25 in
+  // steps of 0.25: exact in TF32.
+  const uint32_t mw_addr = pin_reg(smem_u32(s_mw) + (uint32_t)warp * (192 * 4) + (uint32_t)((min(g, 5) * 4 + t) * 32));
+  for (int k = lane; k < 192; k += 32) {
+    const int which = k & 1, s_ = (k >> 1) & 3, t_ = (k >> 3) & 3, g_ = k >> 5;
+    const float u = (float)((warp & 1) * 8 + t_ + 4 * which) - 7.5f, vv = (float)((warp >> 1) * 4 + s_) - 7.5f;
+    const float f = g_ == 0 ? 1.f : g_ == 1 ? u : g_ == 2 ? vv : g_ == 3 ? u * u : g_ == 4 ? u * vv : vv * vv;
+    s_mw[warp * 192 + k] = f;
+  }
+  // B fragments of the cotangent weights (columns 0..2 = channel): s_cw[((c*4 + t)*4 + s)*4 + {0,1,2,3}] = hi(k=t), hi(k=t+4), lo(k=t), lo(k=t+4)
+  const uint32_t cw_addr = pin_reg(smem_u32(s_cw) + (uint32_t)warp * (192 * 4) + (uint32_t)((min(g, 2) * 4 + t) * 64));
   {
-    const float u = pxf - tcx, w_ = pyf - tcy;
+    float* cw = s_cw + warp * 192;
+    const int col = lane & 7, s = lane >> 3, tt = col & 3, which = col >> 2;
+    const float dpc[3] = {dp0, dp1, dp2};
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const int r = min(12 * red_s + i, 31);
-      const float ur = __shfl_sync(FULL, u, r), vr = __shfl_sync(FULL, w_, r);
-      const float d0 = __shfl_sync(FULL, dp0, r), d1 = __shfl_sync(FULL, dp1, r), d2 = __shfl_sync(FULL, dp2, r);
-      float t;
-      switch (red_k) {
-        case 0: t = 1.f; break;
-        case 1: t = ur; break;
-        case 2: t = vr; break;
-        case 3: t = ur * ur; break;
-        case 4: t = ur * vr; break;
-        case 5: t = vr * vr; break;
-        case 6: t = d0; break;
-        case 7: t = d1; break;
-        default: t = d2; break;
-      }
-      wt[i] = (lane < 27 && 12 * red_s + i < 32) ? t : 0.f;
+    for (int c = 0; c < 3; c++) {
+      cw[((c * 4 + tt) * 4 + s) * 4 + which] = dpc[c];                  // read as trunc(x) by the tensor core
+      cw[((c * 4 + tt) * 4 + s) * 4 + 2 + which] = tf32_lo(dpc[c]);
     }
   }
-  // where this lane reads: the wG half for outputs 0..5, the w half for 6..8; group 2 re-reads quad 7 with weight 0
-  const float4* red_src = reinterpret_cast<const float4*>(xg + (red_k >= 6 ? 32 : 0)) + 3 * red_s;
-  const int q2 = red_s == 2 ? 1 : 2;
+  __syncwarp();
 
-  float T = 1.0f, P0 = 0.f, P1 = 0.f, P2 = 0.f;
+  float T = 1.0f;
   int done = st.inside ? 0 : 1;
+  int id_next = tid < len ? sorted_ids[beg + tid] : -1;
 
   for (int base = 0; base < len; base += BATCH) {
     if (__syncthreads_and(done)) break;
     const int cnt = min(BATCH, len - base);
-    if (tid < cnt) stage_splat(s_rec, tid, splat, sorted_ids[beg + base + tid]);
+    const int id = id_next;
+    if (tid < cnt) stage_splat(s_rec, s_bits, tid, splat, id, tx0, ty0);
+    else s_bits[tid] = 0;
     for (int k = tid; k < cnt * 9; k += BLEND_THREADS) s_g[k] = 0.f;
+    id_next = base + BATCH + tid < len ? sorted_ids[beg + base + BATCH + tid] : -1;
+    if (id_next >= 0) prefetch_l2(splat + (int64_t)id_next * LGR_SPLAT_FLOATS);
     __syncthreads();
     if (!__all_sync(FULL, done)) {
-      for (int c0 = 0; c0 < cnt; c0 += 32) {
-        const int e_l = c0 + lane;
-        bool hit = false;
-        if (e_l < cnt) hit = box_hits(s_rec[3 * e_l], s_rec[3 * e_l + 1], st);
-        unsigned mask = __ballot_sync(FULL, hit);
-        while (mask) {
+      int c0 = -32, pend = 0, my_e = 0;
+      unsigned mask = 0u;
+      bool fin = false;
+      while (true) {
+        if (mask == 0u) {      // next group of 32 staged splats with a hit
+          do {
+            c0 += 32;
+            fin = c0 >= cnt || __all_sync(FULL, done);
+            if (fin) break;
+            mask = __ballot_sync(FULL, (s_bits[c0 + lane] >> warp) & 1u);
+          } while (mask == 0u);
+        }
+        if (!fin) {
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
           const int e = c0 + j;
@@ -278,37 +347,64 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           const float power = eval_power2(r0, r1.x, dx, dy);
           const float G = ex2_approx(power);
           const float alpha = eval_alpha(r1.y, G);
+          const float om = __fsub_rn(1.0f, alpha);
           int contrib = 0;
           float test_T = 0.f;
           if (!done && power <= 0.0f && alpha >= ALPHA_MIN) {
-            test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+            test_T = __fmul_rn(T, om);
             if (test_T < T_STOP) done = 1; else contrib = 1;
           }
-          if (!__any_sync(FULL, contrib)) continue;
-          float wG = 0.f, w = 0.f;
-          if (contrib) {
-            const float4 r2 = lds_f4(rec + 32u);
-            w = alpha * T;
-            const float cdot = r2.x * dp0 + r2.y * dp1 + r2.z * dp2;
-            // colour behind j (+ bg T_final):  S = I - P - c w
-            const float Sdot = (I0 - P0) * dp0 + (I1 - P1) * dp1 + (I2 - P2) * dp2 - cdot * w;
-            P0 = fmaf(r2.x, w, P0); P1 = fmaf(r2.y, w, P1); P2 = fmaf(r2.z, w, P2);
-            const float dL_dalpha = cdot * T - Sdot * rcp_approx(1.0f - alpha);
-            T = test_T;
-            wG = r1.y * dL_dalpha * G;                      // dL/dG * G   (the 0.99 clamp is straight-through)
+          if (__any_sync(FULL, contrib)) {
+            float wG = 0.f, w = 0.f;
+            if (contrib) {
+              const float4 r2 = lds_f4(rec + 32u);
+              w = alpha * T;
+              const float cdot = r2.x * dp0 + r2.y * dp1 + r2.z * dp2;
+              Rd = fmaf(-cdot, w, Rd);                          // what is behind j (+ bg T_final), dotted with dL/dC
+              const float dL_dalpha = cdot * T - Rd * rcp_approx(om);
+              T = test_T;
+              wG = r1.y * dL_dalpha * G;                        // dL/dG * G   (the 0.99 clamp is straight-through)
+            }
+            const uint32_t row = xlane_addr + (uint32_t)pend * (XROW * 4);
+            sts_f32(row, wG); sts_f32(row + HITS * XROW * 4, w);
+            if (lane == pend) my_e = e;
+            pend++;
           }
-          xg[lane] = wG; xg[32 + lane] = w;
-          __syncwarp();
-          const float4 a0 = red_src[0], a1 = red_src[1], a2 = red_src[q2];
-          float sum = wt[0] * a0.x;
-          sum = fmaf(wt[1], a0.y, sum); sum = fmaf(wt[2], a0.z, sum); sum = fmaf(wt[3], a0.w, sum);
-          sum = fmaf(wt[4], a1.x, sum); sum = fmaf(wt[5], a1.y, sum); sum = fmaf(wt[6], a1.z, sum); sum = fmaf(wt[7], a1.w, sum);
-          sum = fmaf(wt[8], a2.x, sum); sum = fmaf(wt[9], a2.y, sum); sum = fmaf(wt[10], a2.z, sum); sum = fmaf(wt[11], a2.w, sum);
-          sum += __shfl_down_sync(FULL, sum, 9) + __shfl_down_sync(FULL, sum, 18);
-          if (lane < 9) red_shared_add_f32(s_g_lane + 36u * (uint32_t)e, sum);
-          __syncwarp();
         }
-        if (__all_sync(FULL, done)) break;
+        if (pend == HITS || (fin && pend > 0)) {
+          // ---- contract the pending hits on the tensor cores ----
+          // A (16 x 32 pixels): rows 0..7 = wG of the 8 hits, rows 8..15 = w of the same hits; one ldmatrix.x4 per k-step
+          // delivers (a0, a1, a2, a3) in place.  B (32 pixels x 8): the weights -- Bm moments (6 columns, exact), Bc the
+          // cotangents (3 columns, hi + lo).  D1 = A Bm (rows 0..7 used), D2 = A Bc (rows 8..15 used): two independent chains.
+          __syncwarp();
+          float d0 = 0.f, d1 = 0.f, z0 = 0.f, z1 = 0.f, y0 = 0.f, y1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(xrow + 32u * s, a0, a1, a2, a3);
+            const uint32_t l0 = __float_as_uint(tf32_lo(__uint_as_float(a0))), l1 = __float_as_uint(tf32_lo(__uint_as_float(a1)));
+            const uint32_t l2 = __float_as_uint(tf32_lo(__uint_as_float(a2))), l3 = __float_as_uint(tf32_lo(__uint_as_float(a3)));
+            float2 bm = make_float2(0.f, 0.f);
+            float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g < 6) bm = lds_f2(mw_addr + 8u * s);
+            if (g < 3) bc = lds_f4(cw_addr + 16u * s);
+            mma_tf32(d0, d1, z0, z1, a0, a1, a2, a3, __float_as_uint(bm.x), __float_as_uint(bm.y));
+            mma_tf32(y0, y1, d2, d3, a0, a1, a2, a3, __float_as_uint(bc.x), __float_as_uint(bc.y));
+            mma_tf32(d0, d1, z0, z1, l0, l1, l2, l3, __float_as_uint(bm.x), __float_as_uint(bm.y));
+            mma_tf32(y0, y1, d2, d3, l0, l1, l2, l3, __float_as_uint(bc.x), __float_as_uint(bc.y));
+            mma_tf32(y0, y1, d2, d3, a0, a1, a2, a3, __float_as_uint(bc.z), __float_as_uint(bc.w));
+          }
+          // lane (g, t): d0/d1 = moments 2t, 2t+1 of hit g (t < 3) ; d2/d3 = colour sums 2t, 2t+1 of hit g (t = 0: 0, 1; t = 1: 2)
+          const uint32_t acc = s_g_addr + 36u * (uint32_t)__shfl_sync(FULL, my_e, g);
+          if (g < pend) {
+            if (t < 3) { red_shared_add_f32(acc + 8u * t, d0); red_shared_add_f32(acc + 8u * t + 4u, d1); }
+            if (t < 2) red_shared_add_f32(acc + 24u + 8u * t, d2);
+            if (t == 0) red_shared_add_f32(acc + 28u, d3);
+          }
+          __syncwarp();
+          pend = 0;
+        }
+        if (fin) break;
       }
     }
     __syncthreads();
@@ -362,8 +458,11 @@ int launch_blend_bwd(const View& v, const int32_t* tile_start, const int32_t* so
                      const float* image, const float* dL_dimage, float* dsplat, cudaStream_t st) {
   const int ntiles = v.gx * (v.row1 - v.row0);
   if (ntiles <= 0) return 0;
+  // > 48 KB of dynamic shared memory needs the opt-in; the attribute is per device and cheap to set, so set it every time
+  cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+  if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_BLEND_BWD, st);
-  blend_bwd_kernel<<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, dL_dimage, dsplat);
+  blend_bwd_kernel<<<ntiles, BLEND_THREADS, BWD_SMEM, st>>>(v, tile_start, sorted_ids, splat, image, dL_dimage, dsplat);
   LGR_CHECK_LAUNCH();
   return 0;
 }

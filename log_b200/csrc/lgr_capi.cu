@@ -15,7 +15,7 @@ int launch_project_bwd(const View&, int64_t, const float*, const float*, const f
 int launch_grad_scatter_add(int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
 int launch_grad_scatter_add_staged(const float*, int, int64_t, int64_t, int64_t, float*, cudaStream_t);
 int launch_band_scan(const View&, cudaStream_t);
-int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, bool, cudaStream_t);
 int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, const int32_t*, int32_t*,
                         uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
 int sort_smem_capacity();
@@ -101,7 +101,7 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
   if (rc) return rc;
   rc = launch_band_scan(v, st);
   if (rc) return rc;
-  return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, st);
+  return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, view->tile_rank_d != nullptr, st);
 }
 
 int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, int32_t max_tile_len,
@@ -234,7 +234,7 @@ int lgr_shard_recv_bin(const lgr_view* view, const lgr_shard_layout* layout, flo
   if (e != cudaSuccess) return (int)e;
   int rc = launch_shard_recv_count(v, make_layout(layout), exchange_d, dsplat_d, tile_cursor_d, meta_d, st);
   if (rc) return rc;
-  return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, st);
+  return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, view->tile_rank_d != nullptr, st);
 }
 
 int lgr_blend_backward(const lgr_view* view, int64_t n, int64_t num_instances, const float* splat_d,
@@ -314,7 +314,7 @@ int lgr_profile_collect(double* ms_out, int32_t* launches_out, int32_t capacity)
 
 const char* lgr_profile_kernel_name(int k) {
   static const char* names[K_COUNT] = {"project_fwd", "tile_scan", "bin_scatter", "tile_sort", "blend_fwd", "blend_bwd",
-                                       "project_bwd", "compute_radius"};
+                                       "project_bwd", "compute_radius", "shard_send", "shard_recv", "shard_return", "shard_gather"};
   return (k >= 0 && k < K_COUNT) ? names[k] : "";
 }
 

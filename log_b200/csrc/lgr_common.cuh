@@ -32,6 +32,7 @@ struct View {
   int32_t* band_count;
   int32_t* band_rows;        // (N) dense row -> Gaussian id, written by the scatter kernel
   float* band_dsplat;        // (N,12) or NULL: rows of listed Gaussians are zeroed by the scatter kernel
+  int32_t* tile_rank;        // (rows,4) or NULL: slots of the <= 4 tiles of a small splat, taken by the counting pass
   int band_blocks;           // B
   const float* view;         // (4,4) transposed storage: t_j = sum_i p_i * view[i*4+j] + view[12+j]
   const float* proj;
@@ -41,7 +42,7 @@ struct View {
 
 inline View make_view(const lgr_view* v, int64_t n = 0) {
   View o;
-  o.num_owners = v->num_owners; o.band_ids = v->band_ids_d; o.band_blk = v->band_blk_d; o.band_count = v->band_count_d; o.band_rows = v->band_rows_d; o.band_dsplat = v->band_dsplat_d;
+  o.num_owners = v->num_owners; o.band_ids = v->band_ids_d; o.band_blk = v->band_blk_d; o.band_count = v->band_count_d; o.band_rows = v->band_rows_d; o.band_dsplat = v->band_dsplat_d; o.tile_rank = v->tile_rank_d;
   o.owner_chunk = o.num_owners > 0 ? (int)LGR_OWNER_CHUNK(n, (int64_t)o.num_owners) : 256;
   if (o.owner_chunk < 256) o.owner_chunk = 256;
   o.band_blocks = (int)((n + 255) / 256);
@@ -208,6 +209,33 @@ __device__ __forceinline__ void tile_rect_tight(float px, float py, int rad, flo
   y0 = max(max(y0, ty0), row0); y1 = min(min(y1, ty1), row1);
   if (x1 < x0) x1 = x0;
   if (y1 < y0) y1 = y0;
+}
+
+// Count the tiles [x0,x1) x [y0,y1) of one splat (row = its index in the splat array).  Per tile two counters share one
+// 128-byte line: [0] splats covering <= 4 tiles, [1] the others.  With View::tile_rank the small splats take their slots
+// here (returning atomics, all issued before the first use so that the L2 round trips overlap) and the scatter kernel
+// needs no atomic for them; big splats are only counted and take their slots behind the small ones in the scatter.
+// Without tile_rank everything is counted in [0] and the scatter takes every slot.
+__device__ __forceinline__ void count_tiles(const View& v, int32_t* __restrict__ tile_count, int64_t row, int x0, int y0, int x1,
+                                            int y1) {
+  const int w = x1 - x0, cnt = w * (y1 - y0);
+  if (v.tile_rank == nullptr) {
+    for (int ty = y0; ty < y1; ty++)
+      for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE, 1);
+    return;
+  }
+  if (cnt <= 4) {
+    int r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      r[k] = -1;
+      if (k < cnt) r[k] = atomicAdd(tile_count + ((y0 + k / max(w, 1) - v.row0) * v.gx + x0 + k % max(w, 1)) * CSTRIDE, 1);
+    }
+    *reinterpret_cast<int4*>(v.tile_rank + 4 * row) = make_int4(r[0], r[1], r[2], r[3]);
+    return;
+  }
+  for (int ty = y0; ty < y1; ty++)
+    for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE + 1, 1);
 }
 
 // ---- SH basis (LoG/model/sh_utils.py:31-58, DC first) ---------------------------------------------------

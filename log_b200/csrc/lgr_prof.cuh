@@ -6,7 +6,7 @@
 namespace lgr {
 
 enum KernelId { K_PROJECT_FWD = 0, K_TILE_SCAN, K_BIN_SCATTER, K_TILE_SORT, K_BLEND_FWD, K_BLEND_BWD, K_PROJECT_BWD,
-                K_COMPUTE_RADIUS, K_COUNT };
+                K_COMPUTE_RADIUS, K_SHARD_SEND, K_SHARD_RECV, K_SHARD_RETURN, K_SHARD_GATHER, K_COUNT };
 
 struct Profiler {
   static constexpr int MAX_PAIRS = 8192;

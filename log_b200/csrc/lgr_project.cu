@@ -10,9 +10,6 @@
 namespace lgr {
 
 constexpr int PROJ_THREADS = 256;
-#ifndef LGR_AGG_ATOMICS
-#define LGR_AGG_ATOMICS 0      // 1: warp-aggregated tile-count / slot atomics (lgr_bin.cu), for spatially coherent input
-#endif
 
 __device__ __forceinline__ void load3(const float* __restrict__ p, int64_t i, float o[3]) {
   o[0] = __ldg(p + 3 * i); o[1] = __ldg(p + 3 * i + 1); o[2] = __ldg(p + 3 * i + 2);
@@ -123,9 +120,6 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     work = threadIdx.x < total;
     i = work ? (int64_t)blockIdx.x * PROJ_THREADS + sSurv[threadIdx.x] : n;
   }
-#if LGR_AGG_ATOMICS
-  int cx0 = 0, cy0 = 0, cx1 = 0, cy1 = 0;      // binning rectangle of this lane's Gaussian (empty if it has none)
-#endif
   if (work) {
     float p[3], s[3], R[9], Sg[9];
     load3(means, i, p);
@@ -212,12 +206,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
         r2 = make_float4(rgb[0], rgb[1], rgb[2], cv.t[2]);
         if (reach) {
           tile_rect_tight(px, py, rad, hx, hy, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
-#if LGR_AGG_ATOMICS
-          cx0 = x0; cy0 = y0; cx1 = x1; cy1 = y1;      // counted after the divergent part, by the whole warp (see below)
-#else
-          for (int ty = y0; ty < y1; ty++)
-            for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE, 1);
-#endif
+          count_tiles(v, tile_count, i, x0, y0, x1, y1);
         }
       }
     }
@@ -230,23 +219,6 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   } else if (i < n) {
     radii[i] = 0;      // only reachable outside band mode (i >= n otherwise)
   }
-#if LGR_AGG_ATOMICS
-  {      // warp-aggregated tile counting (see bin_scatter_agg_kernel in lgr_bin.cu): one RED per distinct tile per warp
-    const int lane_ = threadIdx.x & 31;
-    const int w_ = cx1 - cx0, cnt_ = w_ * (cy1 - cy0);
-    const bool small_ = cnt_ <= 4;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int t = -1 - lane_;
-      if (small_ && k < cnt_) t = (cy0 + k / max(w_, 1) - v.row0) * v.gx + cx0 + k % max(w_, 1);
-      const unsigned peers = __match_any_sync(0xffffffffu, t);
-      if (t >= 0 && lane_ == __ffs(peers) - 1) atomicAdd(tile_count + t * CSTRIDE, __popc(peers));
-    }
-    if (!small_)
-      for (int ty = cy0; ty < cy1; ty++)
-        for (int tx = cx0; tx < cx1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE, 1);
-  }
-#endif
   if (v.num_owners > 0) {      // atomics-free compaction of the ids that reach the band into this CTA's segment
     __shared__ int sCnt[PROJ_THREADS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -197,8 +197,7 @@ shard_recv_count_kernel(View v, ShardLayout L, float* __restrict__ xbuf, float* 
       stock = (unsigned)((x1 - x0) * max(0, min(y1, v.row1) - max(y0, v.row0)));
       vis = 1;
       tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
-      for (int ty = y0; ty < y1; ty++)
-        for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE, 1);
+      count_tiles(v, tile_count, slot, x0, y0, x1, y1);
       float4* z = reinterpret_cast<float4*>(dsplat + slot * LGR_GRAD_FLOATS);
       z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -287,6 +286,7 @@ static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + SHARD_THRE
 int launch_shard_send(const View& v, const ShardLayout& L, int64_t n, int64_t gid_base, const float* splat,
                       const int32_t* radii, int32_t* send_blk, void* const* peer_base, cudaStream_t st) {
   const int B = (int)blocks_for(n > 0 ? n : 1);
+  ProfScope ps(K_SHARD_SEND, st, n > 0 ? 3 : 1);
   if (n > 0) {
     shard_count_kernel<<<B, SHARD_THREADS, 0, st>>>(v, L.R, n, splat, radii, send_blk, B);
     LGR_CHECK_LAUNCH();
@@ -307,6 +307,7 @@ int launch_shard_recv_count(const View& v, const ShardLayout& L, float* xbuf, fl
                             cudaStream_t st) {
   const int64_t total = (int64_t)L.R * L.cap;
   if (total <= 0) return 0;
+  ProfScope ps(K_SHARD_RECV, st);
   shard_recv_count_kernel<<<blocks_for(total), SHARD_THREADS, 0, st>>>(v, L, xbuf, dsplat, tile_count, meta);
   LGR_CHECK_LAUNCH();
   return 0;
@@ -315,6 +316,7 @@ int launch_shard_recv_count(const View& v, const ShardLayout& L, float* xbuf, fl
 int launch_shard_return(const ShardLayout& L, const float* xbuf, int64_t total_rows, const void* rows, int row_floats,
                         int64_t dst_off_floats, void* const* peer_base, cudaStream_t st) {
   if (total_rows <= 0) return 0;
+  ProfScope ps(K_SHARD_RETURN, st);
   if (row_floats % 4 == 0) {
     const int items = row_floats / 4;
     int64_t nb = (total_rows * items + SHARD_THREADS - 1) / SHARD_THREADS;
@@ -336,6 +338,7 @@ int launch_shard_gather(const View& v, const ShardLayout& L, int64_t n, const fl
                         cudaStream_t st) {
   if (n <= 0) return 0;
   const int B = (int)blocks_for(n);
+  ProfScope ps(K_SHARD_GATHER, st);
   shard_gather_kernel<<<B, SHARD_THREADS, 0, st>>>(v, L, n, splat, radii, send_blk, B, xbuf, dsplat_out, weight_out, pcount_out);
   LGR_CHECK_LAUNCH();
   return 0;

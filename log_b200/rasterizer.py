@@ -25,6 +25,8 @@ from . import _capi
 from ._capi import LGR_FILTER_ADD, LGR_FILTER_MAX, LGR_FILTER_NONE, LgrView
 
 PREZERO_DSPLAT = bool(int(__import__('os').environ.get('LGR_PREZERO_DSPLAT', '0')))      # see rasterize_forward
+# tile slots taken once, by the counting pass (lgr_view.tile_rank_d); 0 = the two-pass binning of round 1 (A/B knob)
+RANKED_BIN = bool(int(__import__('os').environ.get('LGR_RANKED_BIN', '1')))
 FLAVOUR_STOCK = 'stock'   # diff_gaussian_rasterization            (graphdeco-inria)   -> 2-tuple, cov += 0.3
 FLAVOUR_FORK = 'fork'     # diff_gaussian_rasterization_wodilate   (chingswy antialias) -> 5-tuple, cov = max(cov, 0.3)
 
@@ -71,7 +73,7 @@ def _stream():
 
 def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep,
                num_owners=0, band_ids=None, band_count=None, band_blk=None, band_rows=None, band_dsplat=None,
-               raw_params=False):
+               raw_params=False, tile_rank=None):
     dev = s.viewmatrix.device
     vm, pm = _f32c(s.viewmatrix, 'viewmatrix'), _f32c(s.projmatrix, 'projmatrix', dev)
     bg = _f32c(s.bg, 'bg', dev)
@@ -91,6 +93,7 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
     v.band_blk_d = band_blk.data_ptr() if band_blk is not None else None
     v.band_rows_d = band_rows.data_ptr() if band_rows is not None else None
     v.band_dsplat_d = band_dsplat.data_ptr() if band_dsplat is not None else None
+    v.tile_rank_d = tile_rank.data_ptr() if tile_rank is not None else None
     v.viewmatrix_d, v.projmatrix_d = vm.data_ptr(), pm.data_ptr()
     v.campos_d = cp.data_ptr() if cp is not None else None
     v.bg_d = bg.data_ptr()
@@ -130,8 +133,10 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         band_ids = torch.empty((max(256 * nb, 1),), dtype=torch.int32, device=dev)
         band_blk = torch.empty((2 * nb + 1,), dtype=torch.int32, device=dev)
         band_count = torch.empty((num_owners,), dtype=torch.int32, device=dev)
+    tile_rank = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev) if RANKED_BIN else None
+    keep.append(tile_rank)
     view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep, num_owners, band_ids, band_count, band_blk, band_rows, band_dsplat,
-                      raw_params)
+                      raw_params, tile_rank)
     H, W = view.image_height, view.image_width
     gx, gy = (W + 15) // 16, (H + 15) // 16
     rows = gy if tile_rows is None else int(tile_rows[1]) - int(tile_rows[0])

@@ -271,7 +271,9 @@ class SplatExchange:
         s.keep, s.n, s.want_aux, s.settings = [], n, bool(want_aux), settings
         K = 0 if sh is None else int(sh.shape[1])
         s.view_full = _make_view(settings, filter_mode, want_aux, K, None, s.keep, raw_params=raw_params)
-        s.view_band = _make_view(settings, filter_mode, want_aux, K, self.band, s.keep, raw_params=raw_params)
+        from .rasterizer import RANKED_BIN
+        rank_rows = self._scratch('tile_rank', (self.world * self.cap, 4), torch.int32) if RANKED_BIN else None
+        s.view_band = _make_view(settings, filter_mode, want_aux, K, self.band, s.keep, raw_params=raw_params, tile_rank=rank_rows)
         H, W = s.view_full.image_height, s.view_full.image_width
         if H != self.image_height:
             raise ValueError('image height differs from the one the bands were cut for')

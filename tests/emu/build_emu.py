@@ -4,7 +4,7 @@ in tests/emu/cuda_runtime.h and build tests/emu/_build/libemu.so.  Test infrastr
 The translation touches exactly three constructs, mechanically:
   kernel<<<grid, block, smem, stream>>>(args);   ->  emu::launch(dim3(grid), dim3(block), smem, [=]() { kernel(args); });
   extern __shared__ T name[];                    ->  T* name = reinterpret_cast<T*>(emu::dyn_smem());
-  the eight inline-PTX helper functions of lgr_blend.cu  ->  host versions in emu_blend_helpers.h
+  the inline-PTX helper functions of lgr_blend.cu (PTX_HELPERS)  ->  host versions in emu_blend_helpers.h
 Everything else (the kernel bodies) is compiled verbatim.
 """
 import os
@@ -18,7 +18,8 @@ BUILD = os.path.join(HERE, '_build')
 LIB = os.path.join(BUILD, 'libemu.so')
 SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))      # every kernel file and the C entry points
 # inline-PTX helpers of lgr_blend.cu, replaced by tests/emu/emu_blend_helpers.h
-PTX_HELPERS = ['ex2_approx', 'rcp_approx', 'smem_u32', 'lds_f4', 'lds_f2', 'pin_reg', 'red_shared_max_u32', 'red_shared_add_f32']
+PTX_HELPERS = ['ex2_approx', 'rcp_approx', 'smem_u32', 'lds_f4', 'lds_f2', 'sts_f32', 'pin_reg', 'red_shared_max_u32', 'red_shared_add_f32',
+               'prefetch_l2', 'ldsm_x4', 'mma_tf32']
 
 
 def _split_top(s):

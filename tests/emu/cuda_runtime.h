@@ -57,6 +57,8 @@ struct dim3 {
 };
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
@@ -89,7 +91,8 @@ struct Cta {
   Fiber* fibers = nullptr;
   int nthreads = 0, alive = 0, cta_waiting = 0;
   int warp_alive[32], warp_waiting[32];
-  unsigned long long scratch[32][32];   // [warp][lane] exchange slots of the warp collectives
+  struct Slot { unsigned long long u[4]; };
+  Slot scratch[32][32];                 // [warp][lane] exchange slots of the warp collectives (up to 32 bytes per lane)
   int cta_acc = 0;                       // __syncthreads_or / _and / _count accumulator
   int cta_gen = 0, warp_gen[32];         // barrier generations (TSan: alternating sync objects)
   char cta_sync[2], warp_sync[32][2], launch_sync, done_sync;
@@ -252,8 +255,8 @@ EMU_NOTSAN inline bool lane_alive(int l) {
   return t < c->nthreads && c->fibers[t].state != DONE;
 }
 template <class T> EMU_NOTSAN inline void publish(T v) {
-  static_assert(sizeof(T) <= 8, "collective payload");
-  unsigned long long u = 0; memcpy(&u, &v, sizeof(T));
+  static_assert(sizeof(T) <= sizeof(Cta::Slot), "collective payload");
+  Cta::Slot u = {{0, 0, 0, 0}}; memcpy(&u, &v, sizeof(T));
   cta()->scratch[warp_id()][lane_id()] = u;
   barrier_warp();
 }

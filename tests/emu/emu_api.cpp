@@ -3,7 +3,7 @@
 #include "lgr_common.cuh"
 
 namespace lgr {
-int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, cudaStream_t);
+int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, bool, cudaStream_t);
 int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, const int32_t*, int32_t*,
                         uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
 int launch_point_compact(int64_t, const int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, cudaStream_t);
@@ -32,7 +32,7 @@ int emu_sort_smem_capacity(void) { return sort_smem_capacity(); }
 // tile_cursor holds the per-tile counts (stride CSTRIDE) on entry, as project_fwd leaves them
 int emu_tile_scan(const lgr_view* view, int32_t* tile_start, int32_t* tile_cursor, int32_t* meta) {
   const View v = make_view(view, 0);
-  return launch_tile_scan(v.gx * (v.row1 - v.row0), tile_start, tile_cursor, meta, nullptr);
+  return launch_tile_scan(v.gx * (v.row1 - v.row0), tile_start, tile_cursor, meta, view->tile_rank_d != nullptr, nullptr);
 }
 
 int emu_bin_and_sort(const lgr_view* view, int64_t n, int64_t num_instances, int32_t max_tile_len, int32_t num_long_tiles,
@@ -60,7 +60,7 @@ int emu_shard_recv_bin(const lgr_view* view, const lgr_shard_layout* layout, flo
   memset(meta, 0, sizeof(int32_t) * LGR_META_INTS);
   int rc = launch_shard_recv_count(v, make_layout(layout), exchange, dsplat, tile_cursor, meta, nullptr);
   if (rc) return rc;
-  return launch_tile_scan(ntiles, tile_start, tile_cursor, meta, nullptr);
+  return launch_tile_scan(ntiles, tile_start, tile_cursor, meta, view->tile_rank_d != nullptr, nullptr);
 }
 
 int emu_shard_return_rows(const lgr_shard_layout* layout, const float* exchange, int64_t total_rows, const void* rows,

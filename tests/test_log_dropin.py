@@ -344,4 +344,7 @@ def test_log_training_loop_with_the_fused_sparse_adam(emulated_backend, monkeypa
     for k in ref:
         # LoG initialises isotropic scales, for which d loss / d rotation is exactly zero: the rotation gradient is float
         # noise, Adam turns noise into +-lr steps, and the two optimisers' differently rounded noise drifts apart (1e-4).
-        assert rel(got[k], ref[k]) < (1e-3 if k == 'rotation' else 2e-6), (k, rel(got[k], ref[k]))
+        # Once the scales have taken their first +-lr steps they are no longer isotropic, so the drifted rotations feed
+        # the scale gradient (and its Adam moments) at the same 1e-4 level; the scales themselves still agree exactly.
+        loose = k in ('rotation', 'm_scaling', 'v_scaling')
+        assert rel(got[k], ref[k]) < (2e-3 if loose else 2e-6), (k, rel(got[k], ref[k]))
