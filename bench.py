@@ -136,6 +136,23 @@ def morton_order(cam, sc, W, H):
     return {k: v[perm].contiguous() for k, v in sc.items()}
 
 
+def pick_cpu_threads(c_oracle, step):
+    """The CPU arm gets the team size that is FASTEST on this box: all logical CPUs or one thread per physical core
+    (half of them) -- the port is bound by memory and atomics, and SMT siblings slow it down on some hosts.  torchrun
+    exports OMP_NUM_THREADS=1 to its children, so the team is always sized explicitly.  Returns (threads, {threads: seconds})."""
+    ncpu = os.cpu_count() or 1
+    tried = {}
+    for nt in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
+        c_oracle.set_num_threads(nt)
+        step()                                     # warm-up at this team size
+        t0 = time.perf_counter()
+        step()
+        tried[nt] = time.perf_counter() - t0
+    best = min(tried, key=tried.get)
+    c_oracle.set_num_threads(best)
+    return best, tried
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port (C, OpenMP, all host threads) on a bounded sample of the workload."""
     if rank != 0:
@@ -146,13 +163,10 @@ def run_reference(args, rank, world):
     cam, sc, G = make_inputs(args.workload)
     sub = {k: v[:ns].numpy() for k, v in sc.items()}
     kw = dict(colors_precomp=sub['colors']) if deg == 0 else dict(shs=sub['shs'])
-    # torchrun exports OMP_NUM_THREADS=1 to its children: size the OpenMP team explicitly from the box's cores
-    c_oracle.set_num_threads(os.cpu_count() or 1)
-    cores = c_oracle.num_threads()
-
     def step():
         c_oracle.render(cam, sub['means3D'], sub['opacities'], sub['scales'], sub['rotations'],
                         filter_mode=c_oracle.FILTER_MAX, dL_dimage=G.numpy(), dtype=np.float32, want_aux=True, **kw)
+    cores, tried = pick_cpu_threads(c_oracle, step)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -160,7 +174,8 @@ def run_reference(args, rank, world):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     val = ns / dt
-    sample = f'first {ns} of {n} Gaussians, {W}x{H}, fwd+bwd, fp32, {cores} OpenMP threads'
+    sample = (f'first {ns} of {n} Gaussians, {W}x{H}, fwd+bwd, fp32, {cores} OpenMP threads (fastest of ' +
+              ', '.join(f'{k}: {v:.2f} s' for k, v in sorted(tried.items())) + ')')
     print(json.dumps({
         'impl': 'reference', 'metric': 'gaussians_per_s_fwd_bwd', 'value': val, 'unit': 'Gaussians/s', 'n_gpus': 0,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong',
@@ -474,6 +489,7 @@ def main():
     kms = {'project_fwd': prof['project_fwd'][0], 'bin_sort': prof['tile_scan'][0] + prof['bin_scatter'][0] + prof['tile_sort'][0],
            'blend_fwd': prof['blend_fwd'][0], 'blend_bwd': prof['blend_bwd'][0], 'project_bwd': prof['project_bwd'][0]}
     kms = {k: v / args.steps for k, v in kms.items()}
+    kms_bin = {k: prof[k][0] / args.steps for k in ('tile_scan', 'bin_scatter', 'tile_sort')}
     dom = max(kms, key=kms.get)
     ach = kb[dom] / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
     traffic = None
@@ -495,7 +511,7 @@ def main():
         'roofline_step': {'b_model_bytes': b_model, 'b_min_bytes': b_min, 'achieved': b_model / (ms_step * 1e-3) / 1e9,
                           'frac': b_model / (ms_step * 1e-3) / 1e9 / peak, 'b_min_frac': b_min / (ms_step * 1e-3) / 1e9 / peak,
                           'frac_stock_rule_instances': b_model_stock / (ms_step * 1e-3) / 1e9 / peak},
-        'kernel_ms': kms, 'phase_ms_rank0': phases, 'gpu_launches': launches, 'clocks': clk, 'e2e': e2e,
+        'kernel_ms': kms, 'kernel_ms_bin_sort': kms_bin, 'phase_ms_rank0': phases, 'gpu_launches': launches, 'clocks': clk, 'e2e': e2e,
     }
     if world > 1:
         line['parity'] = parity
@@ -505,18 +521,20 @@ def main():
         ns = min(n, CPU_SAMPLE[args.workload])
         sub = {k: v[:ns].numpy() for k, v in sc.items()}
         kw = dict(colors_precomp=sub['colors']) if deg == 0 else dict(shs=sub['shs'])
-        c_oracle.set_num_threads(os.cpu_count() or 1)
-        times = []
-        for rep in range(4):                       # one warm-up + three timed repetitions
-            t0 = time.perf_counter()
+        def cpu_step():
             c_oracle.render(cam, sub['means3D'], sub['opacities'], sub['scales'], sub['rotations'], filter_mode=c_oracle.FILTER_MAX,
                             dL_dimage=G.numpy(), dtype=np.float32, want_aux=True, **kw)
-            if rep:
-                times.append(time.perf_counter() - t0)
+        nthreads, tried = pick_cpu_threads(c_oracle, cpu_step)          # includes the warm-up
+        times = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            cpu_step()
+            times.append(time.perf_counter() - t0)
         dt = float(np.median(times))
         line['cpu_baseline'] = {'value': ns / dt, 'unit': 'Gaussians/s', 'cores': c_oracle.num_threads(), 'kind': 'port',
-                                'sample': f'first {ns} of {n} Gaussians, {W}x{H}, fwd+bwd, fp32 C oracle, {c_oracle.num_threads()} OpenMP threads, '
-                                          'median of 3 repetitions after one warm-up', 'seconds': dt, 'seconds_all': times}
+                                'sample': f'first {ns} of {n} Gaussians, {W}x{H}, fwd+bwd, fp32 C oracle, {nthreads} OpenMP threads (fastest of '
+                                          + ', '.join(f'{k}: {v:.2f} s' for k, v in sorted(tried.items())) + '), median of 3 repetitions after warm-up',
+                                'seconds': dt, 'seconds_all': times}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

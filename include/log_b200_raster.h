@@ -77,6 +77,12 @@ typedef struct lgr_view {
                             tile_start + rank without touching an atomic again.  Splats covering more tiles are counted
                             in a second per-tile counter and still take their slots in lgr_forward_render.  NULL: every
                             slot is taken in lgr_forward_render (two atomic passes over the instances). */
+  const int64_t* gather_index_d; /* (n) int64 or NULL (the gather of LoG/model/level_of_gaussian.py:262-296
+                            fused): the n rows of the call are rows gather_index_d[0..n) of the input TABLES (means3D,
+                            scales, rotations, opacities, colors_precomp, shs may hold any number of rows >= max index + 1);
+                            every output -- splat, radii, point_weight, point_count, all gradients -- is compact, row i
+                            belonging to table row gather_index_d[i], which is exactly the gradient layout LoG's
+                            SparseOptimizer consumes (sparse_optimizer.py:163-196).  Not available in band mode. */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */

@@ -472,7 +472,11 @@ int launch_tile_scan(int ntiles, int32_t* tile_start, int32_t* cursor, int32_t* 
 int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len, int num_long, const float* splat,
                         const int32_t* radii, const int32_t* tile_start, int32_t* cursor, uint32_t* inst_key,
                         uint32_t* inst_val, uint32_t* inst_tmp, int32_t* sorted_ids, cudaStream_t st) {
-  if (n == 0 || num_inst == 0) return 0;
+  if (n == 0) return 0;
+  // With no binned instance only the sort is skipped: in band mode the scatter kernel is also the one writer of the
+  // row -> id map and of the zeroed accumulator rows the backward reads (band lists follow the stock rectangle, so they
+  // can be non-empty while nothing reaches alpha >= 1/255), and with band_dsplat set it zeroes the visible rows.
+  if (num_inst == 0 && v.num_owners == 0 && v.band_dsplat == nullptr) return 0;
   const int ntiles = v.gx * (v.row1 - v.row0);
   const unsigned blocks = (unsigned)((n + SCATTER_THREADS - 1) / SCATTER_THREADS);
   {
@@ -480,6 +484,7 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
     bin_scatter_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val);
   }
   LGR_CHECK_LAUNCH();
+  if (num_inst == 0) return 0;
   int id_bits = 8;
   while (id_bits < 32 && (n - 1) >> id_bits) id_bits += 8;
   {      // per device / context and cheap: set on every call (a process may drive several GPUs)

@@ -178,30 +178,49 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
         unsigned mask = __ballot_sync(FULL, (s_bits[e_l] >> warp) & 1u);
         unsigned own_w = 0u;                 // max weight of the splat this lane tested, over this warp's pixels
         while (mask) {
-          const int j = __ffs(mask) - 1;
+          // two hits per iteration: loads and alpha evaluation of both overlap, the transmittance updates are sequential
+          const int jA = __ffs(mask) - 1;
           mask &= mask - 1;
-          const uint32_t rec = s_rec_addr + 48u * (uint32_t)(c0 + j);
-          const float4 r0 = lds_f4(rec);
-          const float2 r1 = lds_f2(rec + 16u);                              // (conic_z, opacity)
-          const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
-          const float power = eval_power2(r0, r1.x, dx, dy);
-          const float alpha = eval_alpha(r1.y, ex2_approx(power));
-          float w = 0.f;
-          if (!done && power <= 0.0f && alpha >= ALPHA_MIN) {
-            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+          const bool two = mask != 0u;
+          const int jB = two ? __ffs(mask) - 1 : jA;
+          mask &= mask - 1;
+          const uint32_t recA = s_rec_addr + 48u * (uint32_t)(c0 + jA), recB = s_rec_addr + 48u * (uint32_t)(c0 + jB);
+          const float4 r0A = lds_f4(recA), r0B = lds_f4(recB);
+          const float2 r1A = lds_f2(recA + 16u), r1B = lds_f2(recB + 16u);                  // (conic_z, opacity)
+          const float dxA = __fsub_rn(r0A.x, pxf), dyA = __fsub_rn(r0A.y, pyf);
+          const float dxB = __fsub_rn(r0B.x, pxf), dyB = __fsub_rn(r0B.y, pyf);
+          const float powerA = eval_power2(r0A, r1A.x, dxA, dyA), powerB = eval_power2(r0B, r1B.x, dxB, dyB);
+          const float alphaA = eval_alpha(r1A.y, ex2_approx(powerA)), alphaB = eval_alpha(r1B.y, ex2_approx(powerB));
+          float wA = 0.f, wB = 0.f;
+          if (!done && powerA <= 0.0f && alphaA >= ALPHA_MIN) {
+            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alphaA));
             if (test_T < T_STOP) done = 1;
             else {
-              w = alpha * T;
-              const float4 r2 = lds_f4(rec + 32u);
-              C0 = fmaf(r2.x, w, C0); C1 = fmaf(r2.y, w, C1); C2 = fmaf(r2.z, w, C2);
+              wA = alphaA * T;
+              const float4 r2 = lds_f4(recA + 32u);
+              C0 = fmaf(r2.x, wA, C0); C1 = fmaf(r2.y, wA, C1); C2 = fmaf(r2.z, wA, C2);
               T = test_T;
-              last = base + c0 + j + 1;
-              if (AUX && w > wmax) { wmax = w; wid = __float_as_int(r2.w); }
+              last = base + c0 + jA + 1;
+              if (AUX && wA > wmax) { wmax = wA; wid = __float_as_int(r2.w); }
+            }
+          }
+          if (two && !done && powerB <= 0.0f && alphaB >= ALPHA_MIN) {
+            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alphaB));
+            if (test_T < T_STOP) done = 1;
+            else {
+              wB = alphaB * T;
+              const float4 r2 = lds_f4(recB + 32u);
+              C0 = fmaf(r2.x, wB, C0); C1 = fmaf(r2.y, wB, C1); C2 = fmaf(r2.z, wB, C2);
+              T = test_T;
+              last = base + c0 + jB + 1;
+              if (AUX && wB > wmax) { wmax = wB; wid = __float_as_int(r2.w); }
             }
           }
           if (AUX) {
-            const unsigned m = __reduce_max_sync(FULL, __float_as_uint(w));   // w >= 0: uint order == float order
-            if (lane == j) own_w = m;
+            const unsigned mA = __reduce_max_sync(FULL, __float_as_uint(wA));   // w >= 0: uint order == float order
+            const unsigned mB = __reduce_max_sync(FULL, __float_as_uint(wB));
+            if (lane == jA) own_w = mA;
+            if (two && lane == jB) own_w = mB;
           }
         }
         if (AUX && own_w) red_shared_max_u32(s_w_addr + 4u * e_l, own_w);
@@ -337,41 +356,67 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           } while (mask == 0u);
         }
         if (!fin) {
-          const int j = __ffs(mask) - 1;
+          // Two hits per iteration: their loads and the evaluation of alpha are independent and overlap; only the
+          // transmittance / colour-behind updates are sequential (A before B).
+          const int jA = __ffs(mask) - 1;
           mask &= mask - 1;
-          const int e = c0 + j;
-          const uint32_t rec = s_rec_addr + 48u * (uint32_t)e;
-          const float4 r0 = lds_f4(rec);
-          const float2 r1 = lds_f2(rec + 16u);                            // (conic_z, opacity)
-          const float dx = __fsub_rn(r0.x, pxf), dy = __fsub_rn(r0.y, pyf);
-          const float power = eval_power2(r0, r1.x, dx, dy);
-          const float G = ex2_approx(power);
-          const float alpha = eval_alpha(r1.y, G);
-          const float om = __fsub_rn(1.0f, alpha);
-          int contrib = 0;
-          float test_T = 0.f;
-          if (!done && power <= 0.0f && alpha >= ALPHA_MIN) {
-            test_T = __fmul_rn(T, om);
-            if (test_T < T_STOP) done = 1; else contrib = 1;
+          const bool two = mask != 0u;
+          const int jB = two ? __ffs(mask) - 1 : jA;
+          mask &= mask - 1;
+          const int eA = c0 + jA, eB = c0 + jB;
+          const uint32_t recA = s_rec_addr + 48u * (uint32_t)eA, recB = s_rec_addr + 48u * (uint32_t)eB;
+          const float4 r0A = lds_f4(recA), r0B = lds_f4(recB);
+          const float2 r1A = lds_f2(recA + 16u), r1B = lds_f2(recB + 16u);                  // (conic_z, opacity)
+          const float dxA = __fsub_rn(r0A.x, pxf), dyA = __fsub_rn(r0A.y, pyf);
+          const float dxB = __fsub_rn(r0B.x, pxf), dyB = __fsub_rn(r0B.y, pyf);
+          const float powerA = eval_power2(r0A, r1A.x, dxA, dyA), powerB = eval_power2(r0B, r1B.x, dxB, dyB);
+          const float GA = ex2_approx(powerA), GB = ex2_approx(powerB);
+          const float alphaA = eval_alpha(r1A.y, GA), alphaB = eval_alpha(r1B.y, GB);
+          const float omA = __fsub_rn(1.0f, alphaA), omB = __fsub_rn(1.0f, alphaB);
+          bool cA = false, cB = false;
+          const float TA = T;
+          if (!done && powerA <= 0.0f && alphaA >= ALPHA_MIN) {
+            const float tt = __fmul_rn(T, omA);
+            if (tt < T_STOP) done = 1; else { cA = true; T = tt; }
           }
-          if (__any_sync(FULL, contrib)) {
+          const float TB = T;
+          if (two && !done && powerB <= 0.0f && alphaB >= ALPHA_MIN) {
+            const float tt = __fmul_rn(T, omB);
+            if (tt < T_STOP) done = 1; else { cB = true; T = tt; }
+          }
+          const bool anyA = __any_sync(FULL, cA), anyB = __any_sync(FULL, cB);
+          if (anyA) {
             float wG = 0.f, w = 0.f;
-            if (contrib) {
-              const float4 r2 = lds_f4(rec + 32u);
-              w = alpha * T;
+            if (cA) {
+              const float4 r2 = lds_f4(recA + 32u);
+              w = alphaA * TA;
               const float cdot = r2.x * dp0 + r2.y * dp1 + r2.z * dp2;
-              Rd = fmaf(-cdot, w, Rd);                          // what is behind j (+ bg T_final), dotted with dL/dC
-              const float dL_dalpha = cdot * T - Rd * rcp_approx(om);
-              T = test_T;
-              wG = r1.y * dL_dalpha * G;                        // dL/dG * G   (the 0.99 clamp is straight-through)
+              Rd = fmaf(-cdot, w, Rd);                          // what is behind the splat (+ bg T_final), dotted with dL/dC
+              const float dL_dalpha = cdot * TA - Rd * rcp_approx(omA);
+              wG = r1A.y * dL_dalpha * GA;                      // dL/dG * G   (the 0.99 clamp is straight-through)
             }
             const uint32_t row = xlane_addr + (uint32_t)pend * (XROW * 4);
             sts_f32(row, wG); sts_f32(row + HITS * XROW * 4, w);
-            if (lane == pend) my_e = e;
+            if (lane == pend) my_e = eA;
+            pend++;
+          }
+          if (anyB) {
+            float wG = 0.f, w = 0.f;
+            if (cB) {
+              const float4 r2 = lds_f4(recB + 32u);
+              w = alphaB * TB;
+              const float cdot = r2.x * dp0 + r2.y * dp1 + r2.z * dp2;
+              Rd = fmaf(-cdot, w, Rd);
+              const float dL_dalpha = cdot * TB - Rd * rcp_approx(omB);
+              wG = r1B.y * dL_dalpha * GB;
+            }
+            const uint32_t row = xlane_addr + (uint32_t)pend * (XROW * 4);
+            sts_f32(row, wG); sts_f32(row + HITS * XROW * 4, w);
+            if (lane == pend) my_e = eB;
             pend++;
           }
         }
-        if (pend == HITS || (fin && pend > 0)) {
+        if (pend >= HITS - 1 || (fin && pend > 0)) {      // fewer than two free rows, or the batch is over
           // ---- contract the pending hits on the tensor cores ----
           // A (16 x 32 pixels): rows 0..7 = wG of the 8 hits, rows 8..15 = w of the same hits; one ldmatrix.x4 per k-step
           // delivers (a0, a1, a2, a3) in place.  B (32 pixels x 8): the weights -- Bm moments (6 columns, exact), Bc the

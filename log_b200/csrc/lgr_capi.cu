@@ -45,6 +45,7 @@ static bool view_ok(const lgr_view* v) {
   const int gy = (v->image_height + TILE - 1) / TILE;
   if (v->tile_row_end > gy) return false;
   if (v->num_owners < 0 || (v->num_owners > 0 && (!v->band_ids_d || !v->band_count_d || !v->band_blk_d || !v->band_rows_d))) return false;
+  if (v->gather_index_d && v->num_owners > 0) return false;      // the gather-fused call has no band mode
   return true;
 }
 

@@ -120,11 +120,13 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     work = threadIdx.x < total;
     i = work ? (int64_t)blockIdx.x * PROJ_THREADS + sSurv[threadIdx.x] : n;
   }
+  // gather-fused call (lgr_view.gather_index_d): row i of every output is Gaussian gather[i] of the input tables
+  const int64_t src = (v.gather && work) ? v.gather[i] : i;
   if (work) {
     float p[3], s[3], R[9], Sg[9];
-    load3(means, i, p);
-    load3(scales, i, s);
-    float4 q = ldg4(rots + 4 * i);
+    load3(means, src, p);
+    load3(scales, src, s);
+    float4 q = ldg4(rots + 4 * src);
     if (v.raw_params) {
       float inv;
 #pragma unroll
@@ -155,7 +157,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
         stock_tiles = (unsigned long long)((x1 - x0) * (max(0, min(y1, v.row1) - max(y0, v.row0))));
         in_band = stock_tiles > 0;      // band lists follow the stock rectangle so that owners see every radius > 0
         const float idet = 1.0f / det;
-        const float o = v.raw_params ? act_sigmoid(__ldg(opac + i)) : __ldg(opac + i);
+        const float o = v.raw_params ? act_sigmoid(__ldg(opac + src)) : __ldg(opac + src);
         // conservative half extents of {alpha >= 1/255}:  d^T Conic d <= 2 ln(255 o)  =>  |dx| <= sqrt(q a)
         float hx = 0.f, hy = 0.f;
         bool reach = o * 255.0f >= 1.0f;
@@ -171,7 +173,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
           float B[16];
           sh_basis(v.sh_degree, d[0] * inv, d[1] * inv, d[2] * inv, B);
           const int nb = (v.sh_degree + 1) * (v.sh_degree + 1);
-          const float* sh = shs + (int64_t)i * v.sh_K * 3;
+          const float* sh = shs + src * v.sh_K * 3;
           rgb[0] = rgb[1] = rgb[2] = 0.5f;
           for (int k = 0; k < nb; k++) {
             rgb[0] += B[k] * __ldg(sh + 3 * k); rgb[1] += B[k] * __ldg(sh + 3 * k + 1); rgb[2] += B[k] * __ldg(sh + 3 * k + 2);
@@ -181,7 +183,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
           for (int ch = 0; ch < 3; ch++) if (rgb[ch] < 0.0f) { cl |= (uint8_t)(1u << ch); rgb[ch] = 0.0f; }
           clamped[i] = cl;
         } else {
-          load3(colors, i, rgb);
+          load3(colors, src, rgb);
           if (v.raw_params) {      // SH2RGB (sh_utils.py:72-73)
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) rgb[ch] = fmaf(SH_C0, rgb[ch], 0.5f);
@@ -192,7 +194,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
             float B[16];
             sh_basis(v.sh_degree, d[0] * inv, d[1] * inv, d[2] * inv, B);
             const int nb = (v.sh_degree + 1) * (v.sh_degree + 1);
-            const float* sh = shs + (int64_t)i * v.sh_K * 3;
+            const float* sh = shs + src * v.sh_K * 3;
             for (int k = 1; k < nb; k++) {
               rgb[0] += B[k] * __ldg(sh + 3 * (k - 1)); rgb[1] += B[k] * __ldg(sh + 3 * (k - 1) + 1);
               rgb[2] += B[k] * __ldg(sh + 3 * (k - 1) + 2);
@@ -283,15 +285,16 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dop = 0.f, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
   float drgb[3] = {0.f, 0.f, 0.f};
   const bool live = active && radii[i] > 0;
+  const int64_t src = (v.gather && live) ? v.gather[i] : i;      // gather-fused call: inputs come from row gather[i] of the tables
   const int K = v.sh_K;
   if (live) {
     const float4 g0 = ldg4(dsplat + i * LGR_GRAD_FLOATS);       // d/dpx d/dpy d/dconx d/dcony
     const float4 g1 = ldg4(dsplat + i * LGR_GRAD_FLOATS + 4);   // d/dconz d/dop d/dr d/dg
     const float4 g2 = ldg4(dsplat + i * LGR_GRAD_FLOATS + 8);   // d/db
     float p[3], s0[3], s[3], R[9], Sg[9];
-    load3(means, i, p);
-    load3(scales, i, s0);
-    float4 q = ldg4(rots + 4 * i);
+    load3(means, src, p);
+    load3(scales, src, s0);
+    float4 q = ldg4(rots + 4 * src);
     float q_inv = 1.0f;
     if (v.raw_params) {
 #pragma unroll
@@ -387,7 +390,7 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
       float B[16];
       sh_basis(v.sh_degree, x, y, z, B);
       const int nb = (v.sh_degree + 1) * (v.sh_degree + 1);
-      const float* sh = shs + (int64_t)i * K * 3;
+      const float* sh = shs + src * K * 3;
       float* dsh = dshs + (int64_t)i * K * 3;
       // c_k = sum_ch shs[k][ch] * drgb[ch]
       float ck[16];
@@ -426,13 +429,13 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   }
   if (v.raw_params && live) {      // chain rule through LoG's activations (activation.py:36-44)
     float s_act[3];
-    load3(scales, i, s_act);
+    load3(scales, src, s_act);
 #pragma unroll
     for (int k = 0; k < 3; k++) dsc[k] *= expf(s_act[k]);                       // d exp(x) = exp(x)
-    const float o = act_sigmoid(__ldg(opac + i));
+    const float o = act_sigmoid(__ldg(opac + src));
     dop *= o * (1.0f - o);                                                        // d sigmoid = o (1 - o)
     float inv;
-    const float4 qn = act_normalize(ldg4(rots + 4 * i), inv);
+    const float4 qn = act_normalize(ldg4(rots + 4 * src), inv);
     const float dot = qn.x * dq[0] + qn.y * dq[1] + qn.z * dq[2] + qn.w * dq[3];
     dq[0] = (dq[0] - qn.x * dot) * inv; dq[1] = (dq[1] - qn.y * dot) * inv;       // d (r/|r|) = (I - q q^T) / |r|
     dq[2] = (dq[2] - qn.z * dot) * inv; dq[3] = (dq[3] - qn.w * dot) * inv;
@@ -441,7 +444,7 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
       int nb = 1;
       if (v.sh_degree > 0) {
         float p[3];
-        load3(means, i, p);
+        load3(means, src, p);
         const float d[3] = {p[0] - sCam[0], p[1] - sCam[1], p[2] - sCam[2]};
         const float inv_d = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
         float B[16];

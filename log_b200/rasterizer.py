@@ -67,13 +67,13 @@ def _f32c(t: Optional[torch.Tensor], name: str, device=None):
     return t
 
 
-def _stream():
-    return _capi.current_stream()
+def _stream(device=None):
+    return _capi.current_stream(device)
 
 
 def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep,
                num_owners=0, band_ids=None, band_count=None, band_blk=None, band_rows=None, band_dsplat=None,
-               raw_params=False, tile_rank=None):
+               raw_params=False, tile_rank=None, gather_index=None):
     dev = s.viewmatrix.device
     vm, pm = _f32c(s.viewmatrix, 'viewmatrix'), _f32c(s.projmatrix, 'projmatrix', dev)
     bg = _f32c(s.bg, 'bg', dev)
@@ -94,6 +94,7 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
     v.band_rows_d = band_rows.data_ptr() if band_rows is not None else None
     v.band_dsplat_d = band_dsplat.data_ptr() if band_dsplat is not None else None
     v.tile_rank_d = tile_rank.data_ptr() if tile_rank is not None else None
+    v.gather_index_d = gather_index.data_ptr() if gather_index is not None else None
     v.viewmatrix_d, v.projmatrix_d = vm.data_ptr(), pm.data_ptr()
     v.campos_d = cp.data_ptr() if cp is not None else None
     v.bg_d = bg.data_ptr()
@@ -108,7 +109,7 @@ class RasterState:
 
 
 def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_precomp, shs, filter_mode, want_aux,
-                      tile_rows=None, num_owners=0, raw_params=False):
+                      tile_rows=None, num_owners=0, raw_params=False, prezero_dsplat=None, gather_index=None):
     """Run the forward through the C ABI.  Returns (image, radii, pid, pwp, point_weight, state).
     num_owners > 0 (multi-GPU band mode, see log_b200/sharded.py): also compact the ids of the Gaussians reaching the
     band `tile_rows`, grouped by owner rank; the backward then returns packed gradient rows instead of dense tensors.
@@ -118,11 +119,27 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     activation is fused: SH2RGB(dc) + eval_sh_wobase(dir, shs, settings.sh_degree), no clamp, direction detached."""
     lib = _capi.load()
     dev = means3D.device
+    for name, t in (('opacities', opacities), ('scales', scales), ('rotations', rotations), ('colors_precomp', colors_precomp),
+                    ('shs', shs), ('viewmatrix', settings.viewmatrix), ('projmatrix', settings.projmatrix), ('bg', settings.bg)):
+        if t is not None and t.device != dev:
+            raise _capi.LgrError(f'{name} is on {t.device}, means3D on {dev}: all inputs of a call must share one device')
     n = int(means3D.shape[0])
     keep = []
+    if gather_index is not None:
+        if gather_index.dtype != torch.int64 or gather_index.device != dev or gather_index.dim() != 1:
+            raise _capi.LgrError('gather_index must be a 1-D int64 tensor on the inputs\' device')
+        if num_owners > 0:
+            raise _capi.LgrError('gather_index is not available in band mode')
+        gather_index = gather_index.contiguous()
+        keep.append(gather_index)
+        n = int(gather_index.shape[0])
     K = 0 if shs is None else int(shs.shape[1])
     band_ids = band_count = band_blk = band_rows = band_dsplat = None
-    if num_owners == 0 and PREZERO_DSPLAT and torch.is_grad_enabled():
+    # prezero_dsplat: decided by the caller (GaussianRasterizer.forward looks at requires_grad BEFORE entering the autograd
+    # function, where grad mode is always off); None = direct callers: follow the LGR_PREZERO_DSPLAT knob
+    if prezero_dsplat is None:
+        prezero_dsplat = PREZERO_DSPLAT and torch.is_grad_enabled()
+    if num_owners == 0 and prezero_dsplat:
         # experiment (LGR_PREZERO_DSPLAT=1): the scatter kernel zeroes the accumulator rows the backward will read, instead of a
         # 48 N-byte memset at the start of the backward
         band_dsplat = torch.empty((max(n, 1), _capi.LGR_GRAD_FLOATS), dtype=torch.float32, device=dev)
@@ -136,7 +153,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     tile_rank = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev) if RANKED_BIN else None
     keep.append(tile_rank)
     view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep, num_owners, band_ids, band_count, band_blk, band_rows, band_dsplat,
-                      raw_params, tile_rank)
+                      raw_params, tile_rank, gather_index)
     H, W = view.image_height, view.image_width
     gx, gy = (W + 15) // 16, (H + 15) // 16
     rows = gy if tile_rows is None else int(tile_rows[1]) - int(tile_rows[0])
@@ -149,7 +166,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     tile_start = torch.empty((ntiles + 1,), **i32)
     tile_cursor = torch.empty((_capi.LGR_TILE_SCRATCH_INTS * max(ntiles, 1),), **i32)
     meta = torch.empty((_capi.LGR_META_INTS,), **i32)
-    st = _stream()
+    st = _stream(dev)
     _capi.check(lib.lgr_forward_project(ctypes.byref(view), n, _ptr(means3D), _ptr(opacities), _ptr(scales),
                                         _ptr(rotations), _ptr(colors_precomp), _ptr(shs), _ptr(splat), _ptr(radii),
                                         _ptr(clamped), _ptr(tile_start), _ptr(tile_cursor), _ptr(meta), st),
@@ -208,14 +225,14 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
                                          _ptr(scales), _ptr(rotations), _ptr(colors_precomp), None, _ptr(state.splat),
                                          _ptr(state.radii), None, _ptr(state.tile_start), _ptr(state.sorted_ids),
                                          _ptr(state.image), _ptr(g), _ptr(dsplat), None, None, None, None, None, None, None,
-                                         None, ctypes.c_void_p(peer_stage.data_ptr()), int(my_rank), m_rows, _stream()), 'lgr_backward')
+                                         None, ctypes.c_void_p(peer_stage.data_ptr()), int(my_rank), m_rows, _stream(dev)), 'lgr_backward')
             return None
         rows = torch.empty((m_rows, _capi.LGR_ROW_FLOATS), **f32)
         _capi.check(lib.lgr_backward(ctypes.byref(state.view), n, state.num_instances, _ptr(means3D), _ptr(opacities),
                                      _ptr(scales), _ptr(rotations), _ptr(colors_precomp), None, _ptr(state.splat),
                                      _ptr(state.radii), None, _ptr(state.tile_start), _ptr(state.sorted_ids),
                                      _ptr(state.image), _ptr(g), _ptr(dsplat), None, None, None, None, None, None, None,
-                                     ctypes.c_void_p(rows.data_ptr()) if rows.numel() else _ptr(dsplat), None, 0, m_rows, _stream()),
+                                     ctypes.c_void_p(rows.data_ptr()) if rows.numel() else _ptr(dsplat), None, 0, m_rows, _stream(dev)),
                     'lgr_backward')
         return rows
     dmeans3D = torch.empty((n, 3), **f32)
@@ -224,13 +241,13 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
     dscales = torch.empty((n, 3), **f32)
     drot = torch.empty((n, 4), **f32)
     dcolors = torch.empty((n, 3), **f32) if colors_precomp is not None else None
-    dshs = torch.empty_like(shs) if shs is not None else None
+    dshs = torch.empty((n,) + tuple(shs.shape[1:]), **f32) if shs is not None else None
     _capi.check(lib.lgr_backward(ctypes.byref(state.view), n, state.num_instances, _ptr(means3D), _ptr(opacities),
                                  _ptr(scales), _ptr(rotations), _ptr(colors_precomp), _ptr(shs), _ptr(state.splat),
                                  _ptr(state.radii), _ptr(state.clamped), _ptr(state.tile_start), _ptr(state.sorted_ids),
                                  _ptr(state.image), _ptr(g), _ptr(dsplat), _ptr(dmeans3D),
                                  _ptr(dmeans2D), _ptr(dopac), _ptr(dscales), _ptr(drot), _ptr(dcolors), _ptr(dshs), None,
-                                 None, 0, 0, _stream()), 'lgr_backward')
+                                 None, 0, 0, _stream(dev)), 'lgr_backward')
     return dmeans3D, dmeans2D, dopac, dscales, drot, dcolors, dshs
 
 
@@ -247,17 +264,16 @@ def point_id_count(point_count: torch.Tensor):
     cnt = torch.empty((n,), **i32)
     num = torch.empty((1,), **i32)
     _capi.check(lib.lgr_point_compact(n, _ptr(point_count), _ptr(scratch), _ptr(ids), _ptr(cnt),
-                                      ctypes.c_void_p(num.data_ptr()), _stream()), 'lgr_point_compact')
+                                      ctypes.c_void_p(num.data_ptr()), _stream(dev)), 'lgr_point_compact')
     k = int(num.item())
     return ids[:k], cnt[:k]
 
 
 class _RasterizeGaussians(torch.autograd.Function):
-    last_point_count = None
 
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, colors_precomp, shs, scales, rotations, settings, filter_mode, want_aux,
-                tile_rows, raw_params=False):
+                tile_rows, raw_params=False, prezero_dsplat=False):
         dev = means3D.device
         m = _f32c(means3D, 'means3D')
         o = _f32c(opacities, 'opacities', dev)
@@ -266,17 +282,16 @@ class _RasterizeGaussians(torch.autograd.Function):
         c = _f32c(colors_precomp, 'colors_precomp', dev)
         sh = _f32c(shs, 'shs', dev)
         image, radii, pid, pwp, pw, state = rasterize_forward(settings, m, o, sc, r, c, sh, filter_mode, want_aux, tile_rows,
-                                                              raw_params=raw_params)
+                                                              raw_params=raw_params, prezero_dsplat=prezero_dsplat)
         state.image = None          # the backward re-reads the rendered image: saved below so autograd guards it
-        _RasterizeGaussians.last_point_count = state.point_count
         ctx.state = state
         ctx.opacity_shape = opacities.shape
         ctx.save_for_backward(m, o, sc, r, c if c is not None else torch.empty(0, device=dev),
                               sh if sh is not None else torch.empty(0, device=dev), image)
         ctx.has_color, ctx.has_sh = c is not None, sh is not None
-        if want_aux:
-            ctx.mark_non_differentiable(radii, pid, pwp, pw)
-            return image, radii, pid, pwp, pw
+        if want_aux:      # the winner histogram travels as a sixth (non-differentiable) output: no process-global state
+            ctx.mark_non_differentiable(radii, pid, pwp, pw, state.point_count)
+            return image, radii, pid, pwp, pw, state.point_count
         ctx.mark_non_differentiable(radii)
         return image, radii
 
@@ -287,7 +302,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         sh = sh if ctx.has_sh else None
         ctx.state.image = image
         dm3, dm2, dop, dsc, drot, dcol, dsh = rasterize_backward(ctx.state, grad_image, m, o, sc, r, c, sh)
-        return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None, None
+        return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None, None, None
 
 
 class GaussianRasterizer(nn.Module):
@@ -329,11 +344,16 @@ class GaussianRasterizer(nn.Module):
         if raw_params and shs is not None and colors_precomp is None:
             raise NotImplementedError('raw_params with SH: pass the raw DC colours as colors_precomp and the REST coefficients '
                                       '(LoG layout, activation.py:27-34) as shs')
+        # will a backward follow?  (decided here: inside autograd.Function.forward grad mode is always off)
+        needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in
+                                                     (means3D, means2D, opacities, colors_precomp, shs, scales, rotations))
         out = _RasterizeGaussians.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
-                                        self.raster_settings, filter_mode, fork, self.tile_rows, raw_params)
-        # fork flavour: per-Gaussian histogram of the per-pixel winners (feeds point_id_count())
-        self.last_point_count = _RasterizeGaussians.last_point_count if fork else None
-        return out
+                                        self.raster_settings, filter_mode, fork, self.tile_rows, raw_params,
+                                        PREZERO_DSPLAT and needs_grad)
+        # fork flavour: per-Gaussian histogram of the per-pixel winners (feeds point_id_count()); kept on THIS rasterizer
+        # object (LoG builds one per view, renderer.py:77), the 5-tuple of the reference is what is returned
+        self.last_point_count = out[5] if fork else None
+        return out[:5] if fork else out
 
 
 class StockGaussianRasterizer(GaussianRasterizer):
@@ -352,5 +372,5 @@ def compute_radius(means3D, scales, rotations, projmatrix, viewmatrix, focal_x, 
     n = int(m.shape[0])
     out = torch.empty((n,), dtype=torch.float32, device=dev)
     _capi.check(lib.lgr_compute_radius(n, _ptr(m), _ptr(s), _ptr(r), _ptr(P), _ptr(V), float(focal_x), float(focal_y),
-                                       float(tan_fovx), float(tan_fovy), _ptr(out), _stream()), 'lgr_compute_radius')
+                                       float(tan_fovx), float(tan_fovy), _ptr(out), _stream(dev)), 'lgr_compute_radius')
     return out

@@ -36,7 +36,7 @@ def emulated_backend(monkeypatch):
     from log_b200 import _capi
     lib = _capi.bind(ctypes.CDLL(build_emu.build()))
     monkeypatch.setattr(_capi, '_lib', lib)
-    monkeypatch.setattr(_capi, 'current_stream', lambda: None)
+    monkeypatch.setattr(_capi, 'current_stream', lambda device=None: None)
     monkeypatch.setattr(_capi, 'require_cuda', lambda t, name: None)
     monkeypatch.setattr(util, 'DEVICE', ['cpu'])
     return lib

@@ -55,6 +55,15 @@ def test_band_mode_rows_and_fused_push(emulated_backend, world):
     gp.test_fused_push_route_emulated_on_one_gpu(True, world, size=(64, 80, 900))
 
 
+def test_band_mode_with_no_binned_instance(emulated_backend):
+    gp.test_band_mode_with_no_binned_instance(True)
+
+
+@pytest.mark.parametrize('deg', [0, 2])
+def test_gather_fused_render(emulated_backend, deg):
+    gp.test_gather_fused_render_equals_log_get_all(True, deg, size=(64, 48, 500, 300))
+
+
 def test_fused_activations(emulated_backend):
     gp.test_fused_activations_match_torch_activations(True, size=(64, 48, 400))
 

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import c_oracle, torch_dense as O
-from util import f32_camera, rel, run_gpu
+from util import f32_camera, record_parity, rel, run_gpu
 
 pytestmark = pytest.mark.gpu
 W, H = 1920, 1080
@@ -19,8 +19,14 @@ def f32_scene(sc):
     return {k: v.to(torch.float32).to(torch.float64) for k, v in sc.items()}
 
 
-def tol(k, ref, ref32):
-    return max(1e-4, 4.0 * rel(ref32[k], ref[k]))
+TOL = 1e-4      # north_star's bound, enforced as is: every full-size case runs with a low-pass filter on
+
+
+def compare(case, got, ref, ref32, keys):
+    errs = {k: (rel(got[k], ref[k]), None if ref32 is None else rel(ref32[k], ref[k])) for k in keys}
+    record_parity(case, errs, TOL, True)
+    for k, (e, _) in errs.items():
+        assert e < TOL, (case, k, e)
 
 
 def test_config1_100k_sh3_direct_parity(built):
@@ -32,8 +38,7 @@ def test_config1_100k_sh3_direct_parity(built):
     ref = c_oracle.render(cam, sc['means3D'], sc['opacities'], sc['scales'], sc['rotations'], dtype=np.float64, **kw)
     ref32 = c_oracle.render(cam, sc['means3D'], sc['opacities'], sc['scales'], sc['rotations'], dtype=np.float32, **kw)
     got = run_gpu(cam, sc, G, flavour='stock', sh_degree=3)
-    for k in ['image', 'dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations', 'dshs']:
-        assert rel(got[k], ref[k]) < tol(k, ref, ref32), (k, rel(got[k], ref[k]), tol(k, ref, ref32))
+    compare('config1[100k,1080p,sh3,stock]', got, ref, ref32, ['image', 'dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations', 'dshs'])
     rg = got['radii'].cpu().numpy()
     assert (rg != ref['radii']).sum() <= 20 and np.abs(rg - ref['radii']).max() <= 1
 
@@ -53,11 +58,26 @@ def test_config3_1m_subset_direct_parity(built, scene10m):
     ref = c_oracle.render(cam, sub['means3D'], sub['opacities'], sub['scales'], sub['rotations'], dtype=np.float64, **kw)
     ref32 = c_oracle.render(cam, sub['means3D'], sub['opacities'], sub['scales'], sub['rotations'], dtype=np.float32, **kw)
     got = run_gpu(cam, sub, G)
-    for k in ['image', 'dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations', 'dcolors', 'point_weight',
-              'point_weight_pixel']:
-        assert rel(got[k], ref[k]) < tol(k, ref, ref32), (k, rel(got[k], ref[k]), tol(k, ref, ref32))
+    compare('config3-subset[1M of 10M,1080p,fork]', got, ref, ref32, ['image', 'dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations',
+                                                                     'dcolors', 'point_weight', 'point_weight_pixel'])
     rg = got['radii'].cpu().numpy()
     assert (rg != ref['radii']).sum() <= 200 and np.abs(rg - ref['radii']).max() <= 1
+    pid = got['point_id_pixel'].cpu().numpy()
+    assert (pid != ref['point_id_pixel']).mean() < 1e-3
+
+
+def test_config3_10m_direct_parity(built, scene10m):
+    """The metric's own configuration (10 M Gaussians, 1080p, fork flavour, precomputed colour) against the fp64 C oracle,
+    directly: image, all six gradient tensors and the aux outputs, north_star's 1e-4 bound.  The oracle needs ~1 minute on
+    the box's host cores for this size; it runs once."""
+    cam, sc, G = scene10m
+    kw = dict(colors_precomp=sc['colors'], filter_mode=c_oracle.FILTER_MAX, dL_dimage=G.to(torch.float64))
+    ref = c_oracle.render(cam, sc['means3D'], sc['opacities'], sc['scales'], sc['rotations'], dtype=np.float64, **kw)
+    got = run_gpu(cam, sc, G)
+    compare('config3[10M,1080p,fork]', got, ref, None, ['image', 'dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations', 'dcolors',
+                                                       'point_weight', 'point_weight_pixel'])
+    rg = got['radii'].cpu().numpy()
+    assert (rg != ref['radii']).sum() <= 2000 and np.abs(rg - ref['radii']).max() <= 1
     pid = got['point_id_pixel'].cpu().numpy()
     assert (pid != ref['point_id_pixel']).mean() < 1e-3
 

@@ -37,19 +37,32 @@ def oracle(cam, sc, G, fm, deg, dtype=np.float64):
                            dL_dimage=G, dtype=dtype, **kw)
 
 
-def check_all(got, ref, deg, fork, n_pix, ref32=None):
+def check_all(got, ref, deg, fork, n_pix, ref32=None, case=None, filter_on=True):
+    """north_star's bound is 1e-4 relative (norm-wise) for RGB and every gradient.  With a low-pass filter on (every
+    training call: stock `+= 0.3`, fork `max(., 0.3)`) that bound is enforced as is.  Only with the filter OFF (the fork's
+    eval-only use_filter=False, LoG/render/renderer.py:151-152, where no backward runs in LoG) is the bound widened to
+    4 x what the fp32 build of the oracle itself achieves against its fp64 build: sub-pixel splats make the conic
+    ill-conditioned for ANY fp32 implementation.  Every achieved error is recorded (util.record_parity)."""
     def tol(k):
-        return TOL if ref32 is None else max(TOL, 4.0 * rel(ref32[k], ref[k]))
-    assert rel(got['image'], ref['image']) < tol('image')
+        if filter_on or ref32 is None:
+            return TOL
+        return max(TOL, 4.0 * rel(ref32[k], ref[k]))
+    errs = {}
+    keys = ['image', 'dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations'] + (['dcolors'] if deg == 0 else ['dshs'])
+    if fork:
+        keys += ['point_weight', 'point_weight_pixel']
+    for k in keys:
+        if k in got:
+            errs[k] = (rel(got[k], ref[k]), None if ref32 is None else rel(ref32[k], ref[k]))
+    if case is not None:
+        from util import record_parity
+        record_parity(case, errs, TOL, filter_on)
     rg, rr = np.asarray(got['radii'].cpu().numpy() if hasattr(got['radii'], 'cpu') else got['radii']), ref['radii']
     assert (rg != rr).sum() <= max(2, int(2e-4 * rr.size)), ((rg != rr).sum(), rr.size)
     assert np.abs(rg - rr).max() <= 1
-    for k in ['dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations'] + (['dcolors'] if deg == 0 else ['dshs']):
-        if k in got:
-            assert rel(got[k], ref[k]) < tol(k), (k, rel(got[k], ref[k]), tol(k))
+    for k, (e, _) in errs.items():
+        assert e < tol(k), (k, e, tol(k))
     if fork:
-        assert rel(got['point_weight'], ref['point_weight']) < tol('point_weight')
-        assert rel(got['point_weight_pixel'], ref['point_weight_pixel']) < tol('point_weight_pixel')
         pg = got['point_id_pixel']
         pg, pr = (pg.cpu().numpy() if hasattr(pg, 'cpu') else pg), ref['point_id_pixel']
         bad = pg != pr
@@ -123,7 +136,8 @@ def test_forward_backward_parity(built, W, H, n, r, deg, flavour, use_filter, ro
     ref = oracle(cam, sc, G, fm, deg)
     ref32 = oracle(cam, sc, G, fm, deg, dtype=np.float32)
     got = run_gpu(cam, sc, G, flavour=flavour, use_filter=use_filter, sh_degree=deg)
-    check_all(got, ref, deg, flavour == 'fork', H * W, ref32)
+    check_all(got, ref, deg, flavour == 'fork', H * W, ref32, case=f'parity[{W}x{H},n={n},sigma={r},sh={deg},{flavour},filter={use_filter},rot={rot}]',
+              filter_on=use_filter)
 
 
 def test_scale_modifier_and_background(built, size=(128, 80, 800)):
@@ -306,6 +320,33 @@ def test_band_mode_rows_reproduce_dense_gradients(built, world, size=(208, 144, 
         assert rel(a, b) < 5e-5
 
 
+@pytest.mark.gpu
+def test_band_mode_with_no_binned_instance(built, size=(64, 48, 300)):
+    """Band mode when the band lists are non-empty (they follow the stock rectangle) but no splat reaches alpha >= 1/255
+    anywhere (D == 0): the scatter kernel must still write the row -> id map and zero the listed accumulator rows, so the
+    backward returns all-zero gradient rows carrying valid ids (round-1 advisor finding: it read an unwritten map)."""
+    from log_b200 import rasterize_backward, rasterize_forward, sharded
+    from log_b200._capi import LGR_FILTER_MAX
+    from util import settings_from_camera
+    W, H, n = size
+    cam = f32_camera(O.make_camera(W, H, bg=(0.2, 0.3, 0.4)))
+    sc = f32_scene(O.make_scene(n, W, H, 5.0, seed=5))
+    sc['opacities'][:] = 0.001                      # below 1/255 everywhere
+    dev = device()
+    s = settings_from_camera(cam, dev)
+    t = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in sc.items()}
+    Gd = O.make_cotangent(3, H, W).to(device=dev, dtype=torch.float32)
+    op = t['opacities'].reshape(-1)
+    for band in sharded.tile_row_partition(H, 2):
+        img, radii, pid, pwp, pw, st = rasterize_forward(s, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None,
+                                                         LGR_FILTER_MAX, True, band, num_owners=2)
+        assert st.num_instances == 0 and sum(st.band_counts_host) > 0
+        rows = rasterize_backward(st, Gd, t['means3D'], op, t['scales'], t['rotations'], t['colors'], None)
+        ids = rows[:, 17].contiguous().view(torch.int32)
+        assert int(ids.min()) >= 0 and int(ids.max()) < n
+        assert float(rows[:, :17].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize('W,H,n,r', [(200, 120, 3000, 6.0), (64, 64, 0, 3.0), (333, 211, 20000, 2.0)])
 def test_point_id_count_equals_torch_unique(built, W, H, n, r):
     """(point_id, point_count) from the blend kernel's winner histogram equals what LoG computes with
@@ -417,7 +458,68 @@ def test_fused_activations_match_torch_activations(built, size=(176, 112, 2500))
     (out['image'] * G.to(torch.float64)).sum().backward()
     assert rel(img_f, out['image'].detach()) < 1e-4
     for k in g_t:
-        assert rel(g_f[k], leaves[k].grad) < 2e-4, (k, rel(g_f[k], leaves[k].grad))
+        assert rel(g_f[k], leaves[k].grad) < TOL, (k, rel(g_f[k], leaves[k].grad))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('deg', [0, 2])
+def test_gather_fused_render_equals_log_get_all(built, deg, size=(160, 96, 3000, 1700)):
+    """SURVEY 8(f) row 3, the gather half: `render_gathered` reads LoG's raw parameter TABLES through an index and applies
+    the activations in the projection kernel.  It must equal what LoG does (level_of_gaussian.py:262-296,
+    activation.py:27-44): gathered `nn.Parameter` copies -> torch activations (+ eval_sh_wobase) -> the ordinary rasteriser
+    call -> autograd; image, aux outputs, the `screenspace_points` gradient and the COMPACT raw-parameter gradients (the
+    rows SparseOptimizer reads) are compared.  The index is unsorted and the tables hold rows the view never touches."""
+    from log_b200 import GaussianRasterizer
+    from log_b200.gathered import render_gathered
+    from util import settings_from_camera
+    W, H, n_table, m = size
+    K = 15
+    cam = f32_camera(O.make_camera(W, H, bg=(0.3, 0.2, 0.1), sh_degree=deg, R=[[0.98, 0.0, 0.199], [0, 1, 0], [-0.199, 0, 0.98]],
+                                   T=[0.1, -0.05, 0.3]))
+    sc = f32_scene(O.make_scene(n_table, W, H, 4.0, seed=57, sh_degree=3))
+    g = torch.Generator().manual_seed(3)
+    dev = device()
+    tables = {'xyz': sc['means3D'], 'scaling': torch.log(sc['scales']), 'opacity': torch.logit(sc['opacities'].clamp(0.02, 0.98)).reshape(-1, 1),
+              'rotation': sc['rotations'] * (0.5 + torch.rand(n_table, 1, generator=g, dtype=torch.float64) * 2.0),
+              'colors': (sc['colors'] - 0.5) / O.C0, 'shs': sc['shs'][:, 1:1 + K].contiguous()}
+    tables = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in tables.items()}
+    index = torch.randperm(n_table, generator=g)[:m].to(dev)
+    G = O.make_cotangent(3, H, W).to(device=dev, dtype=torch.float32)
+    settings = settings_from_camera(cam, dev)
+    # LoG's path
+    ret = {k: torch.nn.Parameter(v[index]) for k, v in tables.items()}
+    colors = ret['colors'] * O.C0 + 0.5
+    if deg > 0:
+        d = ret['xyz'].detach() - settings.campos[None]
+        d = d / torch.norm(d, dim=-1, keepdim=True)
+        colors = colors + _eval_sh_wobase(deg, ret['shs'], d)
+    m2d_t = torch.zeros(m, 3, device=dev, requires_grad=True)
+    out_t = GaussianRasterizer(settings)(means3D=ret['xyz'], means2D=m2d_t, shs=None, colors_precomp=colors, opacities=torch.sigmoid(ret['opacity']),
+                                         scales=torch.exp(ret['scaling']), rotations=torch.nn.functional.normalize(ret['rotation']),
+                                         cov3D_precomp=None)
+    (out_t[0] * G).sum().backward()
+    # fused
+    m2d_f = torch.zeros(m, 3, device=dev, requires_grad=True)
+    use = dict(tables) if deg > 0 else {k: v for k, v in tables.items() if k != 'shs'}
+    out_f, pcount, params = render_gathered(settings, use, index, m2d_f)
+    (out_f[0] * G).sum().backward()
+    assert rel(out_f[0], out_t[0]) < 1e-5
+    assert torch.equal(out_f[1], out_t[1]) and torch.equal(out_f[2], out_t[2])
+    assert rel(out_f[4], out_t[4]) < 1e-5
+    assert rel(m2d_f.grad, m2d_t.grad) < 1e-4
+    for k in use:
+        if k == 'shs' and deg == 0:
+            continue
+        assert params[k].grad.shape == ret[k].grad.shape, k
+        # two fp32 paths against each other (each is checked against the fp64 oracle to 1e-4 elsewhere): twice the bound
+        assert rel(params[k].grad, ret[k].grad) < 2e-4, (k, rel(params[k].grad, ret[k].grad))
+
+
+def _eval_sh_wobase(deg, sh, dirs):
+    """eval_sh_wobase (LoG/model/sh_utils.py:31-58) through the oracle's eval_sh: a zero DC coefficient in front of the rest
+    coefficients, minus the 0.5 offset eval_sh adds (its basis is pinned to the reference by tests/test_oracle_golden.py)."""
+    full = torch.cat([torch.zeros_like(sh[:, :1]), sh], dim=1)
+    return O.eval_sh(deg, full, dirs) - 0.5
 
 
 def check_fused_log_colour_activation_with_sh(deg, size=(160, 96, 1800)):
@@ -473,4 +575,4 @@ def check_fused_log_colour_activation_with_sh(deg, size=(160, 96, 1800)):
     (out['image'] * G.to(torch.float64)).sum().backward()
     assert rel(img_f, out['image'].detach()) < 1e-4
     for k in g_t:
-        assert rel(g_f[k], leaves[k].grad) < 2e-4, (k, rel(g_f[k], leaves[k].grad))
+        assert rel(g_f[k], leaves[k].grad) < TOL, (k, rel(g_f[k], leaves[k].grad))

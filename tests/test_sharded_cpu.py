@@ -141,7 +141,7 @@ def _shard_worker(rank, world, port, tag, n, W, H, steps, out):
     from oracle import torch_dense as O
     from util import f32_camera, rel, run_gpu, settings_from_camera
     _capi._lib = _capi.bind(ctypes.CDLL(build_emu.build()))          # TEST ONLY: the emulated kernels (tests/emu)
-    _capi.current_stream = lambda: None
+    _capi.current_stream = lambda device=None: None
     _capi.require_cuda = lambda t, name: None
     util.DEVICE = ['cpu']
     os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)

@@ -19,6 +19,27 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
+def record_parity(case, errors, bound, filter_on=True, note=None):
+    """Append the achieved norm-wise relative errors of one parity case to gpurun_out/parity.json (hardware runs only; the
+    file travels back with gpurun_out/ and is committed as profiles/parity_rNN.json).  errors: {tensor: (error, fp32-oracle
+    error or None)}."""
+    import json
+    import os
+    if DEVICE[0] == 'cpu':
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, 'gpurun_out', 'parity.json')
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[case] = {'bound': bound, 'low_pass_filter': bool(filter_on), 'note': note,
+                      'errors': {k: {'vs_fp64_oracle': float(v[0]), 'fp32_oracle_vs_fp64_oracle': None if v[1] is None else float(v[1]),
+                                     'exceeds_1e-4': bool(v[0] >= 1e-4)} for k, v in errors.items()}}
+        json.dump(data, open(path, 'w'), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 def settings_from_camera(cam, device, sh_degree=None):
     from log_b200 import GaussianRasterizationSettings
     f = lambda t: t.to(device=device, dtype=torch.float32)
