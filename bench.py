@@ -259,20 +259,23 @@ def main():
             if rank == 0:
                 print(f'bench.py: peer exchange unavailable ({e!r}); using NCCL all-to-all', file=sys.stderr)
 
-    def step_resident():
+    inst_cap = [None]          # N = 1: instance capacity of the device-sized call, learned from the warm-up steps
+
+    def step_resident(record=False):
         if shard is not None:
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            ev[0].record()
+            if record:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
             img, radii, pid, pwp, st = shard.forward(settings, loc['means3D'], loc_op, loc['scales'], loc['rotations'],
                                                      loc['colors'] if deg == 0 else None, loc['shs'] if deg > 0 else None,
                                                      filter_mode=LGR_FILTER_MAX, want_aux=True)
-            ev[1].record()
+            if record:
+                ev[1].record()
             g = shard.backward(st, dG)          # sweep + return, barrier, gather + per-Gaussian backward
-            ev[2].record()
-            ev[3].record()
-            phase_ev.append(ev)
-            stats['rows'] = st.num_rows
-            stats['D'], stats['D_stock'], stats['maxlen'], stats['visible'] = st.num_instances, st.stock_instances, st.max_tile_len, st.num_rows
+            if record:
+                ev[2].record()
+                ev[3].record()
+                phase_ev.append(ev)
             return g
         if world > 1:      # band mode: owner-grouped id lists, packed gradient rows, one all-to-all to the owner ranks
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -288,13 +291,16 @@ def main():
                 ev[2].record()
                 g = sharded.exchange_rows_to_owners(rows, st.band_counts_host, n)
             ev[3].record()
-            phase_ev.append(ev)
+            if record:
+                phase_ev.append(ev)
             stats['rows'] = sum(st.band_counts_host)
         else:
             img, radii, pid, pwp, pw, st = rasterize_forward(settings, d['means3D'], opac, d['scales'], d['rotations'], col, shs,
-                                                             LGR_FILTER_MAX, True, tile_rows)
+                                                             LGR_FILTER_MAX, True, tile_rows, instance_capacity=inst_cap[0])
             g = rasterize_backward(st, dG, d['means3D'], opac, d['scales'], d['rotations'], col, shs)
-        stats['D'], stats['D_stock'], stats['maxlen'], stats['visible'] = st.num_instances, st.stock_instances, st.max_tile_len, st.num_visible
+            stats['state'] = st
+        if st.max_tile_len is not None:
+            stats['D'], stats['D_stock'], stats['maxlen'], stats['visible'] = st.num_instances, st.stock_instances, st.max_tile_len, st.num_visible
         return g
 
     def barrier():
@@ -303,20 +309,73 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sync_free = bool(int(os.environ.get('LGR_SYNC_FREE', '1'))) and (world == 1 or shard is not None)
+    use_graph = sync_free and bool(int(os.environ.get('LGR_GRAPH', '1')))
     for _ in range(args.warmup):
         step_resident()
+        if world == 1 and sync_free and inst_cap[0] is None and stats['maxlen'] <= _capi.load().lgr_sort_smem_capacity():
+            inst_cap[0] = stats['D'] + stats['D'] // 4 + 4096      # later steps: device-sized, nothing read back
+    barrier()
+    # The timed steps: no profiling events, no per-step host reads.  With device-sized calls a step contains no host
+    # synchronisation, so one step is captured in a CUDA graph and replayed (inputs and scratch are static buffers).
+    graph, graph_note = None, 'off'
+    if use_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_resident()
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_static = step_resident()
+            graph_note = 'one step (forward + backward' + (', both exchanges and barriers' if shard is not None else '') + ') captured once, replayed per step'
+        except Exception as e:      # capture is an optimisation: fall back to plain launches and say so
+            graph = None
+            graph_note = f'capture failed ({type(e).__name__}: {str(e)[:120]}); plain launches'
+            torch.cuda.synchronize()
+    flags = torch.tensor([0 if graph is not None else 1], device=dev)
+    if world > 1:      # all ranks replay, or none does
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        if int(flags.item()) and graph is not None:
+            graph, graph_note = None, 'capture failed on another rank; plain launches'
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    _capi.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    phase_ev.clear()
     for _ in range(args.steps):
-        step_resident()
+        if graph is not None:
+            graph.replay()
+        else:
+            step_resident()
     e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    # did every device-sized step fit its buffers?  (one read-back, after the timed region)
+    if shard is not None:
+        sst = shard.check_overflow()
+        stats['rows'] = sst['num_rows']
+        stats['D'], stats['D_stock'], stats['maxlen'], stats['visible'] = sst['num_instances'], sst['stock_instances'], sst['max_tile_len'], sst['num_rows']
+    elif world == 1 and inst_cap[0] is not None:
+        sst = stats['state'].read_stats()
+        if sst['overflow']:
+            raise SystemExit(f'bench.py: device-sized step outgrew its buffers: {sst}')
+        stats['D'], stats['D_stock'], stats['maxlen'], stats['visible'] = sst['num_instances'], sst['stock_instances'], sst['max_tile_len'], sst['num_visible']
+    # ---- a second, PROFILED pass (per-kernel CUDA events, phase events): explains the step, is not the step time ----
+    prof_steps = max(3, min(args.steps, 10))
+    _capi.profile_enable(True)
+    phase_ev.clear()
+    for _ in range(prof_steps):
+        step_resident(record=True)
     barrier()
     phases = None
     if phase_ev:
@@ -325,12 +384,7 @@ def main():
         phases['rows_sent_per_rank'] = stats.get('rows')
     prof = _capi.profile_collect()
     _capi.profile_enable(False)
-    clk = clocks.stop() if rank == 0 else None
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    prof = {k: (v[0] * args.steps / prof_steps, v[1]) for k, v in prof.items()}      # scaled to the K timed steps (reported per step below)
 
     # ---- parity of the multi-GPU result (outside the timed region): the same step on ONE GPU, compared on every rank ----
     parity = None
@@ -496,14 +550,16 @@ def main():
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp) and world == 1:      # the ncu capture is of the single-GPU full-image launch
         traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
-    launches = sum(v[1] for v in prof.values())
+    launches = int(round(sum(v[1] for v in prof.values()) * args.steps / prof_steps))      # of the K timed steps (counted in the profiled pass)
     line = {
         'metric': 'gaussians_per_s_fwd_bwd', 'value': n / (ms_step * 1e-3), 'unit': 'Gaussians/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'mpix_per_s': W * H / (ms_step * 1e-3) / 1e6,
         'config': {'workload': workload_name(args.workload) + ('' if args.order == 'random' else f' [memory order: {args.order}]'),
                    'parallelism': (f'Gaussians sharded x{world} + tile-row bands x{world}: splat records pushed to the band owners, 2D gradients returned, over NVLink peer memory (shard mode)') if shard is not None else (f'tile-row bands x{world}, gradient rows ' + ('pushed to owner ranks over NVLink peer memory (fused in the backward kernel)' if peer is not None else 'NCCL all-to-all to owner ranks')) if world > 1 else 'single GPU', 'l2': 'inputs+intermediates > L2 (126 MB)' if n >= 1_000_000 else 'working set fits L2; not flushed',
-                   'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible']},
+                   'instances_stock_rule': D_stock, 'instances_binned': D_bin, 'longest_tile_list': stats['maxlen'], 'visible': stats['visible'],
+                   'launch': ('device-sized calls (no host read-back inside a step); ' if sync_free else 'host-sized calls (one 32-byte read-back per forward); ') + 'CUDA graph: ' + graph_note,
+                   'kernel_split': f'kernel_ms / phase_ms_rank0 come from a separate profiled pass of {prof_steps} steps (per-kernel CUDA events, plain launches)'},
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                      'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes': kb[dom], 'kernel_ms': kms[dom],
                      'instances': 'binned (instances_binned): the (Gaussian, tile) pairs the launch processes',

@@ -83,6 +83,8 @@ typedef struct lgr_view {
                             every output -- splat, radii, point_weight, point_count, all gradients -- is compact, row i
                             belonging to table row gather_index_d[i], which is exactly the gradient layout LoG's
                             SparseOptimizer consumes (sparse_optimizer.py:163-196).  Not available in band mode. */
+  const int32_t* pid_map_d; /* (n) int32 or NULL: when set, point_id_pixel holds pid_map_d[row] instead of the row index of the
+                            winning splat (shard mode renders received ROWS; the map turns them into global Gaussian ids) */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */
@@ -95,7 +97,8 @@ typedef struct lgr_view {
 #define LGR_TILE_SCRATCH_INTS 33 /* per tile: one counter per 128-byte line (32 ints) + one slot of the long-tile list */
 #define LGR_META_INTS 8     /* meta_d: [0]=D binned instances [1]=longest tile list [2..3]=D by the stock
                                radius-square rule (lo,hi 32 bits) [4]=#Gaussians with radius>0
-                               [5]=#tiles whose list exceeds the small shared-memory sort */
+                               [5]=#tiles whose list exceeds the small shared-memory sort
+                               [6]=overflow flags of lgr_forward_render_device_sized (0 = the outputs are valid) */
 
 int lgr_abi_version(void);
 
@@ -132,6 +135,21 @@ int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, i
                        int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d,
                        int32_t* point_count_d, void* stream);
 int32_t lgr_sort_smem_capacity(void);
+
+/* Stage 2 without the host read of meta_d ("device-sized"): the same work as lgr_forward_render, but every launch shape is
+ * independent of D / the longest list / the number of long tiles -- the kernels read them from meta_d on the device -- so the
+ * whole forward needs no host synchronisation and can be captured in a CUDA graph.  The caller sizes inst_key_d /
+ * inst_val_d / sorted_ids_d for `instance_capacity` instances (e.g. 1.25 x the D of the previous view).  If the view needs
+ * more (meta_d[0] > instance_capacity) or holds a tile list longer than lgr_sort_smem_capacity(), nothing is written out of
+ * bounds, meta_d[6] is set to a non-zero value (bit 0: capacity, bit 1: list too long) and the outputs of this view are
+ * INVALID: the caller checks meta_d[6] when it next synchronises and redoes the view through lgr_forward_render.
+ * tile_start_d is mutable here (emptied on overflow). */
+int lgr_forward_render_device_sized(const lgr_view* view, int64_t n, int64_t instance_capacity, int32_t* meta_d,
+                                    const float* splat_d, const int32_t* radii_d, int32_t* tile_start_d,
+                                    int32_t* tile_cursor_d, uint32_t* inst_key_d, uint32_t* inst_val_d,
+                                    int32_t* sorted_ids_d, float* image_d, float* final_T_d, int32_t* n_contrib_d,
+                                    int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d,
+                                    int32_t* point_count_d, void* stream);
 
 /* Backward: per-tile gradient sweep (front to back, re-using the rendered image_d of the forward for the colour
  * behind each splat), then per-Gaussian projection backward.
@@ -221,6 +239,22 @@ int lgr_shard_return_rows(const lgr_shard_layout* layout, const float* exchange_
 int lgr_shard_gather(const lgr_view* view, const lgr_shard_layout* layout, int64_t n_local, const float* splat_d,
                      const int32_t* radii_d, const int32_t* send_scratch_d, const float* exchange_d,
                      float* dsplat_local_d, float* point_weight_d, int32_t* point_count_d, void* stream);
+
+/* The same three steps with fewer launches and no host-side sizes (what log_b200/sharded.py uses):
+ *  - lgr_shard_recv_bin_aux also zeroes the used rows of the per-row aux accumulators the blend writes (point_weight_rows_d
+ *    fp32, point_count_rows_d int32, each num_ranks*cap; either may be NULL), instead of two full-size memsets per step;
+ *  - lgr_shard_return_packed sends everything back in ONE launch of fixed size: the 12-float gradient row with the aux
+ *    values in its unused floats 9 (max alpha*T, fp32 bits) and 10 (winner-pixel count, int32 bits);
+ *  - lgr_shard_gather_packed reads the aux values from there. */
+int lgr_shard_recv_bin_aux(const lgr_view* view, const lgr_shard_layout* layout, float* exchange_d, float* dsplat_d,
+                           int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, float* point_weight_rows_d,
+                           int32_t* point_count_rows_d, void* stream);
+int lgr_shard_return_packed(const lgr_shard_layout* layout, const float* exchange_d, const float* dsplat_rows_d,
+                            const float* point_weight_rows_d, const int32_t* point_count_rows_d, void* const* peer_base_d,
+                            void* stream);
+int lgr_shard_gather_packed(const lgr_view* view, const lgr_shard_layout* layout, int64_t n_local, const float* splat_d,
+                            const int32_t* radii_d, const int32_t* send_scratch_d, const float* exchange_d,
+                            float* dsplat_local_d, float* point_weight_d, int32_t* point_count_d, void* stream);
 
 /* ---- Level-of-Gaussian tree traversal ----------------------------------------------------------
  * Replaces TensorTree.traverse / _query_tree_torch (LoG/model/tensor_tree.py:132-186) and the per-level

@@ -17,9 +17,9 @@ LGR_STAGE_HEADER_FLOATS = 64
 LGR_ROW_FLOATS = 20
 
 EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
-           'lgr_forward_render', 'lgr_backward', 'lgr_grad_scatter_add', 'lgr_grad_scatter_add_staged', 'lgr_point_compact', 'lgr_sparse_adam', 'lgr_profile_enable', 'lgr_profile_collect',
+           'lgr_forward_render', 'lgr_forward_render_device_sized', 'lgr_backward', 'lgr_grad_scatter_add', 'lgr_grad_scatter_add_staged', 'lgr_point_compact', 'lgr_sparse_adam', 'lgr_profile_enable', 'lgr_profile_collect',
            'lgr_profile_kernel_name', 'lgr_shard_send', 'lgr_shard_recv_bin', 'lgr_blend_backward', 'lgr_shard_return_rows',
-           'lgr_shard_gather', 'lgr_tree_traverse')
+           'lgr_shard_gather', 'lgr_shard_recv_bin_aux', 'lgr_shard_return_packed', 'lgr_shard_gather_packed', 'lgr_tree_traverse')
 LGR_SHARD_MAX_RANKS = 32
 LGR_PROFILE_KERNELS = 12
 
@@ -29,7 +29,7 @@ class LgrView(ctypes.Structure):
     _fields_ = [('image_height', _i32), ('image_width', _i32), ('tanfovx', _f32), ('tanfovy', _f32),
                 ('scale_modifier', _f32), ('sh_degree', _i32), ('sh_coeffs', _i32), ('filter_mode', _i32),
                 ('want_aux', _i32), ('tile_row_begin', _i32), ('tile_row_end', _i32),
-                ('num_owners', _i32), ('raw_params', _i32), ('band_ids_d', _vp), ('band_blk_d', _vp), ('band_count_d', _vp), ('band_rows_d', _vp), ('band_dsplat_d', _vp), ('tile_rank_d', _vp), ('gather_index_d', _vp),
+                ('num_owners', _i32), ('raw_params', _i32), ('band_ids_d', _vp), ('band_blk_d', _vp), ('band_count_d', _vp), ('band_rows_d', _vp), ('band_dsplat_d', _vp), ('tile_rank_d', _vp), ('gather_index_d', _vp), ('pid_map_d', _vp),
                 ('viewmatrix_d', _vp), ('projmatrix_d', _vp), ('campos_d', _vp), ('bg_d', _vp)]
 
 
@@ -72,6 +72,8 @@ def bind(lib):
     lib.lgr_forward_project.argtypes = [ctypes.POINTER(LgrView), _i64] + [_vp] * 13
     lib.lgr_forward_render.restype = ctypes.c_int
     lib.lgr_forward_render.argtypes = [ctypes.POINTER(LgrView), _i64, _i64, _i32, _i32] + [_vp] * 16
+    lib.lgr_forward_render_device_sized.restype = ctypes.c_int
+    lib.lgr_forward_render_device_sized.argtypes = [ctypes.POINTER(LgrView), _i64, _i64] + [_vp] * 16
     lib.lgr_sparse_adam.restype = ctypes.c_int
     lib.lgr_sparse_adam.argtypes = [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_double, ctypes.c_double,
                                     ctypes.c_double, ctypes.c_double, _vp]
@@ -94,6 +96,12 @@ def bind(lib):
     lib.lgr_shard_return_rows.argtypes = [lay, _vp, _i64, _vp, _i32, _i64, _vp, _vp]
     lib.lgr_shard_gather.restype = ctypes.c_int
     lib.lgr_shard_gather.argtypes = [ctypes.POINTER(LgrView), lay, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.lgr_shard_recv_bin_aux.restype = ctypes.c_int
+    lib.lgr_shard_recv_bin_aux.argtypes = [ctypes.POINTER(LgrView), lay, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.lgr_shard_return_packed.restype = ctypes.c_int
+    lib.lgr_shard_return_packed.argtypes = [lay, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.lgr_shard_gather_packed.restype = ctypes.c_int
+    lib.lgr_shard_gather_packed.argtypes = [ctypes.POINTER(LgrView), lay, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.lgr_tree_traverse.restype = ctypes.c_int
     lib.lgr_tree_traverse.argtypes = [ctypes.POINTER(LgrTree), _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _i64, _f32,
                                       _i32, _vp, _vp, _vp, _vp]

@@ -71,7 +71,7 @@ constexpr int SCATTER_THREADS = 256;
 __global__ void __launch_bounds__(SCATTER_THREADS)
 bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
                    const int32_t* __restrict__ tile_start, int32_t* __restrict__ cursor, uint32_t* __restrict__ inst_key,
-                   uint32_t* __restrict__ inst_val) {
+                   uint32_t* __restrict__ inst_val, int64_t capacity /* of inst_key / inst_val: stores beyond it are dropped */) {
   int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
   if (i >= n) return;
   if (v.num_owners > 0) {      // band mode: slot i of the per-CTA id lists written by project_fwd (256 ids per CTA)
@@ -119,8 +119,7 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
     for (int k = 0; k < 4; k++)
       if (t[k] >= 0) {
         const int pos = __ldg(tile_start + t[k]) + slot[k];
-        inst_key[pos] = key;
-        inst_val[pos] = (uint32_t)i;
+        if (pos < capacity) { inst_key[pos] = key; inst_val[pos] = (uint32_t)i; }
       }
     return;
   }
@@ -129,8 +128,7 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
     for (int tx = x0; tx < x1; tx++) {
       const int t = (ty - v.row0) * v.gx + tx;
       const int pos = tile_start[t] + (big ? cursor[t * CSTRIDE] : 0) + atomicAdd(cursor + t * CSTRIDE + big, 1);
-      inst_key[pos] = key;
-      inst_val[pos] = (uint32_t)i;
+      if (pos < capacity) { inst_key[pos] = key; inst_val[pos] = (uint32_t)i; }
     }
 }
 
@@ -352,32 +350,53 @@ __device__ __forceinline__ bool sort_tile_msd(uint32_t* kA, uint32_t* vA, uint32
 
 // mode 0: lists with len <= cap live in shared memory (dynamic smem = 16*cap bytes); longer lists are skipped.
 // mode 1: lists with lo < len are sorted in global memory (inst_* in place, tmp_* scratch).
+// count_ptr == nullptr: one tile per CTA (tile = tile_list ? tile_list[blockIdx.x] : blockIdx.x).  Otherwise the grid is a
+// fixed size and strides over the *count_ptr listed tiles (device-sized launch: no host read of the long-tile count).
+// flags (may be nullptr): bit 1 is set when a list longer than `cap` is met in MODE 0 with lo > 0 (a long-tile launch that
+// cannot hold it: the list stays unsorted and the caller must redo the step with the host-sized path).
 template <int MODE>
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(const int32_t* __restrict__ tile_list /* nullptr: tile = blockIdx.x */,
                  const int32_t* __restrict__ tile_start, uint32_t* __restrict__ inst_key,
                  uint32_t* __restrict__ inst_val, uint32_t* __restrict__ tmp, int32_t* __restrict__ sorted_ids, int lo,
-                 int cap, int id_bits) {
+                 int cap, int id_bits, const int32_t* __restrict__ count_ptr, int32_t* __restrict__ flags) {
   extern __shared__ uint32_t smem_u32[];
   __shared__ int whist[MODE == 1 ? SORT_WARPS * RADIX : 1];
   __shared__ MsdShared msd;
-  const int t = tile_list ? tile_list[blockIdx.x] : (int)blockIdx.x;
-  const int beg = tile_start[t], len = tile_start[t + 1] - beg;
-  if (len <= lo || (MODE == 0 && len > cap)) return;
-  if (MODE == 0) {
-    uint32_t* kA = smem_u32; uint32_t* vA = kA + cap; uint32_t* kB = vA + cap; uint32_t* vB = kB + cap;
-    for (int i = threadIdx.x; i < len; i += SORT_THREADS) { kA[i] = inst_key[beg + i]; vA[i] = inst_val[beg + i]; }
-    __syncthreads();
-    // the work stack holds at most cap / (MSD_SMALL + 1) <= 403 ranges: overflow is unreachable; fail loudly if it is hit
-    if (len > 1 && !sort_tile_msd(kA, vA, kB, vB, len, msd)) __trap();
-    for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
-  } else {
-    uint32_t* kA = inst_key + beg; uint32_t* vA = inst_val + beg;
-    uint32_t* kB = tmp + 2 * (int64_t)beg; uint32_t* vB = kB + len;
-    __syncthreads();
-    sort_tile(kA, vA, kB, vB, len, id_bits, whist);
-    for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
+  const int count = count_ptr ? *count_ptr : (int)gridDim.x;
+  for (int b = blockIdx.x; b < count; b += gridDim.x) {
+    const int t = tile_list ? tile_list[b] : b;
+    const int beg = tile_start[t], len = tile_start[t + 1] - beg;
+    if (len <= lo) continue;
+    if (MODE == 0 && len > cap) {
+      if (flags && lo > 0 && threadIdx.x == 0) atomicOr(flags, 2);
+      continue;
+    }
+    if (MODE == 0) {
+      uint32_t* kA = smem_u32; uint32_t* vA = kA + cap; uint32_t* kB = vA + cap; uint32_t* vB = kB + cap;
+      for (int i = threadIdx.x; i < len; i += SORT_THREADS) { kA[i] = inst_key[beg + i]; vA[i] = inst_val[beg + i]; }
+      __syncthreads();
+      // the work stack holds at most cap / (MSD_SMALL + 1) <= 403 ranges: overflow is unreachable; fail loudly if it is hit
+      if (len > 1 && !sort_tile_msd(kA, vA, kB, vB, len, msd)) __trap();
+      for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
+    } else {
+      uint32_t* kA = inst_key + beg; uint32_t* vA = inst_val + beg;
+      uint32_t* kB = tmp + 2 * (int64_t)beg; uint32_t* vB = kB + len;
+      __syncthreads();
+      sort_tile(kA, vA, kB, vB, len, id_bits, whist);
+      for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
+    }
+    __syncthreads();      // the shared buffers are reused by the next tile of this CTA
   }
+}
+
+// Device-sized binning (no host read of D): if more instances were counted than the caller's buffers hold, flag it (bit 0)
+// and empty every tile list, so that no later kernel reads or writes past `capacity`; the caller redoes the step.
+__global__ void __launch_bounds__(256)
+clamp_lists_kernel(int ntiles, int64_t capacity, int32_t* __restrict__ tile_start, int32_t* __restrict__ meta) {
+  if ((int64_t)meta[0] <= capacity) return;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i <= ntiles; i += gridDim.x * 256) tile_start[i] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(meta + 6, 1);
 }
 
 
@@ -469,10 +488,19 @@ int launch_tile_scan(int ntiles, int32_t* tile_start, int32_t* cursor, int32_t* 
   return 0;
 }
 
+constexpr int LONG_SORT_GRID = 32;      // device-sized long-tile launch: CTAs stride over the (device-side) list of long tiles
+
+// meta_dev != nullptr: device-sized call -- num_inst is the CAPACITY of the instance buffers, max_len / num_long are ignored
+// (read from meta_dev on the device), tile_start is mutable (emptied on overflow).
 int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len, int num_long, const float* splat,
-                        const int32_t* radii, const int32_t* tile_start, int32_t* cursor, uint32_t* inst_key,
-                        uint32_t* inst_val, uint32_t* inst_tmp, int32_t* sorted_ids, cudaStream_t st) {
+                        const int32_t* radii, int32_t* tile_start, int32_t* cursor, uint32_t* inst_key,
+                        uint32_t* inst_val, uint32_t* inst_tmp, int32_t* sorted_ids, int32_t* meta_dev, cudaStream_t st) {
   if (n == 0) return 0;
+  if (meta_dev) {
+    const int nt = v.gx * (v.row1 - v.row0);
+    clamp_lists_kernel<<<(nt + 256) / 256, 256, 0, st>>>(nt, num_inst, tile_start, meta_dev);
+    LGR_CHECK_LAUNCH();
+  }
   // With no binned instance only the sort is skipped: in band mode the scatter kernel is also the one writer of the
   // row -> id map and of the zeroed accumulator rows the backward reads (band lists follow the stock rectangle, so they
   // can be non-empty while nothing reaches alpha >= 1/255), and with band_dsplat set it zeroes the visible rows.
@@ -481,7 +509,8 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
   const unsigned blocks = (unsigned)((n + SCATTER_THREADS - 1) / SCATTER_THREADS);
   {
     ProfScope ps(K_BIN_SCATTER, st);
-    bin_scatter_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val);
+    bin_scatter_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val,
+                                                           meta_dev ? num_inst : (int64_t)0x7fffffffffffffffLL);
   }
   LGR_CHECK_LAUNCH();
   if (num_inst == 0) return 0;
@@ -491,18 +520,29 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
     cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * SORT_CAP_LARGE);
     if (e != cudaSuccess) return (int)e;
   }
+  if (meta_dev) {
+    // device-sized: launch shapes do not depend on D / longest list / number of long tiles (read on the device), so the
+    // forward needs no host synchronisation and can be captured in a CUDA graph
+    ProfScope ps(K_TILE_SORT, st, 2);
+    tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * SORT_CAP_SMALL, st>>>(nullptr, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, SORT_CAP_SMALL, id_bits, nullptr, nullptr);
+    LGR_CHECK_LAUNCH();
+    const int32_t* long_list = cursor + CSTRIDE * ntiles;
+    tile_sort_kernel<0><<<LONG_SORT_GRID, SORT_THREADS, 16 * SORT_CAP_LARGE, st>>>(long_list, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_SMALL, SORT_CAP_LARGE, id_bits, meta_dev + 5, meta_dev + 6);
+    LGR_CHECK_LAUNCH();
+    return 0;
+  }
   ProfScope ps(K_TILE_SORT, st, 1 + (num_long > 0) + (max_len > SORT_CAP_LARGE));
   const int cap_main = max(256, min(max_len, SORT_CAP_SMALL));
-  tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * cap_main, st>>>(nullptr, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, cap_main, id_bits);
+  tile_sort_kernel<0><<<ntiles, SORT_THREADS, 16 * cap_main, st>>>(nullptr, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, 0, cap_main, id_bits, nullptr, nullptr);
   LGR_CHECK_LAUNCH();
   if (num_long > 0) {   // only the long tiles (listed by the scan kernel behind the cursors), smem sized to the longest
     const int32_t* long_list = cursor + CSTRIDE * ntiles;
     const int cap = min(max_len, SORT_CAP_LARGE);
-    tile_sort_kernel<0><<<num_long, SORT_THREADS, 16 * cap, st>>>(long_list, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_SMALL, cap, id_bits);
+    tile_sort_kernel<0><<<num_long, SORT_THREADS, 16 * cap, st>>>(long_list, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_SMALL, cap, id_bits, nullptr, nullptr);
     LGR_CHECK_LAUNCH();
     if (max_len > SORT_CAP_LARGE) {
       if (!inst_tmp) return LGR_E_CAPACITY;
-      tile_sort_kernel<1><<<num_long, SORT_THREADS, 0, st>>>(long_list, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_LARGE, 0, id_bits);
+      tile_sort_kernel<1><<<num_long, SORT_THREADS, 0, st>>>(long_list, tile_start, inst_key, inst_val, inst_tmp, sorted_ids, SORT_CAP_LARGE, 0, id_bits, nullptr, nullptr);
       LGR_CHECK_LAUNCH();
     }
   }

@@ -240,7 +240,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
     final_T[pix] = T;
     n_contrib[pix] = last;
     if (AUX) {
-      pid_pixel[pix] = wid; pw_pixel[pix] = wmax;
+      pid_pixel[pix] = (v.pid_map && wid >= 0) ? v.pid_map[wid] : wid; pw_pixel[pix] = wmax;
       if (point_count && wid >= 0) atomicAdd(point_count + wid, 1);      // histogram of the per-pixel winners
     }
   }

@@ -16,8 +16,8 @@ int launch_grad_scatter_add(int64_t, const float*, int64_t, int64_t, float*, cud
 int launch_grad_scatter_add_staged(const float*, int, int64_t, int64_t, int64_t, float*, cudaStream_t);
 int launch_band_scan(const View&, cudaStream_t);
 int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, bool, cudaStream_t);
-int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, const int32_t*, int32_t*,
-                        uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
+int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, int32_t*, int32_t*,
+                        uint32_t*, uint32_t*, uint32_t*, int32_t*, int32_t*, cudaStream_t);
 int sort_smem_capacity();
 int launch_blend_fwd(const View&, const int32_t*, const int32_t*, const float*, float*, float*, int32_t*, int32_t*,
                      float*, float*, int32_t*, cudaStream_t);
@@ -28,10 +28,11 @@ int launch_blend_bwd(const View&, const int32_t*, const int32_t*, const float*, 
                      cudaStream_t);
 int launch_shard_send(const View&, const ShardLayout&, int64_t, int64_t, const float*, const int32_t*, int32_t*, void* const*,
                       cudaStream_t);
-int launch_shard_recv_count(const View&, const ShardLayout&, float*, float*, int32_t*, int32_t*, cudaStream_t);
+int launch_shard_recv_count(const View&, const ShardLayout&, float*, float*, int32_t*, int32_t*, float*, int32_t*, cudaStream_t);
+int launch_shard_return_packed(const ShardLayout&, const float*, const float*, const float*, const int32_t*, void* const*, cudaStream_t);
 int launch_shard_return(const ShardLayout&, const float*, int64_t, const void*, int, int64_t, void* const*, cudaStream_t);
 int launch_shard_gather(const View&, const ShardLayout&, int64_t, const float*, const int32_t*, const int32_t*, const float*,
-                        float*, float*, int32_t*, cudaStream_t);
+                        float*, float*, int32_t*, int, cudaStream_t);
 int launch_tree_traverse(const TreeArgs&, int64_t, int64_t, const int64_t*, int64_t, int, int32_t*, int64_t*, int64_t*, cudaStream_t);
 }  // namespace lgr
 
@@ -119,8 +120,29 @@ int lgr_forward_render(const lgr_view* view, int64_t n, int64_t num_instances, i
   if (num_instances > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const View v = make_view(view, n);
-  int rc = launch_bin_and_sort(v, n, num_instances, max_tile_len, num_long_tiles, splat_d, radii_d, tile_start_d, tile_cursor_d,
-                               inst_key_d, inst_val_d, inst_tmp_d, sorted_ids_d, st);
+  int rc = launch_bin_and_sort(v, n, num_instances, max_tile_len, num_long_tiles, splat_d, radii_d, const_cast<int32_t*>(tile_start_d), tile_cursor_d,
+                               inst_key_d, inst_val_d, inst_tmp_d, sorted_ids_d, nullptr, st);
+  if (rc) return rc;
+  return launch_blend_fwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, final_T_d, n_contrib_d, point_id_pixel_d,
+                          point_weight_pixel_d, point_weight_d, view->want_aux ? point_count_d : nullptr, st);
+}
+
+int lgr_forward_render_device_sized(const lgr_view* view, int64_t n, int64_t instance_capacity, int32_t* meta_d,
+                                    const float* splat_d, const int32_t* radii_d, int32_t* tile_start_d,
+                                    int32_t* tile_cursor_d, uint32_t* inst_key_d, uint32_t* inst_val_d,
+                                    int32_t* sorted_ids_d, float* image_d, float* final_T_d, int32_t* n_contrib_d,
+                                    int32_t* point_id_pixel_d, float* point_weight_pixel_d, float* point_weight_d,
+                                    int32_t* point_count_d, void* stream) {
+  if (!view_ok(view) || n < 0 || instance_capacity <= 0 || !meta_d || !tile_start_d || !tile_cursor_d || !image_d || !final_T_d ||
+      !n_contrib_d || !inst_key_d || !inst_val_d || !sorted_ids_d)
+    return LGR_E_BADARG;
+  if (n > 0 && (!splat_d || !radii_d)) return LGR_E_BADARG;
+  if (view->want_aux && (!point_id_pixel_d || !point_weight_pixel_d || (n > 0 && !point_weight_d))) return LGR_E_BADARG;
+  if (instance_capacity > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const View v = make_view(view, n);
+  int rc = launch_bin_and_sort(v, n, instance_capacity, 0, 0, splat_d, radii_d, tile_start_d, tile_cursor_d, inst_key_d, inst_val_d,
+                               nullptr, sorted_ids_d, meta_d, st);
   if (rc) return rc;
   return launch_blend_fwd(v, tile_start_d, sorted_ids_d, splat_d, image_d, final_T_d, n_contrib_d, point_id_pixel_d,
                           point_weight_pixel_d, point_weight_d, view->want_aux ? point_count_d : nullptr, st);
@@ -223,6 +245,12 @@ int lgr_shard_send(const lgr_view* view, const lgr_shard_layout* layout, int64_t
 
 int lgr_shard_recv_bin(const lgr_view* view, const lgr_shard_layout* layout, float* exchange_d, float* dsplat_d,
                        int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, void* stream) {
+  return lgr_shard_recv_bin_aux(view, layout, exchange_d, dsplat_d, tile_start_d, tile_cursor_d, meta_d, nullptr, nullptr, stream);
+}
+
+int lgr_shard_recv_bin_aux(const lgr_view* view, const lgr_shard_layout* layout, float* exchange_d, float* dsplat_d,
+                           int32_t* tile_start_d, int32_t* tile_cursor_d, int32_t* meta_d, float* point_weight_rows_d,
+                           int32_t* point_count_rows_d, void* stream) {
   if (!view_ok(view) || !layout_ok(layout) || !exchange_d || !dsplat_d || !tile_start_d || !tile_cursor_d || !meta_d) return LGR_E_BADARG;
   if (view->num_owners != 0) return LGR_E_BADARG;
   if ((int64_t)layout->num_ranks * layout->cap > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
@@ -233,7 +261,8 @@ int lgr_shard_recv_bin(const lgr_view* view, const lgr_shard_layout* layout, flo
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(meta_d, 0, sizeof(int32_t) * LGR_META_INTS, st);
   if (e != cudaSuccess) return (int)e;
-  int rc = launch_shard_recv_count(v, make_layout(layout), exchange_d, dsplat_d, tile_cursor_d, meta_d, st);
+  int rc = launch_shard_recv_count(v, make_layout(layout), exchange_d, dsplat_d, tile_cursor_d, meta_d, point_weight_rows_d,
+                                   point_count_rows_d, st);
   if (rc) return rc;
   return launch_tile_scan(ntiles, tile_start_d, tile_cursor_d, meta_d, view->tile_rank_d != nullptr, st);
 }
@@ -263,7 +292,25 @@ int lgr_shard_gather(const lgr_view* view, const lgr_shard_layout* layout, int64
   if (n_local == 0) return 0;
   if (!splat_d || !radii_d || !send_scratch_d || !exchange_d || !dsplat_local_d) return LGR_E_BADARG;
   return launch_shard_gather(make_view(view, n_local), make_layout(layout), n_local, splat_d, radii_d, send_scratch_d, exchange_d,
-                             dsplat_local_d, point_weight_d, point_count_d, (cudaStream_t)stream);
+                             dsplat_local_d, point_weight_d, point_count_d, 0, (cudaStream_t)stream);
+}
+
+int lgr_shard_gather_packed(const lgr_view* view, const lgr_shard_layout* layout, int64_t n_local, const float* splat_d,
+                            const int32_t* radii_d, const int32_t* send_scratch_d, const float* exchange_d,
+                            float* dsplat_local_d, float* point_weight_d, int32_t* point_count_d, void* stream) {
+  if (!view_ok(view) || !layout_ok(layout) || n_local < 0 || n_local > layout->cap) return LGR_E_BADARG;
+  if (n_local == 0) return 0;
+  if (!splat_d || !radii_d || !send_scratch_d || !exchange_d || !dsplat_local_d) return LGR_E_BADARG;
+  return launch_shard_gather(make_view(view, n_local), make_layout(layout), n_local, splat_d, radii_d, send_scratch_d, exchange_d,
+                             dsplat_local_d, point_weight_d, point_count_d, 1, (cudaStream_t)stream);
+}
+
+int lgr_shard_return_packed(const lgr_shard_layout* layout, const float* exchange_d, const float* dsplat_rows_d,
+                            const float* point_weight_rows_d, const int32_t* point_count_rows_d, void* const* peer_base_d,
+                            void* stream) {
+  if (!layout_ok(layout) || !exchange_d || !dsplat_rows_d || !peer_base_d) return LGR_E_BADARG;
+  return launch_shard_return_packed(make_layout(layout), exchange_d, dsplat_rows_d, point_weight_rows_d, point_count_rows_d,
+                                    peer_base_d, (cudaStream_t)stream);
 }
 
 /* ---- level-of-Gaussian tree traversal ---- */

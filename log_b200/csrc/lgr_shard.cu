@@ -173,7 +173,8 @@ shard_push_kernel(View v, ShardLayout L, int64_t n, int64_t gid_base, const floa
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SHARD_THREADS)
 shard_recv_count_kernel(View v, ShardLayout L, float* __restrict__ xbuf, float* __restrict__ dsplat,
-                        int32_t* __restrict__ tile_count, int32_t* __restrict__ meta) {
+                        int32_t* __restrict__ tile_count, int32_t* __restrict__ meta, float* __restrict__ pw_rows,
+                        int32_t* __restrict__ pc_rows) {
   __shared__ __align__(16) unsigned sStock[SHARD_WARPS];
   __shared__ __align__(16) int sVis[SHARD_WARPS];
   const int64_t slot = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x;
@@ -200,6 +201,8 @@ shard_recv_count_kernel(View v, ShardLayout L, float* __restrict__ xbuf, float* 
       count_tiles(v, tile_count, slot, x0, y0, x1, y1);
       float4* z = reinterpret_cast<float4*>(dsplat + slot * LGR_GRAD_FLOATS);
       z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pw_rows) pw_rows[slot] = 0.f;      // per-row aux accumulators of the blend: only used rows are ever read back
+      if (pc_rows) pc_rows[slot] = 0;
     }
   }
   const unsigned st_w = __reduce_add_sync(FULLMASK, stock);
@@ -237,13 +240,39 @@ shard_return_kernel(ShardLayout L, const float* __restrict__ xbuf, const T* __re
   }
 }
 
+// One launch for everything that travels back: the 48-byte 2D-gradient row with the two per-row aux values (max alpha*T
+// bits, winner-pixel count) packed into its unused floats 9 and 10.  Fixed grid, strides over the (device-side) row total.
+__global__ void __launch_bounds__(SHARD_THREADS)
+shard_return_packed_kernel(ShardLayout L, const float* __restrict__ xbuf, const float* __restrict__ dsplat_rows,
+                           const float* __restrict__ pw_rows, const int32_t* __restrict__ pc_rows,
+                           void* const* __restrict__ peer_base) {
+  const int32_t* count = reinterpret_cast<const int32_t*>(xbuf + L.off_count);
+  int64_t total = 0;
+  for (int s = 0; s < L.R; s++) total += count[s];
+  total *= 3;
+  for (int64_t t = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * SHARD_THREADS) {
+    int s = 0;
+    int64_t first = 0;
+    while (s + 1 < L.R && t >= first + (int64_t)count[s] * 3) { first += (int64_t)count[s] * 3; s++; }
+    const int64_t k = t - first;                                  // float4 index inside region s
+    const int64_t row = (int64_t)s * L.cap + k / 3;
+    float4 val = reinterpret_cast<const float4*>(dsplat_rows)[row * 3 + k % 3];
+    if (k % 3 == 2) {
+      val.y = pw_rows ? pw_rows[row] : 0.f;
+      val.z = pc_rows ? __int_as_float(pc_rows[row]) : 0.f;
+    }
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(peer_base[s]) + L.off_dsplat) + (int64_t)L.me * L.cap * 3 + k;
+    *dst = val;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // source side: gather what the band owners returned into dense per-Gaussian arrays of the local shard
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SHARD_THREADS)
 shard_gather_kernel(View v, ShardLayout L, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
                     const int32_t* __restrict__ send_blk, int B, const float* __restrict__ xbuf,
-                    float* __restrict__ dsplat_out, float* __restrict__ weight_out, int32_t* __restrict__ pcount_out) {
+                    float* __restrict__ dsplat_out, float* __restrict__ weight_out, int32_t* __restrict__ pcount_out, int packed) {
   __shared__ __align__(16) int sW[SHARD_MAX_RANKS][SHARD_WARPS];      // 16-byte aligned: a vectorised load of a row never covers a neighbour
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x;
@@ -266,9 +295,15 @@ shard_gather_kernel(View v, ShardLayout L, int64_t n, const float* __restrict__ 
     const float4 g0 = g[0], g1 = g[1], g2 = g[2];
     a.x += g0.x; a.y += g0.y; a.z += g0.z; a.w += g0.w;
     b.x += g1.x; b.y += g1.y; b.z += g1.z; b.w += g1.w;
-    c.x += g2.x; c.y += g2.y; c.z += g2.z; c.w += g2.w;
-    if (weight_out) wmax = max(wmax, reinterpret_cast<const unsigned*>(xbuf + L.off_weight)[row]);
-    if (pcount_out) pc += reinterpret_cast<const int32_t*>(xbuf + L.off_pcount)[row];
+    c.x += g2.x;
+    if (packed) {      // aux values travel inside the row (floats 9, 10), see shard_return_packed_kernel
+      if (weight_out) wmax = max(wmax, __float_as_uint(g2.y));
+      if (pcount_out) pc += __float_as_int(g2.z);
+    } else {
+      c.y += g2.y; c.z += g2.z; c.w += g2.w;
+      if (weight_out) wmax = max(wmax, reinterpret_cast<const unsigned*>(xbuf + L.off_weight)[row]);
+      if (pcount_out) pc += reinterpret_cast<const int32_t*>(xbuf + L.off_pcount)[row];
+    }
   }
   if (i < n) {
     float4* d = reinterpret_cast<float4*>(dsplat_out + i * LGR_GRAD_FLOATS);
@@ -304,11 +339,11 @@ int launch_shard_send(const View& v, const ShardLayout& L, int64_t n, int64_t gi
 }
 
 int launch_shard_recv_count(const View& v, const ShardLayout& L, float* xbuf, float* dsplat, int32_t* tile_count, int32_t* meta,
-                            cudaStream_t st) {
+                            float* pw_rows, int32_t* pc_rows, cudaStream_t st) {
   const int64_t total = (int64_t)L.R * L.cap;
   if (total <= 0) return 0;
   ProfScope ps(K_SHARD_RECV, st);
-  shard_recv_count_kernel<<<blocks_for(total), SHARD_THREADS, 0, st>>>(v, L, xbuf, dsplat, tile_count, meta);
+  shard_recv_count_kernel<<<blocks_for(total), SHARD_THREADS, 0, st>>>(v, L, xbuf, dsplat, tile_count, meta, pw_rows, pc_rows);
   LGR_CHECK_LAUNCH();
   return 0;
 }
@@ -333,13 +368,21 @@ int launch_shard_return(const ShardLayout& L, const float* xbuf, int64_t total_r
   return 0;
 }
 
+int launch_shard_return_packed(const ShardLayout& L, const float* xbuf, const float* dsplat_rows, const float* pw_rows,
+                               const int32_t* pc_rows, void* const* peer_base, cudaStream_t st) {
+  ProfScope ps(K_SHARD_RETURN, st);
+  shard_return_packed_kernel<<<148 * 8, SHARD_THREADS, 0, st>>>(L, xbuf, dsplat_rows, pw_rows, pc_rows, peer_base);
+  LGR_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_shard_gather(const View& v, const ShardLayout& L, int64_t n, const float* splat, const int32_t* radii,
                         const int32_t* send_blk, const float* xbuf, float* dsplat_out, float* weight_out, int32_t* pcount_out,
-                        cudaStream_t st) {
+                        int packed, cudaStream_t st) {
   if (n <= 0) return 0;
   const int B = (int)blocks_for(n);
   ProfScope ps(K_SHARD_GATHER, st);
-  shard_gather_kernel<<<B, SHARD_THREADS, 0, st>>>(v, L, n, splat, radii, send_blk, B, xbuf, dsplat_out, weight_out, pcount_out);
+  shard_gather_kernel<<<B, SHARD_THREADS, 0, st>>>(v, L, n, splat, radii, send_blk, B, xbuf, dsplat_out, weight_out, pcount_out, packed);
   LGR_CHECK_LAUNCH();
   return 0;
 }

@@ -73,7 +73,7 @@ def _stream(device=None):
 
 def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep,
                num_owners=0, band_ids=None, band_count=None, band_blk=None, band_rows=None, band_dsplat=None,
-               raw_params=False, tile_rank=None, gather_index=None):
+               raw_params=False, tile_rank=None, gather_index=None, pid_map=None):
     dev = s.viewmatrix.device
     vm, pm = _f32c(s.viewmatrix, 'viewmatrix'), _f32c(s.projmatrix, 'projmatrix', dev)
     bg = _f32c(s.bg, 'bg', dev)
@@ -95,6 +95,7 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
     v.band_dsplat_d = band_dsplat.data_ptr() if band_dsplat is not None else None
     v.tile_rank_d = tile_rank.data_ptr() if tile_rank is not None else None
     v.gather_index_d = gather_index.data_ptr() if gather_index is not None else None
+    v.pid_map_d = pid_map.data_ptr() if pid_map is not None else None
     v.viewmatrix_d, v.projmatrix_d = vm.data_ptr(), pm.data_ptr()
     v.campos_d = cp.data_ptr() if cp is not None else None
     v.bg_d = bg.data_ptr()
@@ -105,11 +106,19 @@ class RasterState:
     """Buffers produced by the forward and consumed by the backward (kept alive by autograd)."""
     __slots__ = ('view', 'keep', 'n', 'num_instances', 'max_tile_len', 'stock_instances', 'num_visible', 'splat',
                  'radii', 'clamped', 'tile_start', 'sorted_ids', 'final_T', 'n_contrib', 'image', 'sh', 'num_owners',
-                 'band_ids', 'band_count', 'band_counts_host', 'point_count')
+                 'band_ids', 'band_count', 'band_counts_host', 'point_count', 'meta')
+
+    def read_stats(self):
+        """Counters of this forward, read back from meta_d (synchronises): D, longest tile list, D by the stock rule, visible
+        Gaussians, and `overflow` (non-zero only after a device-sized call that outgrew its buffers: outputs invalid)."""
+        m = self.meta.tolist()
+        return dict(num_instances=int(m[0]), max_tile_len=int(m[1]), stock_instances=(m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32),
+                    num_visible=int(m[4]), overflow=int(m[6]))
 
 
 def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_precomp, shs, filter_mode, want_aux,
-                      tile_rows=None, num_owners=0, raw_params=False, prezero_dsplat=None, gather_index=None):
+                      tile_rows=None, num_owners=0, raw_params=False, prezero_dsplat=None, gather_index=None,
+                      instance_capacity=None):
     """Run the forward through the C ABI.  Returns (image, radii, pid, pwp, point_weight, state).
     num_owners > 0 (multi-GPU band mode, see log_b200/sharded.py): also compact the ids of the Gaussians reaching the
     band `tile_rows`, grouped by owner rank; the backward then returns packed gradient rows instead of dense tensors.
@@ -171,14 +180,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
                                         _ptr(rotations), _ptr(colors_precomp), _ptr(shs), _ptr(splat), _ptr(radii),
                                         _ptr(clamped), _ptr(tile_start), _ptr(tile_cursor), _ptr(meta), st),
                 'lgr_forward_project')
-    m = (meta if band_count is None else torch.cat([meta, band_count])).tolist()   # the one host sync of the forward
-    D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
-    stock_D = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
     u32 = dict(dtype=torch.int32, device=dev)
-    inst_key = torch.empty((D,), **u32)
-    inst_val = torch.empty((D,), **u32)
-    inst_tmp = torch.empty((2 * D,), **u32) if max_len > lib.lgr_sort_smem_capacity() else None
-    sorted_ids = torch.empty((D,), **i32)
     # a sharded call owns only its rows; untouched rows stay zero so that ranks can be summed
     image = torch.empty((3, H, W), **f32) if tile_rows is None else torch.zeros((3, H, W), **f32)
     final_T = torch.empty((H, W), **f32) if tile_rows is None else torch.ones((H, W), **f32)
@@ -189,13 +191,32 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         pid = torch.empty((H, W), **i32) if tile_rows is None else torch.full((H, W), -1, **i32)
         pwp = torch.empty((H, W), **f32) if tile_rows is None else torch.zeros((H, W), **f32)
         pw = torch.zeros((n,), **f32)
-    _capi.check(lib.lgr_forward_render(ctypes.byref(view), n, D, max_len, num_long, _ptr(splat), _ptr(radii), _ptr(tile_start),
-                                       _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
-                                       _ptr(sorted_ids), _ptr(image), _ptr(final_T), _ptr(n_contrib), _ptr(pid),
-                                       _ptr(pwp), _ptr(pw), _ptr(pc), st), 'lgr_forward_render')
+    if instance_capacity:
+        if num_owners > 0:
+            raise _capi.LgrError('instance_capacity (device-sized call) is not available in band mode')
+        D, max_len, num_long, stock_D, m = int(instance_capacity), None, None, None, None
+        inst_key, inst_val = torch.empty((D,), **u32), torch.empty((D,), **u32)
+        sorted_ids = torch.empty((D,), **i32)
+        _capi.check(lib.lgr_forward_render_device_sized(ctypes.byref(view), n, D, _ptr(meta), _ptr(splat), _ptr(radii), _ptr(tile_start),
+                                                        _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(sorted_ids), _ptr(image),
+                                                        _ptr(final_T), _ptr(n_contrib), _ptr(pid), _ptr(pwp), _ptr(pw), _ptr(pc), st),
+                    'lgr_forward_render_device_sized')
+    else:
+        m = (meta if band_count is None else torch.cat([meta, band_count])).tolist()   # the one host sync of the forward
+        D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
+        stock_D = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
+        inst_key = torch.empty((D,), **u32)
+        inst_val = torch.empty((D,), **u32)
+        inst_tmp = torch.empty((2 * D,), **u32) if max_len > lib.lgr_sort_smem_capacity() else None
+        sorted_ids = torch.empty((D,), **i32)
+        _capi.check(lib.lgr_forward_render(ctypes.byref(view), n, D, max_len, num_long, _ptr(splat), _ptr(radii), _ptr(tile_start),
+                                           _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
+                                           _ptr(sorted_ids), _ptr(image), _ptr(final_T), _ptr(n_contrib), _ptr(pid),
+                                           _ptr(pwp), _ptr(pw), _ptr(pc), st), 'lgr_forward_render')
     s = RasterState()
     s.view, s.keep, s.n, s.num_instances, s.max_tile_len = view, keep, n, D, max_len
-    s.stock_instances, s.num_visible = stock_D, int(m[4])
+    s.stock_instances, s.num_visible = stock_D, (int(m[4]) if m is not None else None)
+    s.meta = meta
     s.splat, s.radii, s.clamped, s.tile_start, s.sorted_ids = splat, radii, clamped, tile_start, sorted_ids
     s.final_T, s.n_contrib, s.image, s.sh = final_T, n_contrib, image, shs is not None
     s.point_count = pc
@@ -273,7 +294,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, colors_precomp, shs, scales, rotations, settings, filter_mode, want_aux,
-                tile_rows, raw_params=False, prezero_dsplat=False):
+                tile_rows, raw_params=False, prezero_dsplat=False, instance_capacity=None, holder=None):
         dev = means3D.device
         m = _f32c(means3D, 'means3D')
         o = _f32c(opacities, 'opacities', dev)
@@ -282,7 +303,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         c = _f32c(colors_precomp, 'colors_precomp', dev)
         sh = _f32c(shs, 'shs', dev)
         image, radii, pid, pwp, pw, state = rasterize_forward(settings, m, o, sc, r, c, sh, filter_mode, want_aux, tile_rows,
-                                                              raw_params=raw_params, prezero_dsplat=prezero_dsplat)
+                                                              raw_params=raw_params, prezero_dsplat=prezero_dsplat,
+                                                              instance_capacity=instance_capacity)
+        if holder is not None:
+            holder['state'] = state
         state.image = None          # the backward re-reads the rendered image: saved below so autograd guards it
         ctx.state = state
         ctx.opacity_shape = opacities.shape
@@ -302,7 +326,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         sh = sh if ctx.has_sh else None
         ctx.state.image = image
         dm3, dm2, dop, dsc, drot, dcol, dsh = rasterize_backward(ctx.state, grad_image, m, o, sc, r, c, sh)
-        return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None, None, None
+        return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None, None, None, None, None
 
 
 class GaussianRasterizer(nn.Module):
@@ -313,6 +337,10 @@ class GaussianRasterizer(nn.Module):
         super().__init__()
         self.raster_settings = raster_settings
         self.tile_rows = None      # set by log_b200.sharded for tile-sharded multi-GPU rendering
+        # Opt-in: an int makes every call "device-sized" (no read-back of D, no host synchronisation, CUDA-graph capturable):
+        # instance buffers hold that many (Gaussian, tile) pairs; check `last_state.read_stats()['overflow']` when convenient.
+        self.instance_capacity = None
+        self.last_state = None
 
     def markVisible(self, positions):
         """Stock API: boolean mask of points in front of the near plane (view z > 0.2)."""
@@ -347,9 +375,11 @@ class GaussianRasterizer(nn.Module):
         # will a backward follow?  (decided here: inside autograd.Function.forward grad mode is always off)
         needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in
                                                      (means3D, means2D, opacities, colors_precomp, shs, scales, rotations))
+        holder = {}
         out = _RasterizeGaussians.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
                                         self.raster_settings, filter_mode, fork, self.tile_rows, raw_params,
-                                        PREZERO_DSPLAT and needs_grad)
+                                        PREZERO_DSPLAT and needs_grad, self.instance_capacity, holder)
+        self.last_state = holder.get('state')
         # fork flavour: per-Gaussian histogram of the per-pixel winners (feeds point_id_count()); kept on THIS rasterizer
         # object (LoG builds one per view, renderer.py:77), the 5-tuple of the reference is what is returned
         self.last_point_count = out[5] if fork else None

@@ -223,6 +223,12 @@ class SplatExchange:
         self.recv_radii.zero_()
         self._cache = {}
         self._in_flight = False      # a forward() whose backward() has not run yet (see forward())
+        # Device-sized rendering (lgr_forward_render_device_sized): after a first step has measured D, later steps size
+        # their instance buffers from it (+25 %) and never read anything back -- no host synchronisation inside a step,
+        # so a step can be captured in a CUDA graph.  check_overflow() tells whether a step outgrew its buffers.
+        import os
+        self.sync_free = bool(int(os.environ.get('LGR_SYNC_FREE', '1')))
+        self._inst_cap = 0
 
     def _scratch(self, name: str, shape, dtype):
         """Grow-only scratch tensors that live as long as the exchange (one step is in flight at a time, like the exchange
@@ -273,7 +279,8 @@ class SplatExchange:
         s.view_full = _make_view(settings, filter_mode, want_aux, K, None, s.keep, raw_params=raw_params)
         from .rasterizer import RANKED_BIN
         rank_rows = self._scratch('tile_rank', (self.world * self.cap, 4), torch.int32) if RANKED_BIN else None
-        s.view_band = _make_view(settings, filter_mode, want_aux, K, self.band, s.keep, raw_params=raw_params, tile_rank=rank_rows)
+        s.view_band = _make_view(settings, filter_mode, want_aux, K, self.band, s.keep, raw_params=raw_params, tile_rank=rank_rows,
+                                 pid_map=self.recv_gid)      # point_id_pixel: received row -> global Gaussian index, in the kernel
         H, W = s.view_full.image_height, s.view_full.image_width
         if H != self.image_height:
             raise ValueError('image height differs from the one the bands were cut for')
@@ -313,34 +320,65 @@ class SplatExchange:
         cursor = self._scratch('cursor', (_capi.LGR_TILE_SCRATCH_INTS * max(ntiles, 1),), torch.int32)
         meta = self.meta
         st = _stream()
-        _capi.check(lib.lgr_shard_recv_bin(ctypes.byref(v), ctypes.byref(self.layout), _ptr(self.buf), _ptr(self.dsplat_rows),
-                                           _ptr(s.tile_start), _ptr(cursor), _ptr(meta), st), 'lgr_shard_recv_bin')
-        h = self.header.tolist()                                     # the one host sync of the forward (160 bytes)
+        s.pw_rows = s.pc_rows = None
+        if s.want_aux:      # per-row aux accumulators of the blend; their used rows are zeroed by the counting kernel
+            s.pw_rows = self._scratch('pw_rows', (rows,), torch.float32)
+            s.pc_rows = self._scratch('pc_rows', (rows,), torch.int32)
+        _capi.check(lib.lgr_shard_recv_bin_aux(ctypes.byref(v), ctypes.byref(self.layout), _ptr(self.buf), _ptr(self.dsplat_rows),
+                                               _ptr(s.tile_start), _ptr(cursor), _ptr(meta), _ptr(s.pw_rows), _ptr(s.pc_rows), st),
+                    'lgr_shard_recv_bin_aux')
+        s.image = torch.zeros((3, H, W), **f32)                              # outputs: fresh every step
+        final_T = self._scratch('final_T', (H, W), torch.float32)            # written for the band's pixels, read by nobody
+        n_contrib = self._scratch('n_contrib', (H, W), torch.int32)
+        pid = pwp = None
+        if s.want_aux:
+            pid = torch.full((H, W), -1, **i32)
+            pwp = torch.zeros((H, W), **f32)
+        if self.sync_free and self._inst_cap > 0:
+            cap = self._inst_cap
+            inst_key = self._scratch('inst_key', (cap,), torch.int32)
+            inst_val = self._scratch('inst_val', (cap,), torch.int32)
+            s.sorted_ids = self._scratch('sorted_ids', (cap,), torch.int32)
+            s.num_instances, s.max_tile_len, s.num_rows, s.stock_instances = cap, None, None, None      # see stats()
+            _capi.check(lib.lgr_forward_render_device_sized(ctypes.byref(v), rows, cap, _ptr(meta), _ptr(self.recv_splat), _ptr(self.recv_radii),
+                                                            _ptr(s.tile_start), _ptr(cursor), _ptr(inst_key), _ptr(inst_val), _ptr(s.sorted_ids),
+                                                            _ptr(s.image), _ptr(final_T), _ptr(n_contrib), _ptr(pid), _ptr(pwp),
+                                                            _ptr(s.pw_rows), _ptr(s.pc_rows), st), 'lgr_forward_render_device_sized')
+            return s.image, s.radii, pid, pwp
+        h = self.header.tolist()                                     # the one host sync of a host-sized forward (160 bytes)
         m = h[32:40]
         D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
         s.num_instances, s.max_tile_len, s.num_rows = D, max_len, int(sum(h[:self.world]))
         s.stock_instances = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
+        if max_len <= lib.lgr_sort_smem_capacity():
+            self._inst_cap = max(self._inst_cap, D + D // 4 + 4096)
         inst_key = self._scratch('inst_key', (D,), torch.int32)
         inst_val = self._scratch('inst_val', (D,), torch.int32)
         inst_tmp = self._scratch('inst_tmp', (2 * D,), torch.int32) if max_len > lib.lgr_sort_smem_capacity() else None
         s.sorted_ids = self._scratch('sorted_ids', (D,), torch.int32)
-        s.image = torch.zeros((3, H, W), **f32)                              # outputs: fresh every step
-        final_T = self._scratch('final_T', (H, W), torch.float32)            # written for the band's pixels, read by nobody
-        n_contrib = self._scratch('n_contrib', (H, W), torch.int32)
-        pid = pwp = s.pw_rows = s.pc_rows = None
-        if s.want_aux:
-            pid = torch.full((H, W), -1, **i32)
-            pwp = torch.zeros((H, W), **f32)
-            s.pw_rows = self._scratch('pw_rows', (rows,), torch.float32).zero_()
-            s.pc_rows = self._scratch('pc_rows', (rows,), torch.int32).zero_()
         _capi.check(lib.lgr_forward_render(ctypes.byref(v), rows, D, max_len, num_long, _ptr(self.recv_splat), _ptr(self.recv_radii),
                                            _ptr(s.tile_start), _ptr(cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
                                            _ptr(s.sorted_ids), _ptr(s.image), _ptr(final_T), _ptr(n_contrib), _ptr(pid), _ptr(pwp),
                                            _ptr(s.pw_rows), _ptr(s.pc_rows), st), 'lgr_forward_render')
-        if pid is not None and self.band[1] > self.band[0]:         # rows -> global Gaussian indices (band rows only)
-            sub = pid[self.band[0] * 16:min(self.band[1] * 16, H)]
-            sub.copy_(torch.where(sub >= 0, self.recv_gid[sub.clamp_min(0).long()], sub))
         return s.image, s.radii, pid, pwp
+
+    def stats(self):
+        """Counters of the last received step, read back from the exchange header (synchronises): dict with num_rows,
+        num_instances, stock_instances, max_tile_len, overflow (non-zero: a device-sized step outgrew its buffers and its
+        outputs are invalid -- redo it with sync_free = False, which also re-learns the capacity)."""
+        h = self.header.tolist()
+        m = h[32:40]
+        return dict(num_rows=int(sum(h[:self.world])), num_instances=int(m[0]), max_tile_len=int(m[1]),
+                    stock_instances=(m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32), overflow=int(m[6]))
+
+    def check_overflow(self):
+        """Raise if the last device-sized step did not fit its instance buffers (one 160-byte read-back)."""
+        st = self.stats()
+        if st['overflow']:
+            self._inst_cap = 0          # the next forward goes through the host-sized path and re-learns D
+            raise RuntimeError(f'shard-mode step outgrew its device-sized buffers (flags {st["overflow"]}, D = {st["num_instances"]}, '
+                               f'longest tile list {st["max_tile_len"]}): its outputs are invalid, redo the step')
+        return st
 
     def blend_backward_and_return(self, s: ShardStep, grad_image):
         """Gradient sweep over this rank's band, then the 2D gradients (and the per-row aux outputs) go back to the ranks
@@ -355,11 +393,8 @@ class SplatExchange:
         _capi.check(lib.lgr_blend_backward(ctypes.byref(s.view_band), rows, s.num_instances, _ptr(self.recv_splat),
                                            _ptr(s.tile_start), _ptr(s.sorted_ids), _ptr(s.image), _ptr(s.grad_image),
                                            _ptr(self.dsplat_rows), st), 'lgr_blend_backward')
-        for data, width, off in ((self.dsplat_rows, _capi.LGR_GRAD_FLOATS, L.off_dsplat), (s.pw_rows, 1, L.off_weight),
-                                 (s.pc_rows, 1, L.off_pcount)):
-            if data is not None:
-                _capi.check(lib.lgr_shard_return_rows(ctypes.byref(L), _ptr(self.buf), s.num_rows, _ptr(data), width, off, peers, st),
-                            'lgr_shard_return_rows')
+        _capi.check(lib.lgr_shard_return_packed(ctypes.byref(L), _ptr(self.buf), _ptr(self.dsplat_rows), _ptr(s.pw_rows), _ptr(s.pc_rows),
+                                                peers, st), 'lgr_shard_return_packed')
 
     def gather_and_project_backward(self, s: ShardStep):
         """Sum the returned rows per local Gaussian and run the per-Gaussian backward of the local shard.  Returns
@@ -377,9 +412,9 @@ class SplatExchange:
         pw = torch.empty((n,), **f32) if s.want_aux else None
         pc = torch.empty((n,), dtype=torch.int32, device=dev) if s.want_aux else None
         st = _stream()
-        _capi.check(lib.lgr_shard_gather(ctypes.byref(s.view_full), ctypes.byref(self.layout), n, _ptr(s.splat), _ptr(s.radii),
-                                         _ptr(s.send_scratch), _ptr(self.buf), _ptr(dsplat), _ptr(pw), _ptr(pc), st),
-                    'lgr_shard_gather')
+        _capi.check(lib.lgr_shard_gather_packed(ctypes.byref(s.view_full), ctypes.byref(self.layout), n, _ptr(s.splat), _ptr(s.radii),
+                                                _ptr(s.send_scratch), _ptr(self.buf), _ptr(dsplat), _ptr(pw), _ptr(pc), st),
+                    'lgr_shard_gather_packed')
         dmeans3D, dmeans2D = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)
         dopac, dscales, drot = torch.empty((n,), **f32), torch.empty((n, 3), **f32), torch.empty((n, 4), **f32)
         dcolors = torch.empty((n, 3), **f32) if c is not None else None

@@ -372,6 +372,7 @@ inline float atomicAdd(float* p, float v) {
   return f;
 }
 inline int atomicAdd(int* p, unsigned v) { return __atomic_fetch_add(p, (int)v, __ATOMIC_RELAXED); }
+template <class T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 template <class T> inline T atomicMax(T* p, T v) {
   T o = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

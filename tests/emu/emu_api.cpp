@@ -4,16 +4,16 @@
 
 namespace lgr {
 int launch_tile_scan(int, int32_t*, int32_t*, int32_t*, bool, cudaStream_t);
-int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, const int32_t*, int32_t*,
-                        uint32_t*, uint32_t*, uint32_t*, int32_t*, cudaStream_t);
+int launch_bin_and_sort(const View&, int64_t, int64_t, int, int, const float*, const int32_t*, int32_t*, int32_t*,
+                        uint32_t*, uint32_t*, uint32_t*, int32_t*, int32_t*, cudaStream_t);
 int launch_point_compact(int64_t, const int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, cudaStream_t);
 int sort_smem_capacity();
 int launch_shard_send(const View&, const ShardLayout&, int64_t, int64_t, const float*, const int32_t*, int32_t*, void* const*,
                       cudaStream_t);
-int launch_shard_recv_count(const View&, const ShardLayout&, float*, float*, int32_t*, int32_t*, cudaStream_t);
+int launch_shard_recv_count(const View&, const ShardLayout&, float*, float*, int32_t*, int32_t*, float*, int32_t*, cudaStream_t);
 int launch_shard_return(const ShardLayout&, const float*, int64_t, const void*, int, int64_t, void* const*, cudaStream_t);
 int launch_shard_gather(const View&, const ShardLayout&, int64_t, const float*, const int32_t*, const int32_t*, const float*,
-                        float*, float*, int32_t*, cudaStream_t);
+                        float*, float*, int32_t*, int, cudaStream_t);
 }  // namespace lgr
 using namespace lgr;
 
@@ -38,8 +38,8 @@ int emu_tile_scan(const lgr_view* view, int32_t* tile_start, int32_t* tile_curso
 int emu_bin_and_sort(const lgr_view* view, int64_t n, int64_t num_instances, int32_t max_tile_len, int32_t num_long_tiles,
                      const float* splat, const int32_t* radii, const int32_t* tile_start, int32_t* tile_cursor,
                      uint32_t* inst_key, uint32_t* inst_val, uint32_t* inst_tmp, int32_t* sorted_ids) {
-  return launch_bin_and_sort(make_view(view, n), n, num_instances, max_tile_len, num_long_tiles, splat, radii, tile_start,
-                             tile_cursor, inst_key, inst_val, inst_tmp, sorted_ids, nullptr);
+  return launch_bin_and_sort(make_view(view, n), n, num_instances, max_tile_len, num_long_tiles, splat, radii, const_cast<int32_t*>(tile_start),
+                             tile_cursor, inst_key, inst_val, inst_tmp, sorted_ids, nullptr, nullptr);
 }
 
 int emu_point_compact(int64_t n, const int32_t* count, int32_t* scratch, int32_t* ids, int32_t* counts, int32_t* num) {
@@ -58,7 +58,7 @@ int emu_shard_recv_bin(const lgr_view* view, const lgr_shard_layout* layout, flo
   const int ntiles = v.gx * (v.row1 - v.row0);
   memset(tile_cursor, 0, sizeof(int32_t) * (size_t)(ntiles > 0 ? ntiles : 1) * CSTRIDE);
   memset(meta, 0, sizeof(int32_t) * LGR_META_INTS);
-  int rc = launch_shard_recv_count(v, make_layout(layout), exchange, dsplat, tile_cursor, meta, nullptr);
+  int rc = launch_shard_recv_count(v, make_layout(layout), exchange, dsplat, tile_cursor, meta, nullptr, nullptr, nullptr);
   if (rc) return rc;
   return launch_tile_scan(ntiles, tile_start, tile_cursor, meta, view->tile_rank_d != nullptr, nullptr);
 }
@@ -72,7 +72,7 @@ int emu_shard_gather(const lgr_view* view, const lgr_shard_layout* layout, int64
                      const int32_t* radii, const int32_t* send_scratch, const float* exchange, float* dsplat_local,
                      float* point_weight, int32_t* point_count) {
   return launch_shard_gather(make_view(view, n_local), make_layout(layout), n_local, splat, radii, send_scratch, exchange,
-                             dsplat_local, point_weight, point_count, nullptr);
+                             dsplat_local, point_weight, point_count, 0, nullptr);
 }
 
 }  // extern "C"

@@ -55,6 +55,10 @@ def test_band_mode_rows_and_fused_push(emulated_backend, world):
     gp.test_fused_push_route_emulated_on_one_gpu(True, world, size=(64, 80, 900))
 
 
+def test_device_sized_forward(emulated_backend):
+    gp.test_device_sized_forward_equals_host_sized(True, size=(64, 48, 400))
+
+
 def test_band_mode_with_no_binned_instance(emulated_backend):
     gp.test_band_mode_with_no_binned_instance(True)
 

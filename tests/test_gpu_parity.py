@@ -321,6 +321,44 @@ def test_band_mode_rows_reproduce_dense_gradients(built, world, size=(208, 144, 
 
 
 @pytest.mark.gpu
+def test_device_sized_forward_equals_host_sized(built, size=(160, 112, 3000)):
+    """lgr_forward_render_device_sized (no read-back of D, launch shapes independent of the data: CUDA-graph capturable) must
+    produce exactly what the host-sized call produces, forward and backward; and when the view needs more instances than
+    the caller's capacity it must say so (overflow flag) without touching memory out of bounds."""
+    from log_b200 import GaussianRasterizer
+    from util import settings_from_camera
+    W, H, n = size
+    cam = f32_camera(O.make_camera(W, H, bg=(0.1, 0.2, 0.3)))
+    sc = f32_scene(O.make_scene(n, W, H, 5.0, seed=21))
+    dev = device()
+    G = O.make_cotangent(3, H, W).to(device=dev, dtype=torch.float32)
+
+    def run(capacity):
+        rast = GaussianRasterizer(settings_from_camera(cam, dev))
+        rast.instance_capacity = capacity
+        t = {k: v.to(device=dev, dtype=torch.float32).requires_grad_(True) for k, v in sc.items()}
+        m2d = torch.zeros(n, 3, device=dev, requires_grad=True)
+        out = rast(means3D=t['means3D'], means2D=m2d, shs=None, colors_precomp=t['colors'], opacities=t['opacities'], scales=t['scales'],
+                   rotations=t['rotations'], cov3D_precomp=None)
+        (out[0] * G).sum().backward()
+        return out, {k: v.grad for k, v in t.items()}, m2d.grad, rast.last_state
+    out_h, g_h, m_h, st_h = run(None)
+    D = st_h.num_instances
+    out_d, g_d, m_d, st_d = run(D + D // 4 + 64)
+    stats = st_d.read_stats()
+    assert stats['overflow'] == 0 and stats['num_instances'] == D and stats['max_tile_len'] == st_h.max_tile_len
+    for a, b in zip(out_h, out_d):
+        assert torch.equal(a, b)
+    assert rel(m_d, m_h) < 2e-6                  # float atomics: accumulation order differs from run to run
+    for k in g_h:
+        assert rel(g_d[k], g_h[k]) < 2e-6, k
+    # capacity too small: flagged, nothing out of bounds, image = background
+    out_o, _, _, st_o = run(max(D // 3, 1))
+    assert st_o.read_stats()['overflow'] & 1
+    assert torch.isfinite(out_o[0]).all()
+
+
+@pytest.mark.gpu
 def test_band_mode_with_no_binned_instance(built, size=(64, 48, 300)):
     """Band mode when the band lists are non-empty (they follow the stock rectangle) but no splat reaches alpha >= 1/255
     anywhere (D == 0): the scatter kernel must still write the row -> id map and zero the listed accumulator rows, so the
