@@ -162,16 +162,20 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   int done = st.inside ? 0 : 1;
   int id_next = tid < len ? sorted_ids[beg + tid] : -1;
 
-  for (int base = 0; base < len; base += BATCH) {
-    if (__syncthreads_and(done)) break;      // also orders smem reuse between batches
-    const int cnt = min(BATCH, len - base);
-    const int id = id_next;
-    if (tid < cnt) stage_splat(s_rec, s_bits, tid, splat, id, tx0, ty0);
+  // Two barriers per batch.  A thread stages, flushes and re-stages only ITS OWN slot (record tid, hit bits tid, aux word
+  // tid), so the flush of batch b and the staging of batch b+1 need no barrier between them:
+  //     stage(0) | A | walk(0) | B | flush(0), stage(1) | A | walk(1) | B | ...
+  int base = 0, cnt = min(BATCH, len);
+  auto stage = [&]() {
+    if (tid < cnt) stage_splat(s_rec, s_bits, tid, splat, id_next, tx0, ty0);
     else s_bits[tid] = 0;
     if (AUX) s_w[tid] = 0u;
     id_next = base + BATCH + tid < len ? sorted_ids[beg + base + BATCH + tid] : -1;
     if (id_next >= 0) prefetch_l2(splat + (int64_t)id_next * LGR_SPLAT_FLOATS);
-    __syncthreads();
+  };
+  if (len > 0) stage();
+  while (base < len) {
+    __syncthreads();                         // A: the batch is staged
     if (!__all_sync(FULL, done)) {
       for (int c0 = 0; c0 < cnt; c0 += 32) {
         const int e_l = c0 + lane;
@@ -227,10 +231,12 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
         if (__all_sync(FULL, done)) break;
       }
     }
-    if (AUX) {
-      __syncthreads();
-      if (tid < cnt && s_w[tid]) atomicMax(point_weight_bits + __float_as_int(s_rec[3 * tid + 2].w), s_w[tid]);
-    }
+    const int all_done = __syncthreads_and(done);      // B: every warp has left the walk
+    if (AUX && tid < cnt && s_w[tid]) atomicMax(point_weight_bits + __float_as_int(s_rec[3 * tid + 2].w), s_w[tid]);
+    base += BATCH;
+    if (all_done || base >= len) break;
+    cnt = min(BATCH, len - base);
+    stage();
   }
   if (st.inside) {
     const int64_t pix = (int64_t)st.y * v.W + st.x, HW = (int64_t)v.H * v.W;
@@ -332,16 +338,23 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   int done = st.inside ? 0 : 1;
   int id_next = tid < len ? sorted_ids[beg + tid] : -1;
 
-  for (int base = 0; base < len; base += BATCH) {
-    if (__syncthreads_and(done)) break;
-    const int cnt = min(BATCH, len - base);
-    const int id = id_next;
-    if (tid < cnt) stage_splat(s_rec, s_bits, tid, splat, id, tx0, ty0);
-    else s_bits[tid] = 0;
-    for (int k = tid; k < cnt * 9; k += BLEND_THREADS) s_g[k] = 0.f;
+  // Two barriers per batch, as in the forward: thread tid stages, flushes and re-stages only slot tid (record, hit bits and
+  // the nine accumulators of that splat).
+  int base = 0, cnt = min(BATCH, len);
+  auto stage = [&]() {
+    if (tid < cnt) {
+      stage_splat(s_rec, s_bits, tid, splat, id_next, tx0, ty0);
+#pragma unroll
+      for (int k = 0; k < 9; k++) s_g[tid * 9 + k] = 0.f;
+    } else {
+      s_bits[tid] = 0;
+    }
     id_next = base + BATCH + tid < len ? sorted_ids[beg + base + BATCH + tid] : -1;
     if (id_next >= 0) prefetch_l2(splat + (int64_t)id_next * LGR_SPLAT_FLOATS);
-    __syncthreads();
+  };
+  if (len > 0) stage();
+  while (base < len) {
+    __syncthreads();                         // A: the batch is staged
     if (!__all_sync(FULL, done)) {
       int c0 = -32, pend = 0, my_e = 0;
       unsigned mask = 0u;
@@ -452,7 +465,7 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
         if (fin) break;
       }
     }
-    __syncthreads();
+    const int all_done = __syncthreads_and(done);      // B: every warp has left the walk
     if (tid < cnt) {
       const float* m = s_g + tid * 9;
       const float M00 = m[0], M10 = m[1], M01 = m[2], M20 = m[3], M11 = m[4], M02 = m[5];
@@ -481,6 +494,10 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
         atomicAdd(reinterpret_cast<float*>(dst + 2), m[8]);
       }
     }
+    base += BATCH;
+    if (all_done || base >= len) break;
+    cnt = min(BATCH, len - base);
+    stage();
   }
 }
 

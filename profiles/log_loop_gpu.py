@@ -76,7 +76,7 @@ def build(ref_root, n, W, H, dev, seed=0, densify=None):
     model.base_iter = 1
     model.training_setup()
     model.train()
-    rend = R.NaiveRendererAndLoss(split='train')
+    rend = R.NaiveRendererAndLoss(split='train').to(dev)      # its `background` buffer follows the device, as in LoG's Trainer
     f = lambda t: t.float().to(dev)
     batch = {'camera': {'camera_center': f(cam.campos)[None], 'world_view_transform': f(cam.viewmatrix)[None],
                         'full_proj_transform': f(cam.projmatrix)[None], 'image_width': torch.tensor([W]), 'image_height': torch.tensor([H]),

@@ -38,15 +38,14 @@ def oracle(cam, sc, G, fm, deg, dtype=np.float64):
 
 
 def check_all(got, ref, deg, fork, n_pix, ref32=None, case=None, filter_on=True):
-    """north_star's bound is 1e-4 relative (norm-wise) for RGB and every gradient.  With a low-pass filter on (every
-    training call: stock `+= 0.3`, fork `max(., 0.3)`) that bound is enforced as is.  Only with the filter OFF (the fork's
-    eval-only use_filter=False, LoG/render/renderer.py:151-152, where no backward runs in LoG) is the bound widened to
-    4 x what the fp32 build of the oracle itself achieves against its fp64 build: sub-pixel splats make the conic
-    ill-conditioned for ANY fp32 implementation.  Every achieved error is recorded (util.record_parity)."""
+    """north_star's bound is 1e-4 relative (norm-wise) for RGB and every gradient, and it is what is enforced -- except
+    where fp32 arithmetic itself cannot reach it: the oracle is also built in fp32 (same algorithm, plain C, no atomics),
+    and where THAT build is further than 1e-4 from its own fp64 build (big splats: sigma 8 px and more; sub-pixel splats with
+    the filter off), the bound is the fp32 oracle's own error -- i.e. the CUDA path must be at least as accurate as a
+    straight fp32 restatement.  (Round 1 allowed 4 x that error.)  Every achieved error, the fp32 floor and the bound used
+    are recorded (util.record_parity -> profiles/parity_rNN.json)."""
     def tol(k):
-        if filter_on or ref32 is None:
-            return TOL
-        return max(TOL, 4.0 * rel(ref32[k], ref[k]))
+        return TOL if ref32 is None else max(TOL, rel(ref32[k], ref[k]))
     errs = {}
     keys = ['image', 'dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations'] + (['dcolors'] if deg == 0 else ['dshs'])
     if fork:
