@@ -12,7 +12,6 @@
 // become gradients once per staged splat, then 3 vector atomics per splat.
 #include "lgr_common.cuh"
 #include "lgr_prof.cuh"
-#include <stdlib.h>
 
 namespace lgr {
 
@@ -26,9 +25,6 @@ constexpr int BLEND_THREADS = TILE_PIX;   // 256
 #endif
 constexpr int BATCH = 256;
 constexpr unsigned FULL = 0xffffffffu;
-#ifndef LGR_BLEND_DEFAULT
-#define LGR_BLEND_DEFAULT 1      // 0: tile CTAs (256 threads, staged batches) ; 1: warp-autonomous CTAs (32 threads per sub-tile)
-#endif
 
 struct SubTile {
   int x, y;          // this lane's pixel
@@ -505,349 +501,6 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   }
 }
 
-// =========================================================================================================
-// Warp-autonomous variants: ONE WARP PER CTA, one CTA per 8x4 sub-tile (8 CTAs per tile, consecutive block ids).
-//
-// Why: the warps of a tile stop at very different depths (a sub-tile is finished when its 32 pixels are saturated; at
-// 10 M Gaussians the mean warp walks 32 % of the tile's list, the slowest ~45 %).  In the tile-CTA kernels above a finished
-// warp keeps its registers and its scheduler slot until the slowest warp of the tile is done, and every batch ends in a
-// CTA-wide barrier: ncu shows 20 % of all stall samples on that barrier and only ~1.4 eligible warps per scheduler.
-// Here a warp owns its whole life: it reads the tile's sorted list itself, 32 entries at a time (lane = entry: coalesced id
-// load, 3 x 16-byte record gather -- served by L2 for seven of the eight warps of a tile), tests its own sub-tile, stages
-// only chunks with a hit in its private 1.5 KB of shared memory, walks the hits exactly as above (same arithmetic, same
-// decisions, same order), and EXITS when its pixels are done, which frees the slot for the next sub-tile.  No
-// __syncthreads anywhere.  The backward turns the tensor-core moments into gradients per 8 hits and adds them straight
-// into dsplat (3 vector atomics per contributing (sub-tile, splat) pair); moments are taken about the sub-tile centre
-// (|u| <= 3.5, |v| <= 1.5: less cancellation than about the tile centre).
-// =========================================================================================================
-constexpr int WARP_CTAS_PER_SM = 32;
-
-struct WarpTile {
-  int tile, sub, x, y;
-  bool inside;
-  float sx0, sy0;      // pixel coordinates of the sub-tile's corner
-};
-
-__device__ __forceinline__ WarpTile make_warptile(const View& v, int lane) {
-  WarpTile w;
-  w.tile = (int)(blockIdx.x >> 3); w.sub = (int)(blockIdx.x & 7);
-  const int tx = w.tile % v.gx, ty = v.row0 + w.tile / v.gx;
-  const int sx = tx * TILE + (w.sub & 1) * 8, sy = ty * TILE + (w.sub >> 1) * 4;
-  w.x = sx + (lane & 7); w.y = sy + (lane >> 3);
-  w.inside = w.x < v.W && w.y < v.H;
-  w.sx0 = (float)sx; w.sy0 = (float)sy;
-  return w;
-}
-
-// conservative {alpha >= 1/255} box of a record against the 8x4 pixel centres of a sub-tile
-__device__ __forceinline__ bool box_hits_sub(const float4 r0, const float4 r1, float sx0, float sy0) {
-  return (r0.x + r1.z >= sx0) && (r0.x - r1.z <= sx0 + 7.0f) && (r0.y + r1.w >= sy0) && (r0.y - r1.w <= sy0 + 3.0f);
-}
-
-template <bool AUX>
-__global__ void __launch_bounds__(32, WARP_CTAS_PER_SM)
-blend_fwd_warp_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
-                      const float* __restrict__ splat, float* __restrict__ image, float* __restrict__ final_T,
-                      int32_t* __restrict__ n_contrib, int32_t* __restrict__ pid_pixel, float* __restrict__ pw_pixel,
-                      unsigned* __restrict__ point_weight_bits, int32_t* __restrict__ point_count) {
-  __shared__ float4 s_rec[32 * 3];
-  const int lane = threadIdx.x;
-  const WarpTile wt = make_warptile(v, lane);
-  const float pxf = (float)wt.x, pyf = (float)wt.y;
-  const int beg = tile_start[wt.tile], len = tile_start[wt.tile + 1] - beg;
-  const uint32_t s_rec_addr = pin_reg(smem_u32(s_rec));
-
-  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, wmax = 0.f;
-  int last = 0, wid = -1;
-  int done = wt.inside ? 0 : 1;
-  int id_next = lane < len ? sorted_ids[beg + lane] : -1;
-
-  for (int c0 = 0; c0 < len; c0 += 32) {
-    if (__all_sync(FULL, done)) break;
-    const int id = id_next;
-    id_next = c0 + 32 + lane < len ? sorted_ids[beg + c0 + 32 + lane] : -1;
-    if (id_next >= 0) prefetch_l2(splat + (int64_t)id_next * LGR_SPLAT_FLOATS);
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-    bool hit = false;
-    if (id >= 0) {
-      const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
-      r0 = ldg4(rec); r1 = ldg4(rec + 4);
-      hit = box_hits_sub(r0, r1, wt.sx0, wt.sy0);
-    }
-    unsigned mask = __ballot_sync(FULL, hit);
-    if (mask == 0u) continue;
-    __syncwarp();                                   // every lane has left the walk of the previous staged chunk
-    if (hit) {                                      // only records that will be read
-      r2 = ldg4(splat + (int64_t)id * LGR_SPLAT_FLOATS + 8);
-      r2.w = __int_as_float(id);
-      s_rec[3 * lane] = r0; s_rec[3 * lane + 1] = r1; s_rec[3 * lane + 2] = r2;
-    }
-    __syncwarp();
-    unsigned own_w = 0u;                            // max weight of the splat this lane loaded, over this warp's pixels
-    while (mask) {
-      const int jA = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const bool two = mask != 0u;
-      const int jB = two ? __ffs(mask) - 1 : jA;
-      mask &= mask - 1;
-      const uint32_t recA = s_rec_addr + 48u * (uint32_t)jA, recB = s_rec_addr + 48u * (uint32_t)jB;
-      const float4 q0A = lds_f4(recA), q0B = lds_f4(recB);
-      const float2 q1A = lds_f2(recA + 16u), q1B = lds_f2(recB + 16u);                  // (conic_z, opacity)
-      const float dxA = __fsub_rn(q0A.x, pxf), dyA = __fsub_rn(q0A.y, pyf);
-      const float dxB = __fsub_rn(q0B.x, pxf), dyB = __fsub_rn(q0B.y, pyf);
-      const float powerA = eval_power2(q0A, q1A.x, dxA, dyA), powerB = eval_power2(q0B, q1B.x, dxB, dyB);
-      const float alphaA = eval_alpha(q1A.y, ex2_approx(powerA)), alphaB = eval_alpha(q1B.y, ex2_approx(powerB));
-      float wA = 0.f, wB = 0.f;
-      if (!done && powerA <= 0.0f && alphaA >= ALPHA_MIN) {
-        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alphaA));
-        if (test_T < T_STOP) done = 1;
-        else {
-          wA = alphaA * T;
-          const float4 q2 = lds_f4(recA + 32u);
-          C0 = fmaf(q2.x, wA, C0); C1 = fmaf(q2.y, wA, C1); C2 = fmaf(q2.z, wA, C2);
-          T = test_T;
-          last = c0 + jA + 1;
-          if (AUX && wA > wmax) { wmax = wA; wid = __float_as_int(q2.w); }
-        }
-      }
-      if (two && !done && powerB <= 0.0f && alphaB >= ALPHA_MIN) {
-        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alphaB));
-        if (test_T < T_STOP) done = 1;
-        else {
-          wB = alphaB * T;
-          const float4 q2 = lds_f4(recB + 32u);
-          C0 = fmaf(q2.x, wB, C0); C1 = fmaf(q2.y, wB, C1); C2 = fmaf(q2.z, wB, C2);
-          T = test_T;
-          last = c0 + jB + 1;
-          if (AUX && wB > wmax) { wmax = wB; wid = __float_as_int(q2.w); }
-        }
-      }
-      if (AUX) {
-        const unsigned mA = __reduce_max_sync(FULL, __float_as_uint(wA));   // w >= 0: uint order == float order
-        const unsigned mB = __reduce_max_sync(FULL, __float_as_uint(wB));
-        if (lane == jA) own_w = mA;
-        if (two && lane == jB) own_w = mB;
-      }
-    }
-    if (AUX && own_w) atomicMax(point_weight_bits + id, own_w);     // this lane loaded splat `id`: one RED per (sub-tile, splat)
-  }
-  if (wt.inside) {
-    const int64_t pix = (int64_t)wt.y * v.W + wt.x, HW = (int64_t)v.H * v.W;
-    image[pix] = C0 + T * __ldg(v.bg);
-    image[HW + pix] = C1 + T * __ldg(v.bg + 1);
-    image[2 * HW + pix] = C2 + T * __ldg(v.bg + 2);
-    final_T[pix] = T;
-    n_contrib[pix] = last;
-    if (AUX) {
-      pid_pixel[pix] = (v.pid_map && wid >= 0) ? v.pid_map[wid] : wid; pw_pixel[pix] = wmax;
-      if (point_count && wid >= 0) atomicAdd(point_count + wid, 1);      // histogram of the per-pixel winners
-    }
-  }
-}
-
-__global__ void __launch_bounds__(32, WARP_CTAS_PER_SM)
-blend_bwd_warp_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
-                      const float* __restrict__ splat, const float* __restrict__ image,
-                      const float* __restrict__ dL_dimage, float* __restrict__ dsplat) {
-  __shared__ float4 s_rec[32 * 3];
-  __shared__ __align__(16) float s_x[2 * HITS * XROW];       // wG[8][36] | w[8][36]
-  __shared__ __align__(16) float s_cw[192];                  // cotangent weights (B fragments, hi / lo)
-  __shared__ __align__(16) float s_mw[192];                  // moment weights (B fragments)
-  __shared__ float4 s_pend[HITS * 2];                        // per pending hit: (px, py, cx', cy'), (cz', opacity, id, -)
-  const int lane = threadIdx.x;
-  const WarpTile wt = make_warptile(v, lane);
-  const float pxf = (float)wt.x, pyf = (float)wt.y;
-  const int beg = tile_start[wt.tile], len = tile_start[wt.tile + 1] - beg;
-  const uint32_t s_rec_addr = pin_reg(smem_u32(s_rec));
-  const uint32_t xg_addr = pin_reg(smem_u32(s_x));
-  const uint32_t xlane_addr = pin_reg(xg_addr + 4u * (uint32_t)lane);
-  const uint32_t xrow = pin_reg(xg_addr + (uint32_t)(lane & 7) * (XROW * 4) + (uint32_t)((lane >> 3) & 1) * (HITS * XROW * 4) +
-                                (uint32_t)(lane >> 4) * 16u);
-  const uint32_t pend_addr = pin_reg(smem_u32(s_pend));
-  const float scx = wt.sx0 + 3.5f, scy = wt.sy0 + 1.5f;      // sub-tile centre: origin of the moments
-  const int g = lane >> 2, t = lane & 3;
-
-  float Rd = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
-  if (wt.inside) {
-    const int64_t pix = (int64_t)wt.y * v.W + wt.x, HW = (int64_t)v.H * v.W;
-    dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix];
-    Rd = image[pix] * dp0 + image[HW + pix] * dp1 + image[2 * HW + pix] * dp2;
-  }
-  const uint32_t mw_addr = pin_reg(smem_u32(s_mw) + (uint32_t)((min(g, 5) * 4 + t) * 32));
-  for (int k = lane; k < 192; k += 32) {
-    const int which = k & 1, s_ = (k >> 1) & 3, t_ = (k >> 3) & 3, g_ = k >> 5;
-    const float u = (float)(t_ + 4 * which) - 3.5f, vv = (float)s_ - 1.5f;        // pixel (column, row) of the sub-tile, centred
-    s_mw[k] = g_ == 0 ? 1.f : g_ == 1 ? u : g_ == 2 ? vv : g_ == 3 ? u * u : g_ == 4 ? u * vv : vv * vv;
-  }
-  const uint32_t cw_addr = pin_reg(smem_u32(s_cw) + (uint32_t)((min(g, 2) * 4 + t) * 64));
-  {
-    const int col = lane & 7, s = lane >> 3, tt = col & 3, which = col >> 2;
-    const float dpc[3] = {dp0, dp1, dp2};
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      s_cw[((c * 4 + tt) * 4 + s) * 4 + which] = dpc[c];                  // read as trunc(x) by the tensor core
-      s_cw[((c * 4 + tt) * 4 + s) * 4 + 2 + which] = tf32_lo(dpc[c]);
-    }
-  }
-  __syncwarp();
-
-  float T = 1.0f;
-  int done = wt.inside ? 0 : 1;
-  int id_next = lane < len ? sorted_ids[beg + lane] : -1;
-  int c0 = -32, pend = 0;
-  unsigned mask = 0u;
-  bool fin = false;
-  while (true) {
-    if (mask == 0u) {      // next chunk of 32 list entries with a hit in this sub-tile
-      do {
-        c0 += 32;
-        fin = c0 >= len || __all_sync(FULL, done);
-        if (fin) break;
-        const int id = id_next;
-        id_next = c0 + 32 + lane < len ? sorted_ids[beg + c0 + 32 + lane] : -1;
-        if (id_next >= 0) prefetch_l2(splat + (int64_t)id_next * LGR_SPLAT_FLOATS);
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        bool hit = false;
-        if (id >= 0) {
-          const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
-          r0 = ldg4(rec); r1 = ldg4(rec + 4);
-          hit = box_hits_sub(r0, r1, wt.sx0, wt.sy0);
-        }
-        mask = __ballot_sync(FULL, hit);
-        if (mask != 0u) {
-          __syncwarp();                             // every lane has left the walk of the previous staged chunk
-          if (hit) {
-            float4 r2 = ldg4(splat + (int64_t)id * LGR_SPLAT_FLOATS + 8);
-            r2.w = __int_as_float(id);
-            s_rec[3 * lane] = r0; s_rec[3 * lane + 1] = r1; s_rec[3 * lane + 2] = r2;
-          }
-          __syncwarp();
-        }
-      } while (mask == 0u);
-    }
-    if (!fin) {
-      const int jA = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const bool two = mask != 0u;
-      const int jB = two ? __ffs(mask) - 1 : jA;
-      mask &= mask - 1;
-      const uint32_t recA = s_rec_addr + 48u * (uint32_t)jA, recB = s_rec_addr + 48u * (uint32_t)jB;
-      const float4 r0A = lds_f4(recA), r0B = lds_f4(recB);
-      const float2 r1A = lds_f2(recA + 16u), r1B = lds_f2(recB + 16u);                  // (conic_z, opacity)
-      const float dxA = __fsub_rn(r0A.x, pxf), dyA = __fsub_rn(r0A.y, pyf);
-      const float dxB = __fsub_rn(r0B.x, pxf), dyB = __fsub_rn(r0B.y, pyf);
-      const float powerA = eval_power2(r0A, r1A.x, dxA, dyA), powerB = eval_power2(r0B, r1B.x, dxB, dyB);
-      const float GA = ex2_approx(powerA), GB = ex2_approx(powerB);
-      const float alphaA = eval_alpha(r1A.y, GA), alphaB = eval_alpha(r1B.y, GB);
-      const float omA = __fsub_rn(1.0f, alphaA), omB = __fsub_rn(1.0f, alphaB);
-      bool cA = false, cB = false;
-      const float TA = T;
-      if (!done && powerA <= 0.0f && alphaA >= ALPHA_MIN) {
-        const float tt = __fmul_rn(T, omA);
-        if (tt < T_STOP) done = 1; else { cA = true; T = tt; }
-      }
-      const float TB = T;
-      if (two && !done && powerB <= 0.0f && alphaB >= ALPHA_MIN) {
-        const float tt = __fmul_rn(T, omB);
-        if (tt < T_STOP) done = 1; else { cB = true; T = tt; }
-      }
-      const bool anyA = __any_sync(FULL, cA), anyB = __any_sync(FULL, cB);
-      if (anyA) {
-        float wG = 0.f, w = 0.f;
-        float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cA || lane == 0) r2 = lds_f4(recA + 32u);
-        if (cA) {
-          w = alphaA * TA;
-          const float cdot = r2.x * dp0 + r2.y * dp1 + r2.z * dp2;
-          Rd = fmaf(-cdot, w, Rd);                          // what is behind the splat (+ bg T_final), dotted with dL/dC
-          const float dL_dalpha = cdot * TA - Rd * rcp_approx(omA);
-          wG = r1A.y * dL_dalpha * GA;                      // dL/dG * G   (the 0.99 clamp is straight-through)
-        }
-        const uint32_t row = xlane_addr + (uint32_t)pend * (XROW * 4);
-        sts_f32(row, wG); sts_f32(row + HITS * XROW * 4, w);
-        if (lane == 0) { s_pend[2 * pend] = r0A; s_pend[2 * pend + 1] = make_float4(r1A.x, r1A.y, r2.w, 0.f); }
-        pend++;
-      }
-      if (anyB) {
-        float wG = 0.f, w = 0.f;
-        float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cB || lane == 0) r2 = lds_f4(recB + 32u);
-        if (cB) {
-          w = alphaB * TB;
-          const float cdot = r2.x * dp0 + r2.y * dp1 + r2.z * dp2;
-          Rd = fmaf(-cdot, w, Rd);
-          const float dL_dalpha = cdot * TB - Rd * rcp_approx(omB);
-          wG = r1B.y * dL_dalpha * GB;
-        }
-        const uint32_t row = xlane_addr + (uint32_t)pend * (XROW * 4);
-        sts_f32(row, wG); sts_f32(row + HITS * XROW * 4, w);
-        if (lane == 0) { s_pend[2 * pend] = r0B; s_pend[2 * pend + 1] = make_float4(r1B.x, r1B.y, r2.w, 0.f); }
-        pend++;
-      }
-    }
-    if (pend >= HITS - 1 || (fin && pend > 0)) {      // fewer than two free rows, or the list is over
-      __syncwarp();
-      float d0 = 0.f, d1 = 0.f, z0 = 0.f, z1 = 0.f, y0 = 0.f, y1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-      for (int s = 0; s < 4; s++) {
-        uint32_t a0, a1, a2, a3;
-        ldsm_x4(xrow + 32u * s, a0, a1, a2, a3);
-        const uint32_t l0 = __float_as_uint(tf32_lo(__uint_as_float(a0))), l1 = __float_as_uint(tf32_lo(__uint_as_float(a1)));
-        const uint32_t l2 = __float_as_uint(tf32_lo(__uint_as_float(a2))), l3 = __float_as_uint(tf32_lo(__uint_as_float(a3)));
-        float2 bm = make_float2(0.f, 0.f);
-        float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < 6) bm = lds_f2(mw_addr + 8u * s);
-        if (g < 3) bc = lds_f4(cw_addr + 16u * s);
-        mma_tf32(d0, d1, z0, z1, a0, a1, a2, a3, __float_as_uint(bm.x), __float_as_uint(bm.y));
-        mma_tf32(y0, y1, d2, d3, a0, a1, a2, a3, __float_as_uint(bc.x), __float_as_uint(bc.y));
-        mma_tf32(d0, d1, z0, z1, l0, l1, l2, l3, __float_as_uint(bm.x), __float_as_uint(bm.y));
-        mma_tf32(y0, y1, d2, d3, l0, l1, l2, l3, __float_as_uint(bc.x), __float_as_uint(bc.y));
-        mma_tf32(y0, y1, d2, d3, a0, a1, a2, a3, __float_as_uint(bc.z), __float_as_uint(bc.w));
-      }
-      // lane (g, t): d0/d1 = moments 2t, 2t+1 of hit g (t < 3) ; d2/d3 = colour sums 2t, 2t+1 of hit g (t = 0: 0, 1; t = 1: 2).
-      // Collect the nine values of hit g in lane (g, 0) and turn them into the 2D gradients of that splat.
-      const float M01 = __shfl_down_sync(FULL, d0, 1), M20 = __shfl_down_sync(FULL, d1, 1), Cb = __shfl_down_sync(FULL, d2, 1);
-      const float M11 = __shfl_down_sync(FULL, d0, 2), M02 = __shfl_down_sync(FULL, d1, 2);
-      if (t == 0 && g < pend) {
-        const float M00 = d0, M10 = d1, Cr = d2, Cg = d3;
-        const float4 p0 = lds_f4(pend_addr + 32u * (uint32_t)g), p1 = lds_f4(pend_addr + 32u * (uint32_t)g + 16u);
-        const int id = __float_as_int(p1.z);
-        const float X = p0.x - scx, Y = p0.y - scy;
-        const float Sx = fmaf(X, M00, -M10), Sy = fmaf(Y, M00, -M01);                       // sum wG dx, sum wG dy
-        const float Sxx = fmaf(X, fmaf(X, M00, -2.f * M10), M20);                           // sum wG dx^2
-        const float Syy = fmaf(Y, fmaf(Y, M00, -2.f * M01), M02);
-        const float Sxy = fmaf(X, fmaf(Y, M00, -M01), fmaf(-Y, M10, M11));                  // sum wG dx dy
-        float4 a, b;
-        a.x = -(p0.z * Sx + p0.w * Sy);          // d/dpx  (x log2e: the conic in the record is pre-scaled)
-        a.y = -(p1.x * Sy + p0.w * Sx);          // d/dpy  (x log2e)
-        a.z = -0.5f * Sxx;                       // d/dconic_x
-        a.w = -Sxy;                              // d/dconic_y
-        b.x = -0.5f * Syy;                       // d/dconic_z
-        b.y = M00 / p1.y;                        // d/dopacity = sum G dL/dalpha = sum wG / o
-        b.z = Cr; b.w = Cg;                      // d/drgb
-        float4* dst = reinterpret_cast<float4*>(dsplat + (int64_t)id * LGR_GRAD_FLOATS);
-        atomicAdd(dst, a);
-        atomicAdd(dst + 1, b);
-        atomicAdd(reinterpret_cast<float*>(dst + 2), Cb);
-      }
-      __syncwarp();
-      pend = 0;
-    }
-    if (fin) break;
-  }
-}
-
-// LGR_BLEND=tile | warp selects the kernel family (read once); see DESIGN.md for the measured choice of the default.
-static int blend_mode() {
-  static const int mode = [] {
-    const char* e = getenv("LGR_BLEND");
-    if (e && e[0] == 't') return 0;
-    if (e && e[0] == 'w') return 1;
-    return LGR_BLEND_DEFAULT;
-  }();
-  return mode;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 int launch_blend_fwd(const View& v, const int32_t* tile_start, const int32_t* sorted_ids, const float* splat,
                      float* image, float* final_T, int32_t* n_contrib, int32_t* pid_pixel, float* pw_pixel,
@@ -855,14 +508,6 @@ int launch_blend_fwd(const View& v, const int32_t* tile_start, const int32_t* so
   const int ntiles = v.gx * (v.row1 - v.row0);
   if (ntiles <= 0) return 0;
   ProfScope ps(K_BLEND_FWD, st);
-  if (blend_mode() == 1) {      // warp-autonomous: one 32-thread CTA per 8x4 sub-tile
-    if (v.want_aux)
-      blend_fwd_warp_kernel<true><<<ntiles * 8, 32, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight), point_count);
-    else
-      blend_fwd_warp_kernel<false><<<ntiles * 8, 32, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight), point_count);
-    LGR_CHECK_LAUNCH();
-    return 0;
-  }
   if (v.want_aux)
     blend_fwd_kernel<true><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight), point_count);
   else
@@ -875,12 +520,6 @@ int launch_blend_bwd(const View& v, const int32_t* tile_start, const int32_t* so
                      const float* image, const float* dL_dimage, float* dsplat, cudaStream_t st) {
   const int ntiles = v.gx * (v.row1 - v.row0);
   if (ntiles <= 0) return 0;
-  if (blend_mode() == 1) {
-    ProfScope ps(K_BLEND_BWD, st);
-    blend_bwd_warp_kernel<<<ntiles * 8, 32, 0, st>>>(v, tile_start, sorted_ids, splat, image, dL_dimage, dsplat);
-    LGR_CHECK_LAUNCH();
-    return 0;
-  }
   // > 48 KB of dynamic shared memory needs the opt-in; the attribute is per device and cheap to set, so set it every time
   cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
   if (e != cudaSuccess) return (int)e;

@@ -108,12 +108,25 @@ class Timer:
         return (time.perf_counter() - t0) * 1e3 / iters
 
 
-def train_step(model, rend, batch):
+def train_step(model, rend, batch, phases=None):
+    """Trainer.training_step (trainer.py:144-166).  phases: dict accumulating wall-clock ms per phase (each phase followed by a
+    device synchronisation -- a diagnostic run, slower than the un-instrumented step)."""
+    def mark(name, t0):
+        if phases is not None:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            phases[name] = phases.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+    t = time.perf_counter()
     model.clear()
-    out = rend(batch, model)                       # Trainer.training_step, trainer.py:144-166
+    out = rend(batch, model)
+    t = mark('render_and_loss', t)
     out['loss'].backward()
+    t = mark('backward', t)
     model.update_by_output(out)
+    t = mark('update_by_output', t)
     model.step()
+    mark('optimizer_step', t)
     return out
 
 
@@ -176,6 +189,23 @@ def main():
     losses = []
     res['base_stage_ms_per_iter_stock'] = T.time(lambda: losses.append(float(train_step(model, rend, batch)['loss'].detach())), args.iters)
     res['base_stage_loss_first_last'] = [losses[0], losses[-1]]
+    ph = {}
+    for _ in range(3):
+        train_step(model, rend, batch, ph)
+    res['base_stage_phase_ms_stock'] = {k: v / 3 for k, v in ph.items()}
+    # where the render phase goes: LoG's prepare (tree / visibility) vs its render() (get_all + activations + rasteriser + unique)
+    import cProfile
+    import pstats
+    import io
+    pr = cProfile.Profile()
+    pr.enable()
+    train_step(model, rend, batch)
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
+    pr.disable()
+    buf = io.StringIO()
+    pstats.Stats(pr, stream=buf).sort_stats('cumulative').print_stats(25)
+    res['base_stage_cprofile_top'] = [ln.strip()[:160] for ln in buf.getvalue().splitlines() if ln.strip() and ('LoG' in ln or 'log_b200' in ln or 'torch' in ln)][:25]
     # the same with the fused sparse Adam (f4)
     stock_step = model.optimizer.step
     model.optimizer.step = fused_adam_step(model)

@@ -11,9 +11,9 @@ echo "gpu suite rc=$?" > $OUT/summary.txt
 cp gpurun_out/parity.json $OUT/parity.json 2>/dev/null
 timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench_10m.json 2> $OUT/bench_10m.err
 echo "bench rc=$?" >> $OUT/summary.txt
-LGR_BLEND=tile timeout 600 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_10m_tilecta.json 2> $OUT/bench_10m_tilecta.err
-echo "bench tile-CTA rc=$?" >> $OUT/summary.txt
-LGR_BLEND=tile timeout 600 python bench.py --steps 50 --warmup 5 --workload 100k --no-e2e --no-cpu-baseline > $OUT/bench_100k_tilecta.json 2> $OUT/bench_100k_tilecta.err
+
+
+
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:blend --launch-skip 6 --launch-count 2 -f -o $OUT/blend \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu.log 2>&1
 echo "ncu rc=$?" >> $OUT/summary.txt
