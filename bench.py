@@ -37,9 +37,10 @@ WORKLOADS = {
     '10m': (10_000_000, 1920, 1080, 1.5, 0),     # config 3 (the metric's configuration): precomputed colour, as LoG feeds
     '100k': (100_000, 1920, 1080, 8.0, 3),       # config 1: SH degree 3 in-kernel
     '1k': (1_000, 256, 256, 3.0, 0),             # config 0 (plumbing)
+    'big300k': (300_000, 1920, 1080, 35.0, 0),   # diagnostic: LoG-at-initialisation regime (kNN-sized splats, sigma ~35 px, tile lists > 4096)
     '50m4k': (50_000_000, 3840, 2160, 1.5, 0),   # config 4 (city scale, 4K): meant for `LGR_MULTI=shard` on 8 GPUs; not yet run
 }
-CPU_SAMPLE = {'10m': 1_000_000, '100k': 100_000, '1k': 1_000, '50m4k': 1_000_000}   # Gaussians in the bounded CPU sample
+CPU_SAMPLE = {'10m': 1_000_000, '100k': 100_000, '1k': 1_000, '50m4k': 1_000_000, 'big300k': 20_000}   # Gaussians in the bounded CPU sample
 
 
 def peaks():

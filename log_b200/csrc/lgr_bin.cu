@@ -72,34 +72,41 @@ __global__ void __launch_bounds__(SCATTER_THREADS)
 bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int32_t* __restrict__ radii,
                    const int32_t* __restrict__ tile_start, int32_t* __restrict__ cursor, uint32_t* __restrict__ inst_key,
                    uint32_t* __restrict__ inst_val, int64_t capacity /* of inst_key / inst_val: stores beyond it are dropped */) {
+  // No early return: big splats are scattered by the whole warp below (convergent ballots / shuffles).
   int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
-  if (i >= n) return;
-  if (v.num_owners > 0) {      // band mode: slot i of the per-CTA id lists written by project_fwd (256 ids per CTA)
+  bool live = i < n;
+  if (live && v.num_owners > 0) {      // band mode: slot i of the per-CTA id lists written by project_fwd (256 ids per CTA)
     const int b = (int)(i / 256), sl = (int)(i % 256);
-    if (sl >= v.band_blk[b]) return;
-    const int id = v.band_ids[i];
-    v.band_rows[v.band_blk[v.band_blocks + b] + sl] = id;      // dense packed-row -> id map for the backward
-    if (v.band_dsplat) {                                       // the sweep's accumulators: zero only the listed rows
-      float4* z = reinterpret_cast<float4*>(v.band_dsplat + (int64_t)id * LGR_GRAD_FLOATS);
-      z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sl >= v.band_blk[b]) live = false;
+    else {
+      const int id = v.band_ids[i];
+      v.band_rows[v.band_blk[v.band_blocks + b] + sl] = id;      // dense packed-row -> id map for the backward
+      if (v.band_dsplat) {                                       // the sweep's accumulators: zero only the listed rows
+        float4* z = reinterpret_cast<float4*>(v.band_dsplat + (int64_t)id * LGR_GRAD_FLOATS);
+        z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      i = id;
     }
-    i = id;
   }
-  const int rad = radii[i];
-  if (rad <= 0) return;
-  if (v.num_owners == 0 && v.band_dsplat) {      // optional: zero the backward's accumulator row of every visible Gaussian here,
+  int rad = 0;
+  if (live) { rad = radii[i]; live = rad > 0; }
+  if (live && v.num_owners == 0 && v.band_dsplat) {      // optional: zero the backward's accumulator row of every visible Gaussian here,
     float4* z = reinterpret_cast<float4*>(v.band_dsplat + i * LGR_GRAD_FLOATS);      // instead of a separate full-size memset
     z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const float4 r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);
-  const float4 r1 = ldg4(splat + i * LGR_SPLAT_FLOATS + 4);
-  if (!(r1.z > 0.f)) return;     // hx == 0: opacity below 1/255, contributes nowhere
-  const float depth = __ldg(splat + i * LGR_SPLAT_FLOATS + 11);
-  int x0, y0, x1, y1;
-  tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
-  const uint32_t key = __float_as_uint(depth);   // depth > 0.2 : IEEE bits are order preserving
-  const int w = x1 - x0, cnt = w * (y1 - y0);
-  if (cnt <= 4) {
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  uint32_t key = 0;
+  if (live) {
+    const float4 r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);
+    const float4 r1 = ldg4(splat + i * LGR_SPLAT_FLOATS + 4);
+    live = r1.z > 0.f;      // hx == 0: opacity below 1/255, contributes nowhere
+    if (live) {
+      key = __float_as_uint(__ldg(splat + i * LGR_SPLAT_FLOATS + 11));   // depth > 0.2 : IEEE bits are order preserving
+      tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
+    }
+  }
+  const int w = x1 - x0, cnt = live ? w * (y1 - y0) : 0;
+  if (cnt > 0 && cnt <= 4) {
     int t[4], slot[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -121,15 +128,25 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
         const int pos = __ldg(tile_start + t[k]) + slot[k];
         if (pos < capacity) { inst_key[pos] = key; inst_val[pos] = (uint32_t)i; }
       }
-    return;
   }
-  const int big = v.tile_rank ? 1 : 0;      // ranked: big splats sit behind the cursor[t][0] small ones, slots from cursor[t][1]
-  for (int ty = y0; ty < y1; ty++)
-    for (int tx = x0; tx < x1; tx++) {
-      const int t = (ty - v.row0) * v.gx + tx;
+  // Big splats (more than 4 tiles), one at a time by the whole warp: lane l takes tiles l, l+32, ... of the rectangle, so a
+  // splat covering hundreds of tiles costs a few rounds of overlapping atomics instead of a serial chain in one lane.
+  // ranked: they sit behind the cursor[t][0] small splats of the tile and take their slots from cursor[t][1].
+  const int lane = threadIdx.x & 31, big = v.tile_rank ? 1 : 0;
+  unsigned todo = __ballot_sync(0xffffffffu, cnt > 4);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bw = __shfl_sync(0xffffffffu, w, src), bcnt = __shfl_sync(0xffffffffu, cnt, src);
+    const uint32_t bkey = __shfl_sync(0xffffffffu, key, src);
+    const uint32_t bid = (uint32_t)__shfl_sync(0xffffffffu, (int)i, src);
+    for (int k = lane; k < bcnt; k += 32) {
+      const int t = (by0 + k / bw - v.row0) * v.gx + bx0 + k % bw;
       const int pos = tile_start[t] + (big ? cursor[t * CSTRIDE] : 0) + atomicAdd(cursor + t * CSTRIDE + big, 1);
-      if (pos < capacity) { inst_key[pos] = key; inst_val[pos] = (uint32_t)i; }
+      if (pos < capacity) { inst_key[pos] = bkey; inst_val[pos] = bid; }
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -380,10 +397,13 @@ tile_sort_kernel(const int32_t* __restrict__ tile_list /* nullptr: tile = blockI
       if (len > 1 && !sort_tile_msd(kA, vA, kB, vB, len, msd)) __trap();
       for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
     } else {
+      // Lists beyond the shared-memory capacity: the same MSD partition + rank counting, operating on global memory
+      // (inst_* in place, tmp_* scratch; ~5 passes over the list per partition level, served by L1 / L2).  Only if its
+      // work stack overflows (adversarially clustered depths) does the stable LSD radix sort take over.
       uint32_t* kA = inst_key + beg; uint32_t* vA = inst_val + beg;
       uint32_t* kB = tmp + 2 * (int64_t)beg; uint32_t* vB = kB + len;
       __syncthreads();
-      sort_tile(kA, vA, kB, vB, len, id_bits, whist);
+      if (!sort_tile_msd(kA, vA, kB, vB, len, msd)) sort_tile(kA, vA, kB, vB, len, id_bits, whist);
       for (int i = threadIdx.x; i < len; i += SORT_THREADS) sorted_ids[beg + i] = (int32_t)vA[i];
     }
     __syncthreads();      // the shared buffers are reused by the next tile of this CTA

@@ -213,31 +213,44 @@ __device__ __forceinline__ void tile_rect_tight(float px, float py, int rad, flo
   if (y1 < y0) y1 = y0;
 }
 
-// Count the tiles [x0,x1) x [y0,y1) of one splat (row = its index in the splat array).  Per tile two counters share one
-// 128-byte line: [0] splats covering <= 4 tiles, [1] the others.  With View::tile_rank the small splats take their slots
-// here (returning atomics, all issued before the first use so that the L2 round trips overlap) and the scatter kernel
-// needs no atomic for them; big splats are only counted and take their slots behind the small ones in the scatter.
-// Without tile_rank everything is counted in [0] and the scatter takes every slot.
-__device__ __forceinline__ void count_tiles(const View& v, int32_t* __restrict__ tile_count, int64_t row, int x0, int y0, int x1,
-                                            int y1) {
+// Tile counting.  Per tile two counters share one 128-byte line: [0] splats covering <= 4 tiles, [1] the others.
+// Small splats (count_small_tiles, per thread): with View::tile_rank they take their slots here (returning atomics, all
+// issued before the first use so that the L2 round trips overlap) and the scatter kernel needs no atomic for them; without
+// tile_rank they are only counted.  Big splats are handled by the WHOLE WARP (warp_count_big_tiles / the scatter's twin):
+// a splat covering hundreds of tiles would otherwise keep one lane in a serial loop of that many atomics while 31 lanes
+// idle (LoG right after initialisation, before the tree has refined anything: splats of tens of pixels).
+__device__ __forceinline__ bool count_small_tiles(const View& v, int32_t* __restrict__ tile_count, int64_t row, int x0, int y0, int x1,
+                                                  int y1) {      // returns true when the splat is a big one (not counted here)
   const int w = x1 - x0, cnt = w * (y1 - y0);
+  if (cnt > 4) return true;
   if (v.tile_rank == nullptr) {
-    for (int ty = y0; ty < y1; ty++)
-      for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE, 1);
-    return;
+    for (int k = 0; k < cnt; k++) atomicAdd(tile_count + ((y0 + k / w - v.row0) * v.gx + x0 + k % w) * CSTRIDE, 1);
+    return false;
   }
-  if (cnt <= 4) {
-    int r[4];
+  int r[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      r[k] = -1;
-      if (k < cnt) r[k] = atomicAdd(tile_count + ((y0 + k / max(w, 1) - v.row0) * v.gx + x0 + k % max(w, 1)) * CSTRIDE, 1);
-    }
-    *reinterpret_cast<int4*>(v.tile_rank + 4 * row) = make_int4(r[0], r[1], r[2], r[3]);
-    return;
+  for (int k = 0; k < 4; k++) {
+    r[k] = -1;
+    if (k < cnt) r[k] = atomicAdd(tile_count + ((y0 + k / max(w, 1) - v.row0) * v.gx + x0 + k % max(w, 1)) * CSTRIDE, 1);
   }
-  for (int ty = y0; ty < y1; ty++)
-    for (int tx = x0; tx < x1; tx++) atomicAdd(tile_count + ((ty - v.row0) * v.gx + tx) * CSTRIDE + 1, 1);
+  *reinterpret_cast<int4*>(v.tile_rank + 4 * row) = make_int4(r[0], r[1], r[2], r[3]);
+  return false;
+}
+
+// All 32 lanes must call this (convergent).  big: this lane holds a splat with more than 4 tiles, rectangle [x0,x1) x [y0,y1).
+__device__ __forceinline__ void warp_count_big_tiles(const View& v, int32_t* __restrict__ tile_count, bool big, int x0, int y0, int x1,
+                                                     int y1) {
+  const int lane = threadIdx.x & 31;
+  const int slot = v.tile_rank ? 1 : 0;
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
+    const int w = bx1 - bx0, cnt = w * (by1 - by0);
+    for (int k = lane; k < cnt; k += 32) atomicAdd(tile_count + ((by0 + k / w - v.row0) * v.gx + bx0 + k % w) * CSTRIDE + slot, 1);
+  }
 }
 
 // ---- SH basis (LoG/model/sh_utils.py:31-58, DC first) ---------------------------------------------------

@@ -120,6 +120,8 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     work = threadIdx.x < total;
     i = work ? (int64_t)blockIdx.x * PROJ_THREADS + sSurv[threadIdx.x] : n;
   }
+  bool big_splat = false;      // covers more than 4 tiles: counted by the whole warp after the divergent part
+  int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
   // gather-fused call (lgr_view.gather_index_d): row i of every output is Gaussian gather[i] of the input tables
   const int64_t src = (v.gather && work) ? v.gather[i] : i;
   if (work) {
@@ -208,7 +210,8 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
         r2 = make_float4(rgb[0], rgb[1], rgb[2], cv.t[2]);
         if (reach) {
           tile_rect_tight(px, py, rad, hx, hy, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
-          count_tiles(v, tile_count, i, x0, y0, x1, y1);
+          big_splat = count_small_tiles(v, tile_count, i, x0, y0, x1, y1);
+          bx0 = x0; by0 = y0; bx1 = x1; by1 = y1;
         }
       }
     }
@@ -221,6 +224,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   } else if (i < n) {
     radii[i] = 0;      // only reachable outside band mode (i >= n otherwise)
   }
+  warp_count_big_tiles(v, tile_count, big_splat, bx0, by0, bx1, by1);
   if (v.num_owners > 0) {      // atomics-free compaction of the ids that reach the band into this CTA's segment
     __shared__ int sCnt[PROJ_THREADS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -183,6 +183,8 @@ shard_recv_count_kernel(View v, ShardLayout L, float* __restrict__ xbuf, float* 
   int32_t* radii = reinterpret_cast<int32_t*>(xbuf + L.off_radii);
   unsigned stock = 0;
   int vis = 0;
+  bool big_splat = false;
+  int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
   if (slot < total) {
     const int s = (int)(slot / L.cap);
     const int64_t j = slot - (int64_t)s * L.cap;
@@ -198,13 +200,15 @@ shard_recv_count_kernel(View v, ShardLayout L, float* __restrict__ xbuf, float* 
       stock = (unsigned)((x1 - x0) * max(0, min(y1, v.row1) - max(y0, v.row0)));
       vis = 1;
       tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
-      count_tiles(v, tile_count, slot, x0, y0, x1, y1);
+      big_splat = count_small_tiles(v, tile_count, slot, x0, y0, x1, y1);
+      bx0 = x0; by0 = y0; bx1 = x1; by1 = y1;
       float4* z = reinterpret_cast<float4*>(dsplat + slot * LGR_GRAD_FLOATS);
       z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pw_rows) pw_rows[slot] = 0.f;      // per-row aux accumulators of the blend: only used rows are ever read back
       if (pc_rows) pc_rows[slot] = 0;
     }
   }
+  warp_count_big_tiles(v, tile_count, big_splat, bx0, by0, bx1, by1);
   const unsigned st_w = __reduce_add_sync(FULLMASK, stock);
   const int vis_w = __reduce_add_sync(FULLMASK, vis);
   if ((threadIdx.x & 31) == 0) { sStock[threadIdx.x >> 5] = st_w; sVis[threadIdx.x >> 5] = vis_w; }

@@ -35,21 +35,23 @@ class AD(dict):
     __getattr__ = dict.__getitem__
 
 
-def knn_dist2(x, chunk=2048):
-    """Stand-in for simple_knn.distCUDA2 (CUDA-only third party, used once for the initial scales, LoG/utils/file.py:88):
-    mean squared distance to the 3 nearest neighbours, chunked."""
-    out = torch.empty(x.shape[0], device=x.device)
-    for a in range(0, x.shape[0], chunk):
-        d = torch.cdist(x[a:a + chunk], x)
-        d[torch.arange(d.shape[0]), torch.arange(a, a + d.shape[0])] = float('inf')
-        out[a:a + chunk] = (d.topk(3, largest=False).values ** 2).mean(-1)
-    return out
+def knn_dist2(x, spacing):
+    """Stand-in for simple_knn.distCUDA2 (CUDA-only third party, used once for the initial scales, LoG/utils/file.py:88-89):
+    mean squared distance to the 3 nearest neighbours.  The synthetic cloud is uniform in the view frustum with mean spacing
+    `spacing`, for which that distance is ~0.6 x spacing; a seeded log-normal jitter stands for the local density variation."""
+    g = torch.Generator().manual_seed(3)
+    jitter = torch.exp(0.25 * torch.randn(x.shape[0], generator=g)).to(x.device)
+    return (0.6 * spacing * jitter) ** 2
 
 
 def build(ref_root, n, W, H, dev, seed=0, densify=None):
     from oracle import torch_dense as O
     knn, knn_c = types.ModuleType('simple_knn'), types.ModuleType('simple_knn._C')
-    knn_c.distCUDA2 = lambda x: knn_dist2(x.to(dev)).to(x.device)
+    z_near, z_far = 4.0, 12.0
+    cam = O.make_camera(W, H)
+    volume = 4.0 * cam.tanfovx * cam.tanfovy * (z_far ** 3 - z_near ** 3) / 3.0
+    spacing = (volume / n) ** (1.0 / 3.0)
+    knn_c.distCUDA2 = lambda x: knn_dist2(x, spacing)
     knn._C = knn_c
     sys.modules['simple_knn'], sys.modules['simple_knn._C'] = knn, knn_c
     spec = importlib.util.spec_from_file_location('LoG.cuda.compute_radius', os.path.join(ROOT, 'dropin', 'LoG_cuda', 'compute_radius.py'))
@@ -61,8 +63,7 @@ def build(ref_root, n, W, H, dev, seed=0, densify=None):
     import LoG.model.level_of_gaussian as L
     import LoG.render.renderer as R
     rng = np.random.default_rng(seed)
-    cam = O.make_camera(W, H)
-    z = rng.uniform(2, 12, n)
+    z = (rng.uniform(z_near ** 3, z_far ** 3, n)) ** (1.0 / 3.0)      # uniform in the frustum VOLUME (a COLMAP-like cloud has no pile-up near the camera)
     xyz = np.stack([rng.uniform(-1, 1, n) * cam.tanfovx * z, rng.uniform(-1, 1, n) * cam.tanfovy * z, z], -1).astype(np.float32)
     colors = rng.uniform(0, 1, (n, 3)).astype(np.float32)
     model = L.LoG(gaussian=dict(init_ply=dict(filename={'xyz': xyz, 'colors': colors}, scale3d=1., init_opacity=0.5), sh_degree=1, xyz_scale=1.),
@@ -155,7 +156,7 @@ def fused_adam_step(model):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--points', type=int, default=300_000)
+    ap.add_argument('--points', type=int, default=2_000_000)      # the reference's example scenes hold 2-3 M points (docs/preprocess.md:122-126)
     ap.add_argument('--width', type=int, default=1920)
     ap.add_argument('--height', type=int, default=1080)
     ap.add_argument('--iters', type=int, default=30)
@@ -193,6 +194,14 @@ def main():
     for _ in range(3):
         train_step(model, rend, batch, ph)
     res['base_stage_phase_ms_stock'] = {k: v / 3 for k, v in ph.items()}
+    from log_b200 import _capi as capi
+    capi.profile_enable(True)
+    out1 = train_step(model, rend, batch)
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
+    res['base_stage_kernel_ms_one_iter'] = {k: round(v[0], 4) for k, v in capi.profile_collect().items() if v[1]}
+    capi.profile_enable(False)
+    res['base_stage_rendered_rows'] = int(out1['radii'][0].shape[0]) if 'radii' in out1 else None
     # where the render phase goes: LoG's prepare (tree / visibility) vs its render() (get_all + activations + rasteriser + unique)
     import cProfile
     import pstats

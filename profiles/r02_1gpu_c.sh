@@ -24,7 +24,7 @@ for wl in 100k 1k; do
   LGR_GRAPH=0 LGR_SYNC_FREE=0 timeout 600 python bench.py --steps 50 --warmup 5 --workload $wl --no-e2e --no-cpu-baseline > $OUT/bench_${wl}_hostsized.json 2> $OUT/bench_${wl}_hostsized.err
 done
 if [ -d scratch/reference/LoG ]; then
-  LGR_REFERENCE_ROOT=scratch/reference timeout 900 python profiles/log_loop_gpu.py --points 300000 --iters 20 --out $OUT/log_loop.json > $OUT/log_loop.log 2>&1
+  LGR_REFERENCE_ROOT=scratch/reference timeout 900 python profiles/log_loop_gpu.py --iters 20 --out $OUT/log_loop.json > $OUT/log_loop.log 2>&1
   echo "log loop rc=$?" >> $OUT/summary.txt
 fi
 tail -n 3 $OUT/gpu_suite.log

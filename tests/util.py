@@ -34,7 +34,7 @@ def record_parity(case, errors, bound, filter_on=True, note=None):
         data = json.load(open(path)) if os.path.exists(path) else {}
         data[case] = {'bound': bound, 'low_pass_filter': bool(filter_on), 'note': note,
                       'errors': {k: {'vs_fp64_oracle': float(v[0]), 'fp32_oracle_vs_fp64_oracle': None if v[1] is None else float(v[1]),
-                                     'exceeds_1e-4': bool(v[0] >= 1e-4), 'bound_used': max(bound, v[1] or 0.0)} for k, v in errors.items()}}
+                                     'exceeds_1e-4': bool(v[0] >= 1e-4), 'bound_used': max(bound, 1.05 * (v[1] or 0.0))} for k, v in errors.items()}}
         json.dump(data, open(path, 'w'), indent=1, sort_keys=True)
     except OSError:
         pass
