@@ -205,6 +205,9 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         m = (meta if band_count is None else torch.cat([meta, band_count])).tolist()   # the one host sync of the forward
         D, max_len, num_long = int(m[0]), int(m[1]), int(m[5])
         stock_D = (m[2] & 0xffffffff) | ((m[3] & 0xffffffff) << 32)
+        if D < 0 or stock_D > 0x7fffffff:      # the per-tile counters and list offsets are 32-bit
+            raise _capi.LgrError(f'this view needs {stock_D} (Gaussian, tile) instances by the stock rule (D = {m[0] & 0xffffffff} binned, '
+                                 f'{m[4]} of {n} Gaussians visible, longest tile list {max_len}): more than 2^31 - 1 is unsupported')
         inst_key = torch.empty((D,), **u32)
         inst_val = torch.empty((D,), **u32)
         inst_tmp = torch.empty((2 * D,), **u32) if max_len > lib.lgr_sort_smem_capacity() else None

@@ -74,9 +74,9 @@ def build(ref_root, n, W, H, dev, seed=0, densify=None):
                   densify_and_remove=AD(dict(upgrade_sh_iter=10, densify_from_iter=1, densify_every_iter=1, upgrade_repeat=50), **(densify or {})),
                   use_view_correction=False)
     model = model.to(dev)
-    model.base_iter = 1
-    model.training_setup()
-    model.train()
+    sc_ = model.gaussian.activation.scaling_activation(model.gaussian.scaling)
+    print(f'[log_loop] {n} points, spacing {spacing:.4f}, activated scale min/mean/max {float(sc_.min()):.4f} / {float(sc_.mean()):.4f} / {float(sc_.max()):.4f}, '
+          f'z in [{float(model.gaussian.xyz[:, 2].min()):.2f}, {float(model.gaussian.xyz[:, 2].max()):.2f}]', flush=True)
     rend = R.NaiveRendererAndLoss(split='train').to(dev)      # its `background` buffer follows the device, as in LoG's Trainer
     f = lambda t: t.float().to(dev)
     batch = {'camera': {'camera_center': f(cam.campos)[None], 'world_view_transform': f(cam.viewmatrix)[None],
@@ -84,6 +84,15 @@ def build(ref_root, n, W, H, dev, seed=0, densify=None):
                         'FoVx': torch.tensor([2 * np.arctan(cam.tanfovx)]), 'FoVy': torch.tensor([2 * np.arctan(cam.tanfovy)]),
                         'K': torch.eye(3, device=dev)[None], 'R': torch.eye(3, device=dev)[None], 'T': torch.zeros(1, 3, 1, device=dev)},
              'image': torch.rand(1, H, W, 3, generator=torch.Generator().manual_seed(1)).to(dev), 'index': torch.tensor([0])}
+    # Trainer.init (trainer.py:167-179): per view model.init() -> Gaussian.init_radius3d -> rasterizer.compute_radius (the fork's
+    # method, level_of_gaussian.py:55-63), then at_init_final(): the per-point scale clamps of the Counter.  Without it every scale
+    # is clamped to 1 world unit by LoG.step() -> clamp_scale (counter.py:17-18 defaults).
+    model.at_init_start()
+    model.init(rend, batch, 0)
+    model.at_init_final()
+    model.base_iter = 1
+    model.training_setup()
+    model.train()
     return model, rend, batch, cam, L, R
 
 
@@ -179,6 +188,26 @@ def main():
         args.points, args.width, args.height, args.iters = 300, 64, 48, 2
     else:
         dev = torch.device('cuda:0')
+    if os.environ.get('LGR_LOOP_DEBUG'):      # print what reaches the rasteriser on the first call, then stop
+        import log_b200.rasterizer as RZ
+        orig = RZ.rasterize_forward
+
+        def spy(*a, **k):
+            st_, m_, o_, sc_, r_ = a[0], a[1], a[2], a[3], a[4]
+            print('[debug] n', m_.shape[0], 'means min/max', m_.min(0).values.tolist(), m_.max(0).values.tolist(), 'scales', float(sc_.min()), float(sc_.mean()),
+                  float(sc_.max()), 'opac', float(o_.min()), float(o_.max()), 'rot row0', r_[0].tolist(), 'strides', m_.stride(), sc_.stride(), r_.stride(), flush=True)
+            print('[debug] settings', st_.image_height, st_.image_width, st_.tanfovx, st_.tanfovy, st_.scale_modifier, st_.viewmatrix.tolist(), st_.projmatrix.tolist(), flush=True)
+            try:
+                out = orig(*a, **k)
+            except Exception as e:
+                print('[debug] forward raised', e, flush=True)
+                from log_b200 import compute_radius
+                rr = compute_radius(m_, sc_, r_, st_.projmatrix, st_.viewmatrix, st_.image_width / (2 * st_.tanfovx), st_.image_height / (2 * st_.tanfovy), st_.tanfovx, st_.tanfovy)
+                print('[debug] compute_radius min/mean/max', float(rr.min()), float(rr.mean()), float(rr.max()), flush=True)
+                raise SystemExit(1)
+            print('[debug] radii max/mean', int(out[1].max()), float(out[1].float().mean()), 'D', out[-1].num_instances, flush=True)
+            raise SystemExit(0)
+        RZ.rasterize_forward = spy
     T = Timer(dev)
     res = {'points': args.points, 'image': [args.width, args.height], 'iters': args.iters, 'device': torch.cuda.get_device_name(0) if dev.type == 'cuda' else 'cpu-emulation',
            'what': 'LoG\'s own unmodified LoG / Counter / SparseOptimizer / NaiveRendererAndLoss classes, log_b200 rasteriser + compute_radius behind them'}
