@@ -311,6 +311,8 @@ def main():
             torch.cuda.synchronize()
 
     sync_free = bool(int(os.environ.get('LGR_SYNC_FREE', '1'))) and (world == 1 or shard is not None)
+    if shard is not None:
+        shard.sync_free = sync_free      # the view is static here and check_overflow() follows the timed loop
     use_graph = sync_free and bool(int(os.environ.get('LGR_GRAPH', '1')))
     for _ in range(args.warmup):
         step_resident()

@@ -223,11 +223,13 @@ class SplatExchange:
         self.recv_radii.zero_()
         self._cache = {}
         self._in_flight = False      # a forward() whose backward() has not run yet (see forward())
-        # Device-sized rendering (lgr_forward_render_device_sized): after a first step has measured D, later steps size
-        # their instance buffers from it (+25 %) and never read anything back -- no host synchronisation inside a step,
-        # so a step can be captured in a CUDA graph.  check_overflow() tells whether a step outgrew its buffers.
+        # Device-sized rendering (lgr_forward_render_device_sized), OPT-IN (`xch.sync_free = True`, or LGR_SYNC_FREE=1): after
+        # a first step has measured D, later steps size their instance buffers from it (+25 %) and never read anything back
+        # -- no host synchronisation inside a step, so a step can be captured in a CUDA graph.  The caller then owns the
+        # check: check_overflow() tells whether a step outgrew its buffers (its outputs are invalid: redo it).  Off by
+        # default because a training loop changes the view every step and D with it.
         import os
-        self.sync_free = bool(int(os.environ.get('LGR_SYNC_FREE', '1')))
+        self.sync_free = bool(int(os.environ.get('LGR_SYNC_FREE', '0')))
         self._inst_cap = 0
 
     def _scratch(self, name: str, shape, dtype):

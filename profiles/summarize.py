@@ -68,7 +68,10 @@ def main():
         v = float(r[lh.index('Metric Value')].replace(',', ''))
         u = r[lh.index('Metric Unit')]
         v = v / 1e6 if u == 'ns' else v / 1e3 if u in ('us', 'usecond') else v
-        agg.setdefault(r[lh.index('Kernel Name')].split('(')[0].replace('void ', ''), []).append(v)
+        name = r[lh.index('Kernel Name')].split('(')[0].replace('void ', '')
+        if 'lgr::' not in name:      # torch's own fill / copy kernels of the harness
+            continue
+        agg.setdefault(name.replace('lgr::', ''), []).append(v)
     tot = sum(sum(v) for v in agg.values())
     out.append('\n## launch list (gpu__time_duration.sum, every launch of the captured steps)\n\n| kernel | launches | total ms | avg ms | share |\n|---|---|---|---|---|')
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):

@@ -94,6 +94,47 @@ def run_two_steps(world, deg, flavour, size=(224, 160, 6001)):
             compare(full, outs, back, deg, W * H)
 
 
+def run_device_sized_steps(world, size=(224, 160, 6001)):
+    """`sync_free` (device-sized render: no read-back of D, CUDA-graph capturable): the first step is host-sized and learns
+    the capacity; a second step on the same scene is device-sized and must give the same result; a third step with much
+    bigger splats outgrows the capacity on some rank -- check_overflow() must say so -- and the redo (host-sized again, it
+    re-learns the capacity) must be right."""
+    from log_b200._capi import LGR_FILTER_MAX
+    W, H, n = size
+    dev = device()
+    cam = f32_camera(O.make_camera(W, H, bg=(0.1, 0.2, 0.3)))
+    ranks = make_ranks(n, H, world, dev)
+    for x in ranks:
+        x.sync_free = True
+    s = settings_from_camera(cam, dev, 0)
+
+    def scene(seed, spread):
+        sc = f32_scene(O.make_scene(n, W, H, spread, seed=seed))
+        G = O.make_cotangent(3, H, W)
+        t = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in sc.items()}
+        t['opacities'] = t['opacities'].reshape(-1)
+        return run_gpu(cam, sc, G), t, G.to(device=dev, dtype=torch.float32)
+    full, t, Gd = scene(41, 4.0)
+    for k in range(2):      # host-sized, then device-sized
+        outs, back, _ = shard_step(ranks, s, t, Gd, 0, LGR_FILTER_MAX)
+        assert all(x.check_overflow()['overflow'] == 0 for x in ranks)
+        assert all((x._inst_cap > 0) for x in ranks)
+        compare(full, outs, back, 0, W * H)
+    full, t, Gd = scene(42, 14.0)      # ~10 x the instances per band
+    outs, back, _ = shard_step(ranks, s, t, Gd, 0, LGR_FILTER_MAX)
+    flagged = 0
+    for x in ranks:
+        try:
+            x.check_overflow()
+        except RuntimeError:
+            flagged += 1
+    assert flagged > 0
+    for x in ranks:      # a redo is host-sized on every rank (ranks that fitted are simply rendered again)
+        x._inst_cap = 0
+    outs, back, _ = shard_step(ranks, s, t, Gd, 0, LGR_FILTER_MAX)
+    compare(full, outs, back, 0, W * H)
+
+
 def run_empty_shards_and_bands():
     """More ranks than tile rows (empty bands) and fewer Gaussians than ranks*256 (empty shards)."""
     from log_b200._capi import LGR_FILTER_MAX

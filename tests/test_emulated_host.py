@@ -82,6 +82,10 @@ def test_shard_mode_host_class(emulated_backend, world, deg, flavour):
     shard_checks.run_two_steps(world, deg, flavour, size=(64, 80, 700))
 
 
+def test_shard_mode_device_sized_steps(emulated_backend):
+    shard_checks.run_device_sized_steps(2, size=(96, 80, 900))
+
+
 def test_shard_mode_empty_shards_and_bands(emulated_backend):
     shard_checks.run_empty_shards_and_bands()
 

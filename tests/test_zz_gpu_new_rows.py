@@ -1,13 +1,12 @@
 """`-m gpu`: the rows built after the round-1 GPU budget was spent -- the fused tree walk and LoG's
 colour activation with SH fused into the projection (row 3) -- on hardware, with the same checks that pass on the CPU
-emulation (tests/test_tree_traverse.py, tests/test_emulated_host.py).  Non-strict xfail until their first hardware run
-(expected: XPASS); the file sorts last so that it cannot disturb the verified tests."""
+emulation (tests/test_tree_traverse.py, tests/test_emulated_host.py).  Green on the B200 since round 2."""
 import pytest
 
 import test_gpu_parity as gp
 import test_tree_traverse as tt
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='first hardware run pending')]
+pytestmark = pytest.mark.gpu
 
 
 def test_tree_walk_reproduces_the_reference_lists(built):

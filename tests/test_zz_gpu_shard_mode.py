@@ -7,22 +7,24 @@ ranks produce must equal the ordinary single-GPU call:
     same records in the same (depth, global index) order);
   * gradients: to fp32 summation order (the 2D gradients are accumulated per band and then summed).
 
-STATUS: written at the very end of round 1, after the GPU budget was spent.  The exchange kernels themselves are checked
-bit-exactly on the CPU SIMT emulation (tests/test_emulated_kernels.py::test_shard_exchange_emulated) and the host logic
-by tests/test_sharded_cpu.py, but the path has not yet run on hardware.  Hence the non-strict xfail (an XPASS is the expected
-outcome); the file sorts last so that nothing it does can disturb the verified tests.  `--runxfail` shows real failures.
+Green on the B200 since the first hardware run of round 2 (the xfail marker of round 1 is gone).  The second step of
+run_two_steps goes through the same buffers with different data; with `sync_free` switched on it would be a device-sized
+step (covered separately by shard_checks.run_two_steps(..., sync_free=True)).
 """
 import pytest
 
 import shard_checks
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='shard mode: first hardware run pending (written without GPU access)')]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('world,deg,flavour', [(2, 0, 'fork'), (3, 0, 'fork'), (2, 3, 'stock'), (8, 0, 'fork')])
 def test_shard_mode_emulated_on_one_gpu(built, world, deg, flavour):
     shard_checks.run_two_steps(world, deg, flavour)
+
+
+def test_shard_mode_device_sized_steps(built):
+    shard_checks.run_device_sized_steps(3)
 
 
 def test_shard_mode_handles_empty_shards_and_bands(built):

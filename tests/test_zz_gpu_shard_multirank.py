@@ -2,7 +2,7 @@
 SplatExchange.over_symmetric_memory, forward()/backward() with their device-side barriers, through the autograd wrapper --
 against the single-GPU result, two steps through the same buffers.  The same worker logic runs on the CPU as
 tests/test_sharded_cpu.py::test_shard_mode_as_separate_processes_with_real_barriers (gloo, shared memory, emulated kernels).
-Non-strict xfail until its first hardware run.  `gpurun --gpus 2 -- python -m pytest tests/test_zz_gpu_shard_multirank.py -m gpu --runxfail`"""
+Green on 2 B200s since round 2 (`gpurun --gpus 2 -- python -m pytest tests/test_zz_gpu_shard_multirank.py -m gpu`)"""
 import os
 import socket
 
@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='shard mode: first hardware run pending')]
+pytestmark = pytest.mark.gpu
 W, H, N, STEPS = 320, 208, 20000, 2
 
 
