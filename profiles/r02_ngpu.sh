@@ -14,7 +14,7 @@ run() {  # $1 = label, rest = extra bench args ; env in front
 }
 run shard
 LGR_GRAPH=0 run shard_nograph --no-e2e
-LGR_GRAPH=0 LGR_SYNC_FREE=0 run shard_hostsized --no-e2e
+if [ "${HOSTSIZED:-1}" = "1" ]; then LGR_GRAPH=0 LGR_SYNC_FREE=0 run shard_hostsized --no-e2e; fi
 LGR_MULTI=band run band --no-e2e
 if [ "${TESTS:-1}" = "1" ]; then
   timeout 900 python -m pytest tests/test_gpu_multirank.py tests/test_zz_gpu_shard_multirank.py -q -m gpu --runxfail -p no:cacheprovider > $OUT/multirank.log 2>&1
