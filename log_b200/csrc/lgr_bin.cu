@@ -88,8 +88,20 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
       i = id;
     }
   }
+  // All per-Gaussian loads are issued together, before anything depends on them (radius, the two record quads with the
+  // depth, the four ranks): one memory latency instead of a chain of three.  Nearly every row is live, so nothing is wasted.
   int rad = 0;
-  if (live) { rad = radii[i]; live = rad > 0; }
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+  float depth = 0.f;
+  int4 rk = make_int4(-1, -1, -1, -1);
+  if (live) {
+    rad = radii[i];
+    r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);
+    r1 = ldg4(splat + i * LGR_SPLAT_FLOATS + 4);
+    depth = __ldg(splat + i * LGR_SPLAT_FLOATS + 11);
+    if (v.tile_rank) rk = __ldg(reinterpret_cast<const int4*>(v.tile_rank + 4 * i));
+    live = rad > 0;
+  }
   if (live && v.num_owners == 0 && v.band_dsplat) {      // optional: zero the backward's accumulator row of every visible Gaussian here,
     float4* z = reinterpret_cast<float4*>(v.band_dsplat + i * LGR_GRAD_FLOATS);      // instead of a separate full-size memset
     z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -97,11 +109,9 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   uint32_t key = 0;
   if (live) {
-    const float4 r0 = ldg4(splat + i * LGR_SPLAT_FLOATS);
-    const float4 r1 = ldg4(splat + i * LGR_SPLAT_FLOATS + 4);
     live = r1.z > 0.f;      // hx == 0: opacity below 1/255, contributes nowhere
     if (live) {
-      key = __float_as_uint(__ldg(splat + i * LGR_SPLAT_FLOATS + 11));   // depth > 0.2 : IEEE bits are order preserving
+      key = __float_as_uint(depth);   // depth > 0.2 : IEEE bits are order preserving
       tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
     }
   }
@@ -114,8 +124,7 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
       t[k] = k < cnt ? (ty - v.row0) * v.gx + tx : -1;
     }
     if (v.tile_rank) {      // the counting pass already took the slots: a streaming kernel, no atomics
-      const int4 r = __ldg(reinterpret_cast<const int4*>(v.tile_rank + 4 * i));
-      slot[0] = r.x; slot[1] = r.y; slot[2] = r.z; slot[3] = r.w;
+      slot[0] = rk.x; slot[1] = rk.y; slot[2] = rk.z; slot[3] = rk.w;
     } else {
       // all slot requests are issued before any dependent store, so the returning atomics overlap instead of forming a
       // serial chain of L2 round trips

@@ -153,7 +153,14 @@ def owner_of_row(tile_row: int, image_height: int, world_size: int) -> int:
 
 
 def shard_layout(num_gaussians: int, world_size: int, rank: int):
-    """(LgrShardLayout, floats per exchange buffer).  Every region starts on a 256-byte boundary."""
+    """(LgrShardLayout, floats per exchange buffer).  Every region starts on a 256-byte boundary.
+
+    Footprint: every (source, owner) pair gets room for ALL of the source's Gaussians (cap = ceil(N/R) rows), because any
+    view may send a whole shard into one band; a rank's buffer therefore holds R*cap ~ N rows of 112 bytes, plus the
+    48-byte rows of `dsplat_rows`: ~1.6 GB per rank at 10 M Gaussians, ~8 GB at 50 M, independent of R.  Parameters,
+    gradients, optimiser state and all per-step scratch DO shrink with R; only this staging area does not.  The kernels
+    touch the count[s] used rows of a region, except the receive-side counting pass, which also walks the unused slots to
+    clear their stale radii."""
     from . import _capi
     cap = owner_chunk(num_gaussians, world_size)
     rows = world_size * cap
