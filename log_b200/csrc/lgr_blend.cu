@@ -127,14 +127,15 @@ __device__ __forceinline__ void mma_tf32(float& d0, float& d1, float& d2, float&
 // Staged splat: three consecutive float4 per list entry (48-byte stride: conflict-free for 128-bit accesses),
 //   [0] = (px, py, conic_x', conic_y')   [1] = (conic_z', opacity, hx, hy)   [2] = (r, g, b, id as int bits)
 // plus one byte of sub-tile hit bits.
+// recorded: the entry's byte of View::contrib (backward, when the forward recorded which sub-tiles composited it) or nullptr
 __device__ __forceinline__ void stage_splat(float4* s_rec, unsigned char* s_bits, int slot, const float* __restrict__ splat,
-                                            int id, float tx0, float ty0) {
+                                            int id, float tx0, float ty0, const uint8_t* __restrict__ recorded = nullptr) {
   const float* rec = splat + (int64_t)id * LGR_SPLAT_FLOATS;
   const float4 r0 = ldg4(rec), r1 = ldg4(rec + 4);
   float4 r2 = ldg4(rec + 8);
   r2.w = __int_as_float(id);
   s_rec[3 * slot] = r0; s_rec[3 * slot + 1] = r1; s_rec[3 * slot + 2] = r2;
-  s_bits[slot] = (unsigned char)subtile_bits(r0, r1, tx0, ty0);
+  s_bits[slot] = recorded ? *recorded : (unsigned char)subtile_bits(r0, r1, tx0, ty0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -149,6 +150,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   __shared__ float4 s_rec[BATCH * 3];
   __shared__ unsigned s_w[AUX ? BATCH : 1];
   __shared__ unsigned char s_bits[BATCH];
+  __shared__ unsigned s_cb[(BLEND_THREADS / 32) * (BATCH / 32)];      // per warp: bit e = a pixel of this warp took staged splat e
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SubTile st = make_subtile(v, tile, lane, warp);
   const float pxf = (float)st.x, pyf = (float)st.y;
@@ -176,11 +178,16 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   if (len > 0) stage();
   while (base < len) {
     __syncthreads();                         // A: the batch is staged
+    if (v.contrib) {      // a warp owns its BATCH/32 words of s_cb: cleared here, written below, read by others only after B
+      if (lane < BATCH / 32) s_cb[warp * (BATCH / 32) + lane] = 0u;
+      __syncwarp();
+    }
     if (!__all_sync(FULL, done)) {
       for (int c0 = 0; c0 < cnt; c0 += 32) {
         const int e_l = c0 + lane;
         unsigned mask = __ballot_sync(FULL, (s_bits[e_l] >> warp) & 1u);
         unsigned own_w = 0u;                 // max weight of the splat this lane tested, over this warp's pixels
+        unsigned took = 0u;                  // bit j: some pixel of this warp composited staged splat c0 + j
         while (mask) {
           // two hits per iteration: loads and alpha evaluation of both overlap, the transmittance updates are sequential
           const int jA = __ffs(mask) - 1;
@@ -196,6 +203,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           const float powerA = eval_power2(r0A, r1A.x, dxA, dyA), powerB = eval_power2(r0B, r1B.x, dxB, dyB);
           const float alphaA = eval_alpha(r1A.y, ex2_approx(powerA)), alphaB = eval_alpha(r1B.y, ex2_approx(powerB));
           float wA = 0.f, wB = 0.f;
+          const int done_before = done;
           if (!done && powerA <= 0.0f && alphaA >= ALPHA_MIN) {
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alphaA));
             if (test_T < T_STOP) done = 1;
@@ -225,14 +233,29 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
             const unsigned mB = __reduce_max_sync(FULL, __float_as_uint(wB));
             if (lane == jA) own_w = mA;
             if (two && lane == jB) own_w = mB;
+            if (mA) took |= 1u << jA;          // a composited pixel has w = alpha T >= 1/255 * 1e-4 > 0
+            if (mB) took |= 1u << jB;
+          } else if (v.contrib) {
+            if (__any_sync(FULL, wA != 0.f)) took |= 1u << jA;
+            if (__any_sync(FULL, wB != 0.f)) took |= 1u << jB;
           }
+          // a pixel that STOPS at a splat (T would fall below 1e-4) composites nothing there, but the backward must meet
+          // that splat to stop the same pixel: record the pair as well (both hits of the iteration: a superset is harmless)
+          if (v.contrib && __any_sync(FULL, done != done_before)) took |= (1u << jA) | (1u << jB);
         }
+        if (v.contrib && lane == 0) s_cb[warp * (BATCH / 32) + (c0 >> 5)] = took;
         if (AUX && own_w) red_shared_max_u32(s_w_addr + 4u * e_l, own_w);
         if (__all_sync(FULL, done)) break;
       }
     }
     const int all_done = __syncthreads_and(done);      // B: every warp has left the walk
     if (AUX && tid < cnt && s_w[tid]) atomicMax(point_weight_bits + __float_as_int(s_rec[3 * tid + 2].w), s_w[tid]);
+    if (v.contrib && tid < cnt) {      // for the backward: which sub-tiles composited this list entry
+      unsigned byte = 0u;
+#pragma unroll
+      for (int w = 0; w < BLEND_THREADS / 32; w++) byte |= ((s_cb[w * (BATCH / 32) + (tid >> 5)] >> (tid & 31)) & 1u) << w;
+      v.contrib[beg + base + tid] = (uint8_t)byte;
+    }
     base += BATCH;
     if (all_done || base >= len) break;
     cnt = min(BATCH, len - base);
@@ -343,7 +366,8 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   int base = 0, cnt = min(BATCH, len);
   auto stage = [&]() {
     if (tid < cnt) {
-      stage_splat(s_rec, s_bits, tid, splat, id_next, tx0, ty0);
+      // with View::contrib: walk exactly the (sub-tile, splat) pairs that composited something in the forward
+      stage_splat(s_rec, s_bits, tid, splat, id_next, tx0, ty0, v.contrib ? v.contrib + beg + base + tid : nullptr);
 #pragma unroll
       for (int k = 0; k < 9; k++) s_g[tid * 9 + k] = 0.f;
     } else {

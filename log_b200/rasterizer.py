@@ -27,6 +27,8 @@ from ._capi import LGR_FILTER_ADD, LGR_FILTER_MAX, LGR_FILTER_NONE, LgrView
 PREZERO_DSPLAT = bool(int(__import__('os').environ.get('LGR_PREZERO_DSPLAT', '0')))      # see rasterize_forward
 # tile slots taken once, by the counting pass (lgr_view.tile_rank_d); 0 = the two-pass binning of round 1 (A/B knob)
 RANKED_BIN = bool(int(__import__('os').environ.get('LGR_RANKED_BIN', '1')))
+# the forward blend records, per tile-list entry, the sub-tiles that composited it; the backward walks only those (A/B knob)
+CONTRIB_BITS = bool(int(__import__('os').environ.get('LGR_CONTRIB_BITS', '1')))
 FLAVOUR_STOCK = 'stock'   # diff_gaussian_rasterization            (graphdeco-inria)   -> 2-tuple, cov += 0.3
 FLAVOUR_FORK = 'fork'     # diff_gaussian_rasterization_wodilate   (chingswy antialias) -> 5-tuple, cov = max(cov, 0.3)
 
@@ -197,6 +199,9 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         D, max_len, num_long, stock_D, m = int(instance_capacity), None, None, None, None
         inst_key, inst_val = torch.empty((D,), **u32), torch.empty((D,), **u32)
         sorted_ids = torch.empty((D,), **i32)
+        contrib = torch.empty((D,), dtype=torch.uint8, device=dev) if CONTRIB_BITS else None
+        keep.append(contrib)
+        view.contrib_d = contrib.data_ptr() if contrib is not None and D > 0 else None
         _capi.check(lib.lgr_forward_render_device_sized(ctypes.byref(view), n, D, _ptr(meta), _ptr(splat), _ptr(radii), _ptr(tile_start),
                                                         _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(sorted_ids), _ptr(image),
                                                         _ptr(final_T), _ptr(n_contrib), _ptr(pid), _ptr(pwp), _ptr(pw), _ptr(pc), st),
@@ -212,6 +217,9 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         inst_val = torch.empty((D,), **u32)
         inst_tmp = torch.empty((2 * D,), **u32) if max_len > lib.lgr_sort_smem_capacity() else None
         sorted_ids = torch.empty((D,), **i32)
+        contrib = torch.empty((D,), dtype=torch.uint8, device=dev) if CONTRIB_BITS else None      # forward -> backward: see lgr_view.contrib_d
+        keep.append(contrib)
+        view.contrib_d = contrib.data_ptr() if contrib is not None and D > 0 else None
         _capi.check(lib.lgr_forward_render(ctypes.byref(view), n, D, max_len, num_long, _ptr(splat), _ptr(radii), _ptr(tile_start),
                                            _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
                                            _ptr(sorted_ids), _ptr(image), _ptr(final_T), _ptr(n_contrib), _ptr(pid),

@@ -55,6 +55,11 @@ def test_band_mode_rows_and_fused_push(emulated_backend, world):
     gp.test_fused_push_route_emulated_on_one_gpu(True, world, size=(64, 80, 900))
 
 
+@pytest.mark.parametrize('size', [(48, 32, 3000, 2.0), (64, 48, 1500, 5.0)])
+def test_recorded_subtile_bits(emulated_backend, monkeypatch, size):
+    gp.test_recorded_subtile_bits_do_not_change_the_backward(True, monkeypatch, size)
+
+
 def test_device_sized_forward(emulated_backend):
     gp.test_device_sized_forward_equals_host_sized(True, size=(64, 48, 400))
 

@@ -320,6 +320,26 @@ def test_band_mode_rows_reproduce_dense_gradients(built, world, size=(208, 144, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('size', [(48, 32, 3000, 2.0), (96, 64, 2500, 5.0)])
+def test_recorded_subtile_bits_do_not_change_the_backward(built, monkeypatch, size):
+    """lgr_view.contrib_d: the forward records, per tile-list entry, which sub-tiles composited it (or stopped a pixel at
+    it), and the backward walks only those pairs.  Same contributions, so the gradients must equal the backward that
+    re-tests the boxes itself -- on tile lists of several staged batches (> 256 entries), where the record crosses batches."""
+    import log_b200.rasterizer as R
+    W, H, n, r = size
+    cam = f32_camera(O.make_camera(W, H, bg=(0.1, 0.2, 0.3)))
+    sc = f32_scene(O.make_scene(n, W, H, r, seed=41))
+    G = O.make_cotangent(3, H, W)
+    monkeypatch.setattr(R, 'CONTRIB_BITS', False)
+    a = run_gpu(cam, sc, G)
+    monkeypatch.setattr(R, 'CONTRIB_BITS', True)
+    b = run_gpu(cam, sc, G)
+    assert torch.equal(a['image'], b['image'])
+    for k in ['dmeans3D', 'dmeans2D', 'dopacities', 'dscales', 'drotations', 'dcolors']:
+        assert rel(b[k], a[k]) < 2e-6, (k, rel(b[k], a[k]))
+
+
+@pytest.mark.gpu
 def test_device_sized_forward_equals_host_sized(built, size=(160, 112, 3000)):
     """lgr_forward_render_device_sized (no read-back of D, launch shapes independent of the data: CUDA-graph capturable) must
     produce exactly what the host-sized call produces, forward and backward; and when the view needs more instances than
