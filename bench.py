@@ -449,27 +449,32 @@ def main():
         if shard is not None:
             host = {k: v[shard.lo:shard.hi].contiguous().pin_memory() for k, v in sc.items()}
         in_keys = [k for k in host if not (k == 'colors' and use_sh)]
-        h2d_bytes = sum(host[k].numel() * 4 for k in in_keys) + host_G.numel() * 4
+        # the cotangent image: a rank of the shard mode needs only the rows of its band (the rest of its image is zero)
+        gy0, gy1 = (shard.band[0] * 16, min(shard.band[1] * 16, H)) if shard is not None else (0, H)
+        host_Gb = host_G[:, gy0:gy1].contiguous().pin_memory()
+        h2d_bytes = sum(host[k].numel() * 4 for k in in_keys) + host_Gb.numel() * 4
         sets = []
         for _ in range(2):
             t_ = {k: torch.empty_like(host[k], device=dev).requires_grad_(True) for k in in_keys}
-            sets.append((t_, torch.empty_like(host_G, device=dev), torch.zeros(host['means3D'].shape[0], 3, device=dev, requires_grad=True)))
+            sets.append((t_, torch.zeros_like(host_G, device=dev), torch.zeros(host['means3D'].shape[0], 3, device=dev, requires_grad=True),
+                         torch.empty_like(host_Gb, device=dev)))
         copy_stream = torch.cuda.Stream(device=dev)
         rast = GaussianRasterizer(settings)
 
         def h2d(which):
             """Issue one step's host->device copies into input set `which` on the copy stream; returns the event that follows them."""
-            t_, Gd, _ = sets[which]
+            t_, Gd, _, Gb = sets[which]
             with torch.cuda.stream(copy_stream), torch.no_grad():
                 for k in in_keys:
                     t_[k].copy_(host[k], non_blocking=True)
-                Gd.copy_(host_G, non_blocking=True)
+                Gb.copy_(host_Gb, non_blocking=True)
+                Gd[:, gy0:gy1].copy_(Gb)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             return ev
 
         def compute(which, ev):
-            t_, Gd, m2d = sets[which]
+            t_, Gd, m2d, _ = sets[which]
             torch.cuda.current_stream().wait_event(ev)
             for v_ in list(t_.values()) + [m2d]:
                 v_.grad = None

@@ -89,7 +89,11 @@ typedef struct lgr_view {
                             entry which of the tile's eight 8x4 sub-tiles had a CONTRIBUTING pixel for that splat (bit w =
                             sub-tile w), and the backward sweep walks exactly those (sub-tile, splat) pairs instead of
                             re-testing the conservative boxes: the ~20 % of box hits that contribute nothing are never
-                            evaluated again.  Pass the same view (and buffer) to the forward and to the backward. */
+                            evaluated again.  Pass the same view (and buffer) to the forward and to the backward, and give
+                            the backward the forward's n_contrib_d as last_contrib_d. */
+  const int32_t* last_contrib_d; /* (H,W) int32 or NULL: the n_contrib_d output of lgr_forward_render (per pixel: list index + 1 of
+                            its last contributor).  Read by lgr_backward / lgr_blend_backward together with contrib_d: a pixel
+                            is finished once the sweep has passed its last contributor (both must be set, or neither). */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */

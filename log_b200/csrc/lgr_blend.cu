@@ -203,7 +203,6 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           const float powerA = eval_power2(r0A, r1A.x, dxA, dyA), powerB = eval_power2(r0B, r1B.x, dxB, dyB);
           const float alphaA = eval_alpha(r1A.y, ex2_approx(powerA)), alphaB = eval_alpha(r1B.y, ex2_approx(powerB));
           float wA = 0.f, wB = 0.f;
-          const int done_before = done;
           if (!done && powerA <= 0.0f && alphaA >= ALPHA_MIN) {
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alphaA));
             if (test_T < T_STOP) done = 1;
@@ -233,16 +232,14 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
             const unsigned mB = __reduce_max_sync(FULL, __float_as_uint(wB));
             if (lane == jA) own_w = mA;
             if (two && lane == jB) own_w = mB;
-            if (mA) took |= 1u << jA;          // a composited pixel has w = alpha T >= 1/255 * 1e-4 > 0
-            if (mB) took |= 1u << jB;
           } else if (v.contrib) {
             if (__any_sync(FULL, wA != 0.f)) took |= 1u << jA;
             if (__any_sync(FULL, wB != 0.f)) took |= 1u << jB;
           }
-          // a pixel that STOPS at a splat (T would fall below 1e-4) composites nothing there, but the backward must meet
-          // that splat to stop the same pixel: record the pair as well (both hits of the iteration: a superset is harmless)
-          if (v.contrib && __any_sync(FULL, done != done_before)) took |= (1u << jA) | (1u << jB);
         }
+        // fork flavour: the lane that staged a splat holds its max weight over this warp's pixels; non-zero <=> composited here
+        // (a composited pixel has w = alpha T >= 1/255 * 1e-4 > 0): one ballot per 32 staged splats
+        if (AUX && v.contrib) took = __ballot_sync(FULL, own_w != 0u);
         if (v.contrib && lane == 0) s_cb[warp * (BATCH / 32) + (c0 >> 5)] = took;
         if (AUX && own_w) red_shared_max_u32(s_w_addr + 4u * e_l, own_w);
         if (__all_sync(FULL, done)) break;
@@ -301,6 +298,10 @@ constexpr int HITS = 8;          // hits per contraction (half the m of mma.m16n
 constexpr int XROW = 36;         // floats per published row: 32 pixels + 4 pad, so the 8 rows of an ldmatrix block hit 8 bank groups
 constexpr int BWD_SMEM = BATCH * 48 + BATCH * 36 + (BLEND_THREADS / 32) * (2 * HITS * XROW + 192 + 192) * 4 + BATCH;
 
+// REC: the forward recorded (View::contrib) which sub-tiles composited each list entry and (View::last_contrib = its
+// n_contrib output) where every pixel's last contributor sits; the sweep then meets exactly the contributing (sub-tile,
+// splat) pairs and a pixel is finished once the walk has passed its last contributor -- no box tests, no T < 1e-4 test.
+template <bool REC>
 __global__ void __launch_bounds__(BLEND_THREADS, LGR_BWD_MIN_CTAS)
 blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
                  const float* __restrict__ splat, const float* __restrict__ image,
@@ -328,10 +329,12 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   const int g = lane >> 2, t = lane & 3;        // mma fragment coordinates of this lane
 
   float Rd = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+  int last = 0;                                  // REC: list index + 1 of this pixel's last contributor (0: none)
   if (st.inside) {
     const int64_t pix = (int64_t)st.y * v.W + st.x, HW = (int64_t)v.H * v.W;
     dp0 = dL_dimage[pix]; dp1 = dL_dimage[HW + pix]; dp2 = dL_dimage[2 * HW + pix];
     Rd = image[pix] * dp0 + image[HW + pix] * dp1 + image[2 * HW + pix] * dp2;
+    if (REC) last = v.last_contrib[pix];
   }
   // B fragments of the moment weights, per warp in shared memory: s_mw[((g*4 + t)*4 + s)*2 + {0,1}] = weight of output g at
   // the pixel of k-step s with k = t (column t, row s of the sub-tile) / k = t + 4 (column t + 4).  |values| <= 56.25 in
@@ -358,7 +361,7 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   __syncwarp();
 
   float T = 1.0f;
-  int done = st.inside ? 0 : 1;
+  int done = st.inside ? (REC ? (last == 0) : 0) : 1;
   int id_next = tid < len ? sorted_ids[beg + tid] : -1;
 
   // Two barriers per batch, as in the forward: thread tid stages, flushes and re-stages only slot tid (record, hit bits and
@@ -367,7 +370,7 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   auto stage = [&]() {
     if (tid < cnt) {
       // with View::contrib: walk exactly the (sub-tile, splat) pairs that composited something in the forward
-      stage_splat(s_rec, s_bits, tid, splat, id_next, tx0, ty0, v.contrib ? v.contrib + beg + base + tid : nullptr);
+      stage_splat(s_rec, s_bits, tid, splat, id_next, tx0, ty0, REC ? v.contrib + beg + base + tid : nullptr);
 #pragma unroll
       for (int k = 0; k < 9; k++) s_g[tid * 9 + k] = 0.f;
     } else {
@@ -412,14 +415,27 @@ blend_bwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
           const float omA = __fsub_rn(1.0f, alphaA), omB = __fsub_rn(1.0f, alphaB);
           bool cA = false, cB = false;
           const float TA = T;
-          if (!done && powerA <= 0.0f && alphaA >= ALPHA_MIN) {
-            const float tt = __fmul_rn(T, omA);
-            if (tt < T_STOP) done = 1; else { cA = true; T = tt; }
-          }
-          const float TB = T;
-          if (two && !done && powerB <= 0.0f && alphaB >= ALPHA_MIN) {
-            const float tt = __fmul_rn(T, omB);
-            if (tt < T_STOP) done = 1; else { cB = true; T = tt; }
+          float TB;
+          if (REC) {
+            // every visited splat in front of the pixel's last contributor with alpha >= 1/255 was composited by the forward
+            // (it would otherwise have stopped the pixel there); same multiplications, so T follows the forward bit for bit
+            cA = !done && powerA <= 0.0f && alphaA >= ALPHA_MIN;
+            if (cA) T = __fmul_rn(T, omA);
+            done = (base + eA + 1 >= last);
+            TB = T;
+            cB = two && !done && powerB <= 0.0f && alphaB >= ALPHA_MIN;
+            if (cB) T = __fmul_rn(T, omB);
+            if (two) done = (base + eB + 1 >= last);
+          } else {
+            if (!done && powerA <= 0.0f && alphaA >= ALPHA_MIN) {
+              const float tt = __fmul_rn(T, omA);
+              if (tt < T_STOP) done = 1; else { cA = true; T = tt; }
+            }
+            TB = T;
+            if (two && !done && powerB <= 0.0f && alphaB >= ALPHA_MIN) {
+              const float tt = __fmul_rn(T, omB);
+              if (tt < T_STOP) done = 1; else { cB = true; T = tt; }
+            }
           }
           const bool anyA = __any_sync(FULL, cA), anyB = __any_sync(FULL, cB);
           if (anyA) {
@@ -545,10 +561,13 @@ int launch_blend_bwd(const View& v, const int32_t* tile_start, const int32_t* so
   const int ntiles = v.gx * (v.row1 - v.row0);
   if (ntiles <= 0) return 0;
   // > 48 KB of dynamic shared memory needs the opt-in; the attribute is per device and cheap to set, so set it every time
-  cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+  const bool rec = v.contrib != nullptr && v.last_contrib != nullptr;
+  cudaError_t e = rec ? cudaFuncSetAttribute(blend_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM)
+                      : cudaFuncSetAttribute(blend_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_BLEND_BWD, st);
-  blend_bwd_kernel<<<ntiles, BLEND_THREADS, BWD_SMEM, st>>>(v, tile_start, sorted_ids, splat, image, dL_dimage, dsplat);
+  if (rec) blend_bwd_kernel<true><<<ntiles, BLEND_THREADS, BWD_SMEM, st>>>(v, tile_start, sorted_ids, splat, image, dL_dimage, dsplat);
+  else blend_bwd_kernel<false><<<ntiles, BLEND_THREADS, BWD_SMEM, st>>>(v, tile_start, sorted_ids, splat, image, dL_dimage, dsplat);
   LGR_CHECK_LAUNCH();
   return 0;
 }

@@ -36,6 +36,7 @@ struct View {
   const int64_t* gather;     // (n) or NULL: input row of output row i (gather fused into the projection)
   const int32_t* pid_map;    // (n) or NULL: point_id_pixel = pid_map[winning row]
   uint8_t* contrib;          // (instances) or NULL: per list entry, the sub-tiles with a contributing pixel (forward -> backward)
+  const int32_t* last_contrib;   // (H,W) or NULL: the forward's n_contrib (list index + 1 of each pixel's last contributor), backward only
   int band_blocks;           // B
   const float* view;         // (4,4) transposed storage: t_j = sum_i p_i * view[i*4+j] + view[12+j]
   const float* proj;
@@ -45,7 +46,7 @@ struct View {
 
 inline View make_view(const lgr_view* v, int64_t n = 0) {
   View o;
-  o.num_owners = v->num_owners; o.band_ids = v->band_ids_d; o.band_blk = v->band_blk_d; o.band_count = v->band_count_d; o.band_rows = v->band_rows_d; o.band_dsplat = v->band_dsplat_d; o.tile_rank = v->tile_rank_d; o.gather = v->gather_index_d; o.pid_map = v->pid_map_d; o.contrib = v->contrib_d;
+  o.num_owners = v->num_owners; o.band_ids = v->band_ids_d; o.band_blk = v->band_blk_d; o.band_count = v->band_count_d; o.band_rows = v->band_rows_d; o.band_dsplat = v->band_dsplat_d; o.tile_rank = v->tile_rank_d; o.gather = v->gather_index_d; o.pid_map = v->pid_map_d; o.contrib = v->contrib_d; o.last_contrib = v->last_contrib_d;
   o.owner_chunk = o.num_owners > 0 ? (int)LGR_OWNER_CHUNK(n, (int64_t)o.num_owners) : 256;
   if (o.owner_chunk < 256) o.owner_chunk = 256;
   o.band_blocks = (int)((n + 255) / 256);

@@ -202,6 +202,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         contrib = torch.empty((D,), dtype=torch.uint8, device=dev) if CONTRIB_BITS else None
         keep.append(contrib)
         view.contrib_d = contrib.data_ptr() if contrib is not None and D > 0 else None
+        view.last_contrib_d = n_contrib.data_ptr() if view.contrib_d else None
         _capi.check(lib.lgr_forward_render_device_sized(ctypes.byref(view), n, D, _ptr(meta), _ptr(splat), _ptr(radii), _ptr(tile_start),
                                                         _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(sorted_ids), _ptr(image),
                                                         _ptr(final_T), _ptr(n_contrib), _ptr(pid), _ptr(pwp), _ptr(pw), _ptr(pc), st),
@@ -220,6 +221,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
         contrib = torch.empty((D,), dtype=torch.uint8, device=dev) if CONTRIB_BITS else None      # forward -> backward: see lgr_view.contrib_d
         keep.append(contrib)
         view.contrib_d = contrib.data_ptr() if contrib is not None and D > 0 else None
+        view.last_contrib_d = n_contrib.data_ptr() if view.contrib_d else None      # the backward stops a pixel after its last contributor
         _capi.check(lib.lgr_forward_render(ctypes.byref(view), n, D, max_len, num_long, _ptr(splat), _ptr(radii), _ptr(tile_start),
                                            _ptr(tile_cursor), _ptr(inst_key), _ptr(inst_val), _ptr(inst_tmp),
                                            _ptr(sorted_ids), _ptr(image), _ptr(final_T), _ptr(n_contrib), _ptr(pid),
