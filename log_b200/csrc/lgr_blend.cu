@@ -141,7 +141,8 @@ __device__ __forceinline__ void stage_splat(float4* s_rec, unsigned char* s_bits
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-template <bool AUX>
+// REC: also record, per tile-list entry, the sub-tiles that composited it (View::contrib), for the backward
+template <bool AUX, bool REC>
 __global__ void __launch_bounds__(BLEND_THREADS, LGR_FWD_MIN_CTAS)
 blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* __restrict__ sorted_ids,
                  const float* __restrict__ splat, float* __restrict__ image, float* __restrict__ final_T,
@@ -150,7 +151,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   __shared__ float4 s_rec[BATCH * 3];
   __shared__ unsigned s_w[AUX ? BATCH : 1];
   __shared__ unsigned char s_bits[BATCH];
-  __shared__ unsigned s_cb[(BLEND_THREADS / 32) * (BATCH / 32)];      // per warp: bit e = a pixel of this warp took staged splat e
+  __shared__ unsigned s_cb[REC ? (BLEND_THREADS / 32) * (BATCH / 32) : 1];      // per warp: bit e = a pixel of this warp took staged splat e
   const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SubTile st = make_subtile(v, tile, lane, warp);
   const float pxf = (float)st.x, pyf = (float)st.y;
@@ -178,7 +179,7 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
   if (len > 0) stage();
   while (base < len) {
     __syncthreads();                         // A: the batch is staged
-    if (v.contrib) {      // a warp owns its BATCH/32 words of s_cb: cleared here, written below, read by others only after B
+    if (REC) {      // a warp owns its BATCH/32 words of s_cb: cleared here, written below, read by others only after B
       if (lane < BATCH / 32) s_cb[warp * (BATCH / 32) + lane] = 0u;
       __syncwarp();
     }
@@ -232,22 +233,22 @@ blend_fwd_kernel(View v, const int32_t* __restrict__ tile_start, const int32_t* 
             const unsigned mB = __reduce_max_sync(FULL, __float_as_uint(wB));
             if (lane == jA) own_w = mA;
             if (two && lane == jB) own_w = mB;
-          } else if (v.contrib) {
+          } else if (REC) {
             if (__any_sync(FULL, wA != 0.f)) took |= 1u << jA;
             if (__any_sync(FULL, wB != 0.f)) took |= 1u << jB;
           }
         }
         // fork flavour: the lane that staged a splat holds its max weight over this warp's pixels; non-zero <=> composited here
         // (a composited pixel has w = alpha T >= 1/255 * 1e-4 > 0): one ballot per 32 staged splats
-        if (AUX && v.contrib) took = __ballot_sync(FULL, own_w != 0u);
-        if (v.contrib && lane == 0) s_cb[warp * (BATCH / 32) + (c0 >> 5)] = took;
+        if (AUX && REC) took = __ballot_sync(FULL, own_w != 0u);
+        if (REC && lane == 0) s_cb[warp * (BATCH / 32) + (c0 >> 5)] = took;
         if (AUX && own_w) red_shared_max_u32(s_w_addr + 4u * e_l, own_w);
         if (__all_sync(FULL, done)) break;
       }
     }
     const int all_done = __syncthreads_and(done);      // B: every warp has left the walk
     if (AUX && tid < cnt && s_w[tid]) atomicMax(point_weight_bits + __float_as_int(s_rec[3 * tid + 2].w), s_w[tid]);
-    if (v.contrib && tid < cnt) {      // for the backward: which sub-tiles composited this list entry
+    if (REC && tid < cnt) {      // for the backward: which sub-tiles composited this list entry
       unsigned byte = 0u;
 #pragma unroll
       for (int w = 0; w < BLEND_THREADS / 32; w++) byte |= ((s_cb[w * (BATCH / 32) + (tid >> 5)] >> (tid & 31)) & 1u) << w;
@@ -548,10 +549,16 @@ int launch_blend_fwd(const View& v, const int32_t* tile_start, const int32_t* so
   const int ntiles = v.gx * (v.row1 - v.row0);
   if (ntiles <= 0) return 0;
   ProfScope ps(K_BLEND_FWD, st);
-  if (v.want_aux)
-    blend_fwd_kernel<true><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight), point_count);
+  unsigned* pwb = reinterpret_cast<unsigned*>(point_weight);
+  const bool rec = v.contrib != nullptr;
+  if (v.want_aux && rec)
+    blend_fwd_kernel<true, true><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, pwb, point_count);
+  else if (v.want_aux)
+    blend_fwd_kernel<true, false><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, pwb, point_count);
+  else if (rec)
+    blend_fwd_kernel<false, true><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, pwb, point_count);
   else
-    blend_fwd_kernel<false><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, reinterpret_cast<unsigned*>(point_weight), point_count);
+    blend_fwd_kernel<false, false><<<ntiles, BLEND_THREADS, 0, st>>>(v, tile_start, sorted_ids, splat, image, final_T, n_contrib, pid_pixel, pw_pixel, pwb, point_count);
   LGR_CHECK_LAUNCH();
   return 0;
 }
