@@ -9,7 +9,9 @@
 // Backward: the same front-to-back walk (closed form of the published recurrence, see below).  Per contributing hit every
 // lane publishes two scalars; every 8 hits the warp contracts them against fixed per-pixel weights (pixel-coordinate
 // moments and cotangent-weighted sums) on the tensor cores (mma.sync m16n8k8, split TF32 = fp32 accuracy); the moments
-// become gradients once per staged splat, then 3 vector atomics per splat.
+// become gradients once per staged splat, then 3 vector atomics per splat.  With View::contrib the forward records which
+// sub-tiles composited each list entry and the backward (REC) walks exactly those pairs, stopping every pixel after its
+// last contributor (the forward's n_contrib) instead of re-testing boxes and transmittances.
 #include "lgr_common.cuh"
 #include "lgr_prof.cuh"
 
