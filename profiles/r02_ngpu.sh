@@ -13,9 +13,9 @@ run() {  # $1 = label, rest = extra bench args ; env in front
   echo "$label N=$N rc=$?" >> $OUT/summary.txt
 }
 run shard
-LGR_GRAPH=0 run shard_nograph --no-e2e
+if [ "${NOGRAPH:-1}" = "1" ]; then LGR_GRAPH=0 run shard_nograph --no-e2e; fi
 if [ "${HOSTSIZED:-1}" = "1" ]; then LGR_GRAPH=0 LGR_SYNC_FREE=0 run shard_hostsized --no-e2e; fi
-LGR_MULTI=band run band --no-e2e
+if [ "${BAND:-1}" = "1" ]; then LGR_MULTI=band run band --no-e2e; fi
 if [ "${TESTS:-1}" = "1" ]; then
   timeout 900 python -m pytest tests/test_gpu_multirank.py tests/test_zz_gpu_shard_multirank.py -q -m gpu --runxfail -p no:cacheprovider > $OUT/multirank.log 2>&1
   echo "multirank rc=$?" >> $OUT/summary.txt
