@@ -517,7 +517,7 @@ int launch_tile_scan(int ntiles, int32_t* tile_start, int32_t* cursor, int32_t* 
   return 0;
 }
 
-constexpr int LONG_SORT_GRID = 32;      // device-sized long-tile launch: CTAs stride over the (device-side) list of long tiles
+constexpr int LONG_SORT_GRID = 148;     // device-sized long-tile launch (208 KB of shared memory: one CTA per SM): CTAs stride over the device-side list of long tiles
 
 // meta_dev != nullptr: device-sized call -- num_inst is the CAPACITY of the instance buffers, max_len / num_long are ignored
 // (read from meta_dev on the device), tile_start is mutable (emptied on overflow).
