@@ -250,23 +250,41 @@ __global__ void __launch_bounds__(SHARD_THREADS)
 shard_return_packed_kernel(ShardLayout L, const float* __restrict__ xbuf, const float* __restrict__ dsplat_rows,
                            const float* __restrict__ pw_rows, const int32_t* __restrict__ pc_rows,
                            void* const* __restrict__ peer_base) {
-  const int32_t* count = reinterpret_cast<const int32_t*>(xbuf + L.off_count);
-  int64_t total = 0;
-  for (int s = 0; s < L.R; s++) total += count[s];
-  total *= 3;
-  for (int64_t t = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * SHARD_THREADS) {
-    int s = 0;
-    int64_t first = 0;
-    while (s + 1 < L.R && t >= first + (int64_t)count[s] * 3) { first += (int64_t)count[s] * 3; s++; }
-    const int64_t k = t - first;                                  // float4 index inside region s
-    const int64_t row = (int64_t)s * L.cap + k / 3;
-    float4 val = reinterpret_cast<const float4*>(dsplat_rows)[row * 3 + k % 3];
-    if (k % 3 == 2) {
-      val.y = pw_rows ? pw_rows[row] : 0.f;
-      val.z = pc_rows ? __int_as_float(pc_rows[row]) : 0.f;
+  // first[s] = index of the first float4 of region s in the concatenation of the used rows (3 float4 per row)
+  __shared__ int64_t first[SHARD_MAX_RANKS + 1];
+  if (threadIdx.x == 0) {
+    const int32_t* count = reinterpret_cast<const int32_t*>(xbuf + L.off_count);
+    int64_t acc = 0;
+    for (int s = 0; s < L.R; s++) { first[s] = acc; acc += (int64_t)count[s] * 3; }
+    first[L.R] = acc;
+  }
+  __syncthreads();
+  const int64_t total = first[L.R], stride = (int64_t)gridDim.x * SHARD_THREADS;
+  constexpr int U = 4;      // float4s in flight per thread: the loads are issued together, then the (mostly remote) stores
+  for (int64_t t0 = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x; t0 < total; t0 += U * stride) {
+    float4 val[U];
+    float4* dst[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int64_t t = t0 + u * stride;
+      dst[u] = nullptr;
+      if (t < total) {
+        int s = 0;
+        while (s + 1 < L.R && t >= first[s + 1]) s++;
+        const int64_t k = t - first[s];                               // float4 index inside region s
+        const int64_t row = (int64_t)s * L.cap + k / 3;
+        const int part = (int)(k % 3);
+        val[u] = reinterpret_cast<const float4*>(dsplat_rows)[row * 3 + part];
+        if (part == 2) {
+          val[u].y = pw_rows ? pw_rows[row] : 0.f;
+          val[u].z = pc_rows ? __int_as_float(pc_rows[row]) : 0.f;
+        }
+        dst[u] = reinterpret_cast<float4*>(reinterpret_cast<float*>(peer_base[s]) + L.off_dsplat) + (int64_t)L.me * L.cap * 3 + k;
+      }
     }
-    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(peer_base[s]) + L.off_dsplat) + (int64_t)L.me * L.cap * 3 + k;
-    *dst = val;
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (dst[u]) *dst[u] = val[u];
   }
 }
 
