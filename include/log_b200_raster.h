@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 14
+#define LGR_ABI_VERSION 15
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -94,6 +94,15 @@ typedef struct lgr_view {
   const int32_t* last_contrib_d; /* (H,W) int32 or NULL: the n_contrib_d output of lgr_forward_render (per pixel: list index + 1 of
                             its last contributor).  Read by lgr_backward / lgr_blend_backward together with contrib_d: a pixel
                             is finished once the sweep has passed its last contributor (both must be set, or neither). */
+  const int32_t* region_count_d; /* (num_regions) int32 or NULL.  Shard mode: the rows of the call are num_regions regions of
+                            region_cap rows each (rows = num_regions * region_cap) and only the first region_count_d[s] rows
+                            of region s are in use (lgr_shard_layout: the counts live in the exchange buffer at off_count).
+                            When set, lgr_shard_recv_bin[_aux] and lgr_forward_render[_device_sized] visit the used rows
+                            only -- unused rows are neither read nor written (their radii are stale) -- so their cost
+                            follows the rows a rank received, not the size of the exchange buffer. */
+  int64_t region_cap;    /* rows per region (with region_count_d) */
+  int32_t num_regions;   /* 1 .. LGR_SHARD_MAX_RANKS (with region_count_d) */
+  int32_t reserved0;
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */

@@ -73,8 +73,14 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
                    const int32_t* __restrict__ tile_start, int32_t* __restrict__ cursor, uint32_t* __restrict__ inst_key,
                    uint32_t* __restrict__ inst_val, int64_t capacity /* of inst_key / inst_val: stores beyond it are dropped */) {
   // No early return: big splats are scattered by the whole warp below (convergent ballots / shuffles).
-  int64_t i = (int64_t)blockIdx.x * SCATTER_THREADS + threadIdx.x;
-  bool live = i < n;
+  // Shard mode (View::region_count): the kernel strides over the USED rows only; otherwise the grid covers the n rows and
+  // the loop runs once.
+  __shared__ int64_t s_first[LGR_SHARD_MAX_RANKS + 1];
+  const int64_t total = v.region_count ? region_setup(v, s_first) : n;
+  for (int64_t base = (int64_t)blockIdx.x * SCATTER_THREADS; base < total; base += (int64_t)gridDim.x * SCATTER_THREADS) {
+  int64_t i = base + threadIdx.x;
+  bool live = i < total;
+  if (live && v.region_count) i = region_row(v, s_first, i);
   if (live && v.num_owners > 0) {      // band mode: slot i of the per-CTA id lists written by project_fwd (256 ids per CTA)
     const int b = (int)(i / 256), sl = (int)(i % 256);
     if (sl >= v.band_blk[b]) live = false;
@@ -156,6 +162,7 @@ bin_scatter_kernel(View v, int64_t n, const float* __restrict__ splat, const int
       if (pos < capacity) { inst_key[pos] = bkey; inst_val[pos] = bid; }
     }
   }
+  }      // rows
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -535,7 +542,8 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
   // can be non-empty while nothing reaches alpha >= 1/255), and with band_dsplat set it zeroes the visible rows.
   if (num_inst == 0 && v.num_owners == 0 && v.band_dsplat == nullptr) return 0;
   const int ntiles = v.gx * (v.row1 - v.row0);
-  const unsigned blocks = (unsigned)((n + SCATTER_THREADS - 1) / SCATTER_THREADS);
+  unsigned blocks = (unsigned)((n + SCATTER_THREADS - 1) / SCATTER_THREADS);
+  if (v.region_count && blocks > 148u * 16u) blocks = 148u * 16u;      // strides over the used rows (count known on the device only)
   {
     ProfScope ps(K_BIN_SCATTER, st);
     bin_scatter_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val,

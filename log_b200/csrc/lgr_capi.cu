@@ -47,6 +47,9 @@ static bool view_ok(const lgr_view* v) {
   if (v->tile_row_end > gy) return false;
   if (v->num_owners < 0 || (v->num_owners > 0 && (!v->band_ids_d || !v->band_count_d || !v->band_blk_d || !v->band_rows_d))) return false;
   if (v->gather_index_d && v->num_owners > 0) return false;      // the gather-fused call has no band mode
+  if (v->region_count_d && (v->num_regions <= 0 || v->num_regions > LGR_SHARD_MAX_RANKS || v->region_cap <= 0 || v->num_owners > 0 ||
+                            v->gather_index_d))
+    return false;
   return true;
 }
 
@@ -253,6 +256,10 @@ int lgr_shard_recv_bin_aux(const lgr_view* view, const lgr_shard_layout* layout,
                            int32_t* point_count_rows_d, void* stream) {
   if (!view_ok(view) || !layout_ok(layout) || !exchange_d || !dsplat_d || !tile_start_d || !tile_cursor_d || !meta_d) return LGR_E_BADARG;
   if (view->num_owners != 0) return LGR_E_BADARG;
+  // the view must carry the layout's region map: this call and the render that follows visit the used rows only
+  if (view->region_count_d != reinterpret_cast<const int32_t*>(exchange_d + layout->off_count) || view->region_cap != layout->cap ||
+      view->num_regions != layout->num_ranks)
+    return LGR_E_BADARG;
   if ((int64_t)layout->num_ranks * layout->cap > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const View v = make_view(view, (int64_t)layout->num_ranks * layout->cap);

@@ -37,6 +37,9 @@ struct View {
   const int32_t* pid_map;    // (n) or NULL: point_id_pixel = pid_map[winning row]
   uint8_t* contrib;          // (instances) or NULL: per list entry, the sub-tiles with a contributing pixel (forward -> backward)
   const int32_t* last_contrib;   // (H,W) or NULL: the forward's n_contrib (list index + 1 of each pixel's last contributor), backward only
+  const int32_t* region_count;   // (regions) or NULL: rows = regions x region_cap, the first region_count[s] rows of region s in use
+  int64_t region_cap;
+  int regions;
   int band_blocks;           // B
   const float* view;         // (4,4) transposed storage: t_j = sum_i p_i * view[i*4+j] + view[12+j]
   const float* proj;
@@ -47,6 +50,7 @@ struct View {
 inline View make_view(const lgr_view* v, int64_t n = 0) {
   View o;
   o.num_owners = v->num_owners; o.band_ids = v->band_ids_d; o.band_blk = v->band_blk_d; o.band_count = v->band_count_d; o.band_rows = v->band_rows_d; o.band_dsplat = v->band_dsplat_d; o.tile_rank = v->tile_rank_d; o.gather = v->gather_index_d; o.pid_map = v->pid_map_d; o.contrib = v->contrib_d; o.last_contrib = v->last_contrib_d;
+  o.region_count = v->region_count_d; o.region_cap = v->region_cap; o.regions = v->region_count_d ? v->num_regions : 0;
   o.owner_chunk = o.num_owners > 0 ? (int)LGR_OWNER_CHUNK(n, (int64_t)o.num_owners) : 256;
   if (o.owner_chunk < 256) o.owner_chunk = 256;
   o.band_blocks = (int)((n + 255) / 256);
@@ -213,6 +217,29 @@ __device__ __forceinline__ void tile_rect_tight(float px, float py, int rad, flo
   y0 = max(max(y0, ty0), row0); y1 = min(min(y1, ty1), row1);
   if (x1 < x0) x1 = x0;
   if (y1 < y0) y1 = y0;
+}
+
+// Region map (View::region_count, shard mode): rows = regions x region_cap, only the first region_count[s] rows of region s
+// are in use.  region_setup fills first[s] = number of used rows before region s (first[regions] = their total; `first` is
+// a shared array of LGR_SHARD_MAX_RANKS + 1 entries) and contains a block barrier: call it from convergent code.
+// region_row maps the t-th used row to its row index.
+__device__ __forceinline__ int64_t region_setup(const View& v, int64_t* first) {
+  if (threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int s = 0; s < v.regions; s++) {
+      first[s] = acc;
+      const int64_t c = v.region_count[s];
+      acc += c < 0 ? 0 : (c > v.region_cap ? v.region_cap : c);
+    }
+    first[v.regions] = acc;
+  }
+  __syncthreads();
+  return first[v.regions];
+}
+__device__ __forceinline__ int64_t region_row(const View& v, const int64_t* first, int64_t t) {
+  int s = 0;
+  while (s + 1 < v.regions && t >= first[s + 1]) s++;
+  return (int64_t)s * v.region_cap + (t - first[s]);
 }
 
 // Tile counting.  Per tile two counters share one 128-byte line: [0] splats covering <= 4 tiles, [1] the others.

@@ -177,28 +177,26 @@ shard_recv_count_kernel(View v, ShardLayout L, float* __restrict__ xbuf, float* 
                         int32_t* __restrict__ pc_rows) {
   __shared__ __align__(16) unsigned sStock[SHARD_WARPS];
   __shared__ __align__(16) int sVis[SHARD_WARPS];
-  const int64_t slot = (int64_t)blockIdx.x * SHARD_THREADS + threadIdx.x;
-  const int64_t total = (int64_t)L.R * L.cap;
-  const int32_t* count = reinterpret_cast<const int32_t*>(xbuf + L.off_count);
-  int32_t* radii = reinterpret_cast<int32_t*>(xbuf + L.off_radii);
+  // strides over the USED rows (the first count[s] rows of region s); unused rows are never touched -- every later kernel
+  // of the band render follows the same map (View::region_count)
+  __shared__ int64_t s_first[LGR_SHARD_MAX_RANKS + 1];
+  const int64_t total = region_setup(v, s_first);
+  const int32_t* radii = reinterpret_cast<const int32_t*>(xbuf + L.off_radii);
   unsigned stock = 0;
   int vis = 0;
-  bool big_splat = false;
-  int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
-  if (slot < total) {
-    const int s = (int)(slot / L.cap);
-    const int64_t j = slot - (int64_t)s * L.cap;
-    if (j >= count[s]) {
-      radii[slot] = 0;
-    } else {
+  for (int64_t base = (int64_t)blockIdx.x * SHARD_THREADS; base < total; base += (int64_t)gridDim.x * SHARD_THREADS) {
+    bool big_splat = false;
+    int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;
+    if (base + threadIdx.x < total) {
+      const int64_t slot = region_row(v, s_first, base + threadIdx.x);
       const float* rec = xbuf + L.off_splat + slot * LGR_SPLAT_FLOATS;
       const float4 r0 = *reinterpret_cast<const float4*>(rec);
       const float4 r1 = *reinterpret_cast<const float4*>(rec + 4);
       const int rad = radii[slot];
       int x0, y0, x1, y1;
       tile_rect(r0.x, r0.y, rad, v.gx, v.gy, x0, y0, x1, y1);
-      stock = (unsigned)((x1 - x0) * max(0, min(y1, v.row1) - max(y0, v.row0)));
-      vis = 1;
+      stock += (unsigned)((x1 - x0) * max(0, min(y1, v.row1) - max(y0, v.row0)));
+      vis += 1;
       tile_rect_tight(r0.x, r0.y, rad, r1.z, r1.w, v.gx, v.gy, v.row0, v.row1, x0, y0, x1, y1);
       big_splat = count_small_tiles(v, tile_count, slot, x0, y0, x1, y1);
       bx0 = x0; by0 = y0; bx1 = x1; by1 = y1;
@@ -207,8 +205,8 @@ shard_recv_count_kernel(View v, ShardLayout L, float* __restrict__ xbuf, float* 
       if (pw_rows) pw_rows[slot] = 0.f;      // per-row aux accumulators of the blend: only used rows are ever read back
       if (pc_rows) pc_rows[slot] = 0;
     }
+    warp_count_big_tiles(v, tile_count, big_splat, bx0, by0, bx1, by1);
   }
-  warp_count_big_tiles(v, tile_count, big_splat, bx0, by0, bx1, by1);
   const unsigned st_w = __reduce_add_sync(FULLMASK, stock);
   const int vis_w = __reduce_add_sync(FULLMASK, vis);
   if ((threadIdx.x & 31) == 0) { sStock[threadIdx.x >> 5] = st_w; sVis[threadIdx.x >> 5] = vis_w; }
@@ -364,8 +362,11 @@ int launch_shard_recv_count(const View& v, const ShardLayout& L, float* xbuf, fl
                             float* pw_rows, int32_t* pc_rows, cudaStream_t st) {
   const int64_t total = (int64_t)L.R * L.cap;
   if (total <= 0) return 0;
+  if (!v.region_count) return LGR_E_BADARG;
+  int64_t blocks = blocks_for(total);
+  if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope ps(K_SHARD_RECV, st);
-  shard_recv_count_kernel<<<blocks_for(total), SHARD_THREADS, 0, st>>>(v, L, xbuf, dsplat, tile_count, meta, pw_rows, pc_rows);
+  shard_recv_count_kernel<<<(unsigned)blocks, SHARD_THREADS, 0, st>>>(v, L, xbuf, dsplat, tile_count, meta, pw_rows, pc_rows);
   LGR_CHECK_LAUNCH();
   return 0;
 }

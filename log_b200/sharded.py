@@ -290,6 +290,9 @@ class SplatExchange:
         rank_rows = self._scratch('tile_rank', (self.world * self.cap, 4), torch.int32) if RANKED_BIN else None
         s.view_band = _make_view(settings, filter_mode, want_aux, K, self.band, s.keep, raw_params=raw_params, tile_rank=rank_rows,
                                  pid_map=self.recv_gid)      # point_id_pixel: received row -> global Gaussian index, in the kernel
+        # the receive and render kernels visit only the rows the sources filled (the first count[s] of each region)
+        s.view_band.region_count_d = self.buf.data_ptr() + 4 * int(self.layout.off_count)
+        s.view_band.region_cap, s.view_band.num_regions = self.cap, self.world
         H, W = s.view_full.image_height, s.view_full.image_width
         if H != self.image_height:
             raise ValueError('image height differs from the one the bands were cut for')

@@ -229,6 +229,15 @@ def test_shard_exchange_emulated(emu, world, W, H, n):
             L = lays[o]
             ntiles = gx * (band[1] - band[0])
             vb = make_view(H, W, band)
+            # the region map: receive, scatter and sort visit only the first count[s] rows of each region ...
+            vb.region_count_d = bufs[o].ctypes.data + 4 * L.off_count
+            vb.region_cap, vb.num_regions = cap, world
+            valid = np.zeros(rows, bool)
+            for s in range(world):
+                valid[s * cap:s * cap + want_rows[o, s].size] = True
+            # ... so what the unused rows hold must not matter: poison them (a huge radius would flood every tile list)
+            bufs[o][L.off_radii:L.off_radii + rows].view(np.int32)[~valid] = 1000
+            bufs[o][L.off_splat:L.off_splat + rows * 12].reshape(rows, 12)[~valid] = F(3.0)
             tile_start = np.full(ntiles + 1, -1, np.int32)
             cursor = np.zeros(33 * max(ntiles, 1), np.int32)
             meta = np.zeros(8, np.int32)
@@ -237,10 +246,7 @@ def test_shard_exchange_emulated(emu, world, W, H, n):
                                           P(meta)) == 0
             sp = bufs[o][L.off_splat:L.off_splat + rows * 12].reshape(rows, 12)
             rd = bufs[o][L.off_radii:L.off_radii + rows].view(np.int32)
-            valid = np.zeros(rows, bool)
-            for s in range(world):
-                valid[s * cap:s * cap + want_rows[o, s].size] = True
-            assert not rd[~valid].any()                                               # stale slots cleared
+            assert (rd[~valid] == 1000).all()                                         # unused rows are not touched
             assert not dsplat[o][valid].any() and np.array_equal(dsplat[o][~valid], before[~valid])
             assert meta[4] == valid.sum()
             # the owner's lists: rows in band tiles, ordered by (depth, row) == (depth, global index)
