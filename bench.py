@@ -530,14 +530,21 @@ def main():
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             res[mode] = float(te.item())
-        e2e = {'value': n / res[True], 'unit': 'Gaussians/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
-               'ms_per_step': res[True] * 1e3, 'steps': ne,
+        # Both schedules are end to end (every step's copies and its read-back are inside the timed region); which one wins
+        # depends on the box (host memory placement, PCIe contention with the peer traffic of the other ranks), so the
+        # headline is the better of the two and both are reported.
+        best = min(res, key=res.get)
+        e2e = {'value': n / res[best], 'unit': 'Gaussians/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+               'ms_per_step': res[best] * 1e3, 'steps': ne,
                'api': ('SplatExchange.rasterize + autograd (each rank copies the Gaussians it owns)' if shard is not None else
                        'rasterize_forward / rasterize_backward (band mode has no autograd front end)' if world > 1 else
                        'GaussianRasterizer(...) + loss.backward()'),
                'h2d': 'every step copies all of its inputs from pinned host memory into one of two preallocated device sets on a copy '
-                      'stream (double-buffered against the previous step) and reads the loss back; max over ranks, wall clock',
-               'ms_per_step_serial_copy': res[False] * 1e3}
+                      'stream and reads the loss back; max over ranks, wall clock.  Two schedules are timed: pipelined (the copies of '
+                      'step k+1 are issued before step k is read back) and serial (copy, compute, read back in turn); '
+                      'ms_per_step is the faster one (`schedule`)',
+               'schedule': 'pipelined' if best else 'serial',
+               'ms_per_step_pipelined': res[True] * 1e3, 'ms_per_step_serial_copy': res[False] * 1e3}
 
     if rank != 0:
         if world > 1:
