@@ -543,7 +543,7 @@ int launch_bin_and_sort(const View& v, int64_t n, int64_t num_inst, int max_len,
   if (num_inst == 0 && v.num_owners == 0 && v.band_dsplat == nullptr) return 0;
   const int ntiles = v.gx * (v.row1 - v.row0);
   unsigned blocks = (unsigned)((n + SCATTER_THREADS - 1) / SCATTER_THREADS);
-  if (v.region_count && blocks > 148u * 16u) blocks = 148u * 16u;      // strides over the used rows (count known on the device only)
+  if (v.region_count && blocks > (unsigned)LGR_REGION_GRID) blocks = (unsigned)LGR_REGION_GRID;      // strides over the used rows (count known on the device only)
   {
     ProfScope ps(K_BIN_SCATTER, st);
     bin_scatter_kernel<<<blocks, SCATTER_THREADS, 0, st>>>(v, n, splat, radii, tile_start, cursor, inst_key, inst_val,

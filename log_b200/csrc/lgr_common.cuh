@@ -219,6 +219,12 @@ __device__ __forceinline__ void tile_rect_tight(float px, float py, int rad, flo
   if (y1 < y0) y1 = y0;
 }
 
+// Grid of the kernels that stride over the used rows of a region map (their number is known on the device only).  The CPU
+// emulation builds with a tiny grid so that its tests take the loop more than once.
+#ifndef LGR_REGION_GRID
+#define LGR_REGION_GRID (148 * 16)
+#endif
+
 // Region map (View::region_count, shard mode): rows = regions x region_cap, only the first region_count[s] rows of region s
 // are in use.  region_setup fills first[s] = number of used rows before region s (first[regions] = their total; `first` is
 // a shared array of LGR_SHARD_MAX_RANKS + 1 entries) and contains a block barrier: call it from convergent code.

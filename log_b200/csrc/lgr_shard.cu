@@ -364,7 +364,7 @@ int launch_shard_recv_count(const View& v, const ShardLayout& L, float* xbuf, fl
   if (total <= 0) return 0;
   if (!v.region_count) return LGR_E_BADARG;
   int64_t blocks = blocks_for(total);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > LGR_REGION_GRID) blocks = LGR_REGION_GRID;
   ProfScope ps(K_SHARD_RECV, st);
   shard_recv_count_kernel<<<(unsigned)blocks, SHARD_THREADS, 0, st>>>(v, L, xbuf, dsplat, tile_count, meta, pw_rows, pc_rows);
   LGR_CHECK_LAUNCH();
