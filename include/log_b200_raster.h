@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 15
+#define LGR_ABI_VERSION 16
 #define LGR_TILE 16
 
 /* low-pass filter on the 2D covariance */
@@ -103,6 +103,13 @@ typedef struct lgr_view {
   int64_t region_cap;    /* rows per region (with region_count_d) */
   int32_t num_regions;   /* 1 .. LGR_SHARD_MAX_RANKS (with region_count_d) */
   int32_t reserved0;
+  const float* cov3D_precomp_d; /* (N,6) or NULL: the stock API's cov3D_precomp (upper triangle xx xy xz yy yz zz of the world-space
+                            covariance, diff_gaussian_rasterization's layout).  When set, lgr_forward_project / lgr_backward
+                            take the covariance from here (scale_modifier is NOT applied, as in the stock rasteriser),
+                            scales_d / rotations_d / dscales_d / drotations_d may be NULL, and lgr_backward writes
+                            dL/dcov3D into dcov3D_d.  Not available with raw_params or in band mode. */
+  float* dcov3D_d;       /* (N,6): gradient w.r.t. cov3D_precomp_d (off-diagonal entries receive the sum of the two symmetric
+                            partials, like the stock backward); required by lgr_backward when cov3D_precomp_d is set */
   const float* viewmatrix_d; /* (4,4) world_view_transform, stored transposed (LoG/dataset/base.py:40-46) */
   const float* projmatrix_d; /* (4,4) full_proj_transform, same convention */
   const float* campos_d;     /* (3,) */
@@ -125,6 +132,11 @@ int lgr_abi_version(void);
 int lgr_compute_radius(int64_t n, const float* means3D_d, const float* scales_d, const float* rotations_d,
                        const float* projmatrix_d, const float* viewmatrix_d, float focal_x, float focal_y,
                        float tan_fovx, float tan_fovy, float* radii_d, void* stream);
+
+/* visible_d[i] = 1 when point i lies in front of the near plane (view-space z > 0.2), else 0: the stock module's
+ * GaussianRasterizer.markVisible(positions) (diff_gaussian_rasterization; not called by LoG, part of the class LoG
+ * instantiates at LoG/render/renderer.py:77).  viewmatrix_d as in lgr_view. */
+int lgr_mark_visible(int64_t n, const float* means3D_d, const float* viewmatrix_d, uint8_t* visible_d, void* stream);
 
 /* Stage 1 of the forward: per-Gaussian projection + EWA covariance + colour, tile counting, tile scan.
  *   in : means3D (N,3) opacities (N) scales (N,3) rotations (N,4); colors_precomp (N,3) XOR shs (N,K,3)

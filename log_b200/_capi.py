@@ -12,14 +12,14 @@ LGR_SPLAT_FLOATS = 12
 LGR_GRAD_FLOATS = 12
 LGR_META_INTS = 8
 LGR_TILE_SCRATCH_INTS = 33
-LGR_ABI_VERSION = 15
+LGR_ABI_VERSION = 16
 LGR_STAGE_HEADER_FLOATS = 64
 LGR_ROW_FLOATS = 20
 
 EXPORTS = ('lgr_abi_version', 'lgr_sort_smem_capacity', 'lgr_compute_radius', 'lgr_forward_project',
            'lgr_forward_render', 'lgr_forward_render_device_sized', 'lgr_backward', 'lgr_grad_scatter_add', 'lgr_grad_scatter_add_staged', 'lgr_point_compact', 'lgr_sparse_adam', 'lgr_profile_enable', 'lgr_profile_collect',
            'lgr_profile_kernel_name', 'lgr_shard_send', 'lgr_shard_recv_bin', 'lgr_blend_backward', 'lgr_shard_return_rows',
-           'lgr_shard_gather', 'lgr_shard_recv_bin_aux', 'lgr_shard_return_packed', 'lgr_shard_gather_packed', 'lgr_tree_traverse')
+           'lgr_shard_gather', 'lgr_shard_recv_bin_aux', 'lgr_shard_return_packed', 'lgr_shard_gather_packed', 'lgr_tree_traverse', 'lgr_mark_visible')
 LGR_SHARD_MAX_RANKS = 32
 LGR_PROFILE_KERNELS = 12
 
@@ -30,7 +30,7 @@ class LgrView(ctypes.Structure):
                 ('scale_modifier', _f32), ('sh_degree', _i32), ('sh_coeffs', _i32), ('filter_mode', _i32),
                 ('want_aux', _i32), ('tile_row_begin', _i32), ('tile_row_end', _i32),
                 ('num_owners', _i32), ('raw_params', _i32), ('band_ids_d', _vp), ('band_blk_d', _vp), ('band_count_d', _vp), ('band_rows_d', _vp), ('band_dsplat_d', _vp), ('tile_rank_d', _vp), ('gather_index_d', _vp), ('pid_map_d', _vp), ('contrib_d', _vp), ('last_contrib_d', _vp),
-                ('region_count_d', _vp), ('region_cap', _i64), ('num_regions', _i32), ('reserved0', _i32),
+                ('region_count_d', _vp), ('region_cap', _i64), ('num_regions', _i32), ('reserved0', _i32), ('cov3D_precomp_d', _vp), ('dcov3D_d', _vp),
                 ('viewmatrix_d', _vp), ('projmatrix_d', _vp), ('campos_d', _vp), ('bg_d', _vp)]
 
 
@@ -67,6 +67,8 @@ def bind(lib):
     """Declare restype / argtypes of every entry point of include/log_b200_raster.h on a loaded library handle."""
     lib.lgr_abi_version.restype = ctypes.c_int
     lib.lgr_sort_smem_capacity.restype = _i32
+    lib.lgr_mark_visible.restype = ctypes.c_int
+    lib.lgr_mark_visible.argtypes = [_i64, _vp, _vp, _vp, _vp]
     lib.lgr_compute_radius.restype = ctypes.c_int
     lib.lgr_compute_radius.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _vp]
     lib.lgr_forward_project.restype = ctypes.c_int

@@ -5,6 +5,7 @@
 #include <math.h>
 
 namespace lgr {
+int launch_mark_visible(int64_t, const float*, const float*, uint8_t*, cudaStream_t);
 int launch_compute_radius(int64_t, const float*, const float*, const float*, const float*, const float*, float, float,
                           float, float, float*, cudaStream_t);
 int launch_project_fwd(const View&, int64_t, const float*, const float*, const float*, const float*, const float*,
@@ -68,6 +69,11 @@ int lgr_compute_radius(int64_t n, const float* means3D_d, const float* scales_d,
                                tan_fovx, tan_fovy, radii_d, (cudaStream_t)stream);
 }
 
+int lgr_mark_visible(int64_t n, const float* means3D_d, const float* viewmatrix_d, uint8_t* visible_d, void* stream) {
+  if (n < 0 || !viewmatrix_d || (n > 0 && (!means3D_d || !visible_d))) return LGR_E_BADARG;
+  return launch_mark_visible(n, means3D_d, viewmatrix_d, visible_d, (cudaStream_t)stream);
+}
+
 int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d, const float* opacities_d,
                         const float* scales_d, const float* rotations_d, const float* colors_precomp_d,
                         const float* shs_d, float* splat_d, int32_t* radii_d, uint8_t* clamped_d,
@@ -88,7 +94,9 @@ int lgr_forward_project(const lgr_view* view, int64_t n, const float* means3D_d,
     if (view->sh_degree < 0 || view->sh_degree > 3) return LGR_E_UNSUPPORTED;
     if (view->sh_coeffs < (view->sh_degree + 1) * (view->sh_degree + 1)) return LGR_E_BADARG;
   }
-  if (n > 0 && (!means3D_d || !opacities_d || !scales_d || !rotations_d || !splat_d || !radii_d)) return LGR_E_BADARG;
+  const bool cov3d = view->cov3D_precomp_d != nullptr;      // stock cov3D_precomp: scales / rotations not needed
+  if (n > 0 && (!means3D_d || !opacities_d || (!cov3d && (!scales_d || !rotations_d)) || !splat_d || !radii_d)) return LGR_E_BADARG;
+  if (cov3d && (view->raw_params || view->num_owners > 0)) return LGR_E_UNSUPPORTED;
   if (n > 0x7fffffffLL) return LGR_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const View v = make_view(view, n);
@@ -165,7 +173,9 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
   const bool use_sh = shs_d != nullptr && !log_sh;
   if (!log_sh && use_sh == (colors_precomp_d != nullptr)) return LGR_E_BADARG;
   if (log_sh && (!dshs_d || !view->campos_d || view->num_owners > 0)) return LGR_E_BADARG;
-  if (!means3D_d || !scales_d || !rotations_d || !splat_d || !radii_d || !dsplat_d) return LGR_E_BADARG;
+  const bool cov3d = view->cov3D_precomp_d != nullptr;
+  if (!means3D_d || (!cov3d && (!scales_d || !rotations_d)) || !splat_d || !radii_d || !dsplat_d) return LGR_E_BADARG;
+  if (cov3d && (!view->dcov3D_d || view->raw_params || view->num_owners > 0 || grad_rows_d || peer_stage_d)) return LGR_E_BADARG;
   if (view->raw_params && (!opacities_d || use_sh)) return LGR_E_BADARG;
   if (grad_rows_d || peer_stage_d) {
     if (view->num_owners <= 0 || use_sh) return LGR_E_BADARG;
@@ -173,7 +183,7 @@ int lgr_backward(const lgr_view* view, int64_t n, int64_t num_instances, const f
     if (num_rows < 0 || num_rows > n) return LGR_E_BADARG;
   } else {
     if (view->num_owners > 0) return LGR_E_BADARG;   // band mode writes no splat records outside the band: rows only
-    if (!dmeans3D_d || !dmeans2D_d || !dopacities_d || !dscales_d || !drotations_d) return LGR_E_BADARG;
+    if (!dmeans3D_d || !dmeans2D_d || !dopacities_d || (!cov3d && (!dscales_d || !drotations_d))) return LGR_E_BADARG;
     if (use_sh ? (!dshs_d || !clamped_d || !view->campos_d) : !dcolors_d) return LGR_E_BADARG;
   }
   if (num_instances > 0 && !sorted_ids_d) return LGR_E_BADARG;

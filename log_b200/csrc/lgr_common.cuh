@@ -40,6 +40,8 @@ struct View {
   const int32_t* region_count;   // (regions) or NULL: rows = regions x region_cap, the first region_count[s] rows of region s in use
   int64_t region_cap;
   int regions;
+  const float* cov3d;        // (N,6) or NULL: precomputed world-space covariance (stock cov3D_precomp) instead of scales / rotations
+  float* dcov3d;             // (N,6): its gradient (backward)
   int band_blocks;           // B
   const float* view;         // (4,4) transposed storage: t_j = sum_i p_i * view[i*4+j] + view[12+j]
   const float* proj;
@@ -51,6 +53,7 @@ inline View make_view(const lgr_view* v, int64_t n = 0) {
   View o;
   o.num_owners = v->num_owners; o.band_ids = v->band_ids_d; o.band_blk = v->band_blk_d; o.band_count = v->band_count_d; o.band_rows = v->band_rows_d; o.band_dsplat = v->band_dsplat_d; o.tile_rank = v->tile_rank_d; o.gather = v->gather_index_d; o.pid_map = v->pid_map_d; o.contrib = v->contrib_d; o.last_contrib = v->last_contrib_d;
   o.region_count = v->region_count_d; o.region_cap = v->region_cap; o.regions = v->region_count_d ? v->num_regions : 0;
+  o.cov3d = v->cov3D_precomp_d; o.dcov3d = v->dcov3D_d;
   o.owner_chunk = o.num_owners > 0 ? (int)LGR_OWNER_CHUNK(n, (int64_t)o.num_owners) : 256;
   if (o.owner_chunk < 256) o.owner_chunk = 256;
   o.band_blocks = (int)((n + 255) / 256);

@@ -16,6 +16,20 @@ __device__ __forceinline__ void load3(const float* __restrict__ p, int64_t i, fl
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// markVisible of the stock module (diff_gaussian_rasterization's GaussianRasterizer.markVisible): a point is visible
+// when its view-space depth exceeds the near plane -- the same cull the projection applies (NEAR_Z)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PROJ_THREADS)
+mark_visible_kernel(int64_t n, const float* __restrict__ means, const float* __restrict__ view, uint8_t* __restrict__ visible) {
+  const int64_t i = (int64_t)blockIdx.x * PROJ_THREADS + threadIdx.x;
+  if (i >= n) return;
+  float p[3];
+  load3(means, i, p);
+  const float z = p[0] * __ldg(view + 2) + p[1] * __ldg(view + 6) + p[2] * __ldg(view + 10) + __ldg(view + 14);
+  visible[i] = z > NEAR_Z ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // compute_radius  (reference: LoG/cuda/compute_radius_kernel.cu:107-156)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PROJ_THREADS)
@@ -44,7 +58,8 @@ compute_radius_kernel(int64_t n, const float* __restrict__ means, const float* _
 // LOG_SH (with USE_SH = false and View::raw_params): LoG's colour activation (LoG/model/activation.py:27-34) fused --
 // rgb = SH2RGB(dc) + eval_sh_wobase(dir, rest, degree) with dc = `colors` (N,3) raw and rest = `shs` (N,K,3); unlike the
 // stock SH path there is NO clamp at 0 and the direction comes from the DETACHED position (no gradient to the mean).
-template <bool USE_SH, bool LOG_SH = false>
+// COV3D: the world-space covariance comes precomputed from View::cov3d (stock cov3D_precomp) instead of scales / rotations.
+template <bool USE_SH, bool LOG_SH = false, bool COV3D = false>
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ opac,
                    const float* __restrict__ scales, const float* __restrict__ rots,
@@ -125,20 +140,27 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   // gather-fused call (lgr_view.gather_index_d): row i of every output is Gaussian gather[i] of the input tables
   const int64_t src = (v.gather && work) ? v.gather[i] : i;
   if (work) {
-    float p[3], s[3], R[9], Sg[9];
+    float p[3], Sg[9];
     load3(means, src, p);
-    load3(scales, src, s);
-    float4 q = ldg4(rots + 4 * src);
-    if (v.raw_params) {
-      float inv;
+    if (COV3D) {      // upper triangle xx xy xz yy yz zz, used as given (no scale modifier, like the stock rasteriser)
+      const float* c6 = v.cov3d + 6 * src;
+      const float cxx = __ldg(c6), cxy = __ldg(c6 + 1), cxz = __ldg(c6 + 2), cyy = __ldg(c6 + 3), cyz = __ldg(c6 + 4), czz = __ldg(c6 + 5);
+      Sg[0] = cxx; Sg[1] = cxy; Sg[2] = cxz; Sg[3] = cxy; Sg[4] = cyy; Sg[5] = cyz; Sg[6] = cxz; Sg[7] = cyz; Sg[8] = czz;
+    } else {
+      float s[3], R[9];
+      load3(scales, src, s);
+      float4 q = ldg4(rots + 4 * src);
+      if (v.raw_params) {
+        float inv;
 #pragma unroll
-      for (int k = 0; k < 3; k++) s[k] = expf(s[k]);
-      q = act_normalize(q, inv);
+        for (int k = 0; k < 3; k++) s[k] = expf(s[k]);
+        q = act_normalize(q, inv);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) s[k] *= v.scale_mod;
+      quat_to_R(q, R);
+      cov3d(s, R, Sg);
     }
-#pragma unroll
-    for (int k = 0; k < 3; k++) s[k] *= v.scale_mod;
-    quat_to_R(q, R);
-    cov3d(s, R, Sg);
     Cov2D cv;
     cov2d(sV, p, Sg, v.fx, v.fy, v.tanfovx, v.tanfovy, v.filter_mode, cv);
     float det;
@@ -257,7 +279,7 @@ project_fwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
 // ---------------------------------------------------------------------------------------------------------
 // backward projection: dsplat (d/dpx, d/dpy, d/dconic xyz, d/dopacity, d/drgb) -> input gradients
 // ---------------------------------------------------------------------------------------------------------
-template <bool USE_SH, bool ROWS, bool LOG_SH = false>
+template <bool USE_SH, bool ROWS, bool LOG_SH = false, bool COV3D = false>
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const float* __restrict__ opac,
                    const float* __restrict__ scales, const float* __restrict__ rots, const float* __restrict__ shs, const int32_t* __restrict__ radii,
@@ -297,18 +319,25 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     const float4 g2 = ldg4(dsplat + i * LGR_GRAD_FLOATS + 8);   // d/db
     float p[3], s0[3], s[3], R[9], Sg[9];
     load3(means, src, p);
-    load3(scales, src, s0);
-    float4 q = ldg4(rots + 4 * src);
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
     float q_inv = 1.0f;
-    if (v.raw_params) {
+    if (COV3D) {
+      const float* c6 = v.cov3d + 6 * src;
+      const float cxx = __ldg(c6), cxy = __ldg(c6 + 1), cxz = __ldg(c6 + 2), cyy = __ldg(c6 + 3), cyz = __ldg(c6 + 4), czz = __ldg(c6 + 5);
+      Sg[0] = cxx; Sg[1] = cxy; Sg[2] = cxz; Sg[3] = cxy; Sg[4] = cyy; Sg[5] = cyz; Sg[6] = cxz; Sg[7] = cyz; Sg[8] = czz;
+    } else {
+      load3(scales, src, s0);
+      q = ldg4(rots + 4 * src);
+      if (v.raw_params) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) s0[k] = expf(s0[k]);
-      q = act_normalize(q, q_inv);
+        for (int k = 0; k < 3; k++) s0[k] = expf(s0[k]);
+        q = act_normalize(q, q_inv);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) s[k] = s0[k] * v.scale_mod;
+      quat_to_R(q, R);
+      cov3d(s, R, Sg);
     }
-#pragma unroll
-    for (int k = 0; k < 3; k++) s[k] = s0[k] * v.scale_mod;
-    quat_to_R(q, R);
-    cov3d(s, R, Sg);
     Cov2D cv;
     cov2d(sV, p, Sg, v.fx, v.fy, v.tanfovx, v.tanfovy, v.filter_mode, cv);
     dop = g1.y;
@@ -333,8 +362,13 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     for (int r = 0; r < 3; r++)
 #pragma unroll
       for (int j = 0; j < 3; j++) dS[r * 3 + j] = cv.T[r] * GT[j] + cv.T[3 + r] * GT[3 + j];
+    if (COV3D) {      // symmetric storage: an off-diagonal entry collects both partials
+      float* d6 = v.dcov3d + 6 * i;
+      d6[0] = dS[0]; d6[1] = dS[1] + dS[3]; d6[2] = dS[2] + dS[6]; d6[3] = dS[4]; d6[4] = dS[5] + dS[7]; d6[5] = dS[8];
+    }
     // Sigma = M M^T, M = R diag(s): dM = 2 dS M
     float dR[9];
+    if (!COV3D) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       float acc = 0.f;
@@ -353,6 +387,7 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
       dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
       dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
     }
+    }      // !COV3D
     // dT = 2 G T Sigma ; dJ = dT W^T  (only J00,J02,J11,J12 depend on t)
     float TS[6], dT[6];
 #pragma unroll
@@ -431,6 +466,11 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
     float* dsh = dshs + (int64_t)i * K * 3;
     for (int k = 0; k < K * 3; k++) dsh[k] = 0.f;
   }
+  if (COV3D && active && !live) {
+    float* d6 = v.dcov3d + 6 * i;
+#pragma unroll
+    for (int k = 0; k < 6; k++) d6[k] = 0.f;
+  }
   if (v.raw_params && live) {      // chain rule through LoG's activations (activation.py:36-44)
     float s_act[3];
     load3(scales, src, s_act);
@@ -503,8 +543,10 @@ project_bwd_kernel(View v, int64_t n, const float* __restrict__ means, const flo
   dmeans[3 * i] = dm[0]; dmeans[3 * i + 1] = dm[1]; dmeans[3 * i + 2] = dm[2];
   dmeans2D[3 * i] = dm2[0]; dmeans2D[3 * i + 1] = dm2[1]; dmeans2D[3 * i + 2] = 0.f;
   dopac[i] = dop;
-  dscales[3 * i] = dsc[0]; dscales[3 * i + 1] = dsc[1]; dscales[3 * i + 2] = dsc[2];
-  reinterpret_cast<float4*>(drots)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+  if (!COV3D) {
+    dscales[3 * i] = dsc[0]; dscales[3 * i + 1] = dsc[1]; dscales[3 * i + 2] = dsc[2];
+    reinterpret_cast<float4*>(drots)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+  }
   if (!USE_SH) { dcolors[3 * i] = drgb[0]; dcolors[3 * i + 1] = drgb[1]; dcolors[3 * i + 2] = drgb[2]; }
 }
 
@@ -636,13 +678,24 @@ int launch_compute_radius(int64_t n, const float* means, const float* scales, co
   return 0;
 }
 
+int launch_mark_visible(int64_t n, const float* means, const float* view, uint8_t* visible, cudaStream_t st) {
+  if (n == 0) return 0;
+  mark_visible_kernel<<<(unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS), PROJ_THREADS, 0, st>>>(n, means, view, visible);
+  LGR_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_project_fwd(const View& v, int64_t n, const float* means, const float* opac, const float* scales,
                        const float* rots, const float* colors, const float* shs, float* splat, int32_t* radii,
                        uint8_t* clamped, int32_t* tile_count, int32_t* meta, cudaStream_t st) {
   if (n == 0) return 0;
   const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
   ProfScope ps(K_PROJECT_FWD, st);
-  if (colors && shs)      // LoG-style SH on top of raw DC colours (checked by the caller: raw_params, no band mode)
+  if (v.cov3d && colors)      // stock cov3D_precomp (checked by the caller: no raw_params, no band mode)
+    project_fwd_kernel<false, false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
+  else if (v.cov3d)
+    project_fwd_kernel<true, false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
+  else if (colors && shs)      // LoG-style SH on top of raw DC colours (checked by the caller: raw_params, no band mode)
     project_fwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
   else if (colors)
     project_fwd_kernel<false><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, colors, shs, splat, radii, clamped, tile_count, meta);
@@ -663,7 +716,11 @@ int launch_project_bwd(const View& v, int64_t n, const float* means, const float
   if (n == 0) return 0;
   const unsigned blocks = (unsigned)((n + PROJ_THREADS - 1) / PROJ_THREADS);
   ProfScope ps(K_PROJECT_BWD, st);
-  if (grad_rows || peer_stage)
+  if (v.cov3d && !use_sh)
+    project_bwd_kernel<false, false, false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
+  else if (v.cov3d)
+    project_bwd_kernel<true, false, false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
+  else if (grad_rows || peer_stage)
     project_bwd_kernel<false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);
   else if (!use_sh && shs)      // LoG-style SH: dcolors (DC) and dshs (rest) both written
     project_bwd_kernel<false, false, true><<<blocks, PROJ_THREADS, 0, st>>>(v, n, means, opac, scales, rots, shs, radii, clamped, dsplat, dmeans, dmeans2D, dopac, dscales, drots, dcolors, dshs, grad_rows, peer_stage, my_rank);

@@ -11,6 +11,8 @@ Reference surface reproduced here (all call sites are in /root/reference):
     ``(image, radii, point_id_pixel, point_weight_pixel, point_weight)`` (renderer.py:154-155)
   * ``rasterizer.compute_radius(xyz, scaling, rotation)`` (fork only) -- LoG/model/level_of_gaussian.py:59
   * ``means2D.grad`` is populated with d loss / d (NDC x, y)        -- read at LoG/model/counter.py:40
+  * of the stock class but unused by LoG: ``cov3D_precomp`` (N,6) instead of scales / rotations (always None at
+    renderer.py:133,149), ``markVisible(positions)``, ``raster_settings.debug`` (synchronise after each pass)
 
 PyTorch is used for device memory, the current stream and autograd plumbing only; every computation is a
 hand-written sm_100a kernel behind the C ABI.  There is no CPU path: CPU tensors raise.
@@ -75,7 +77,7 @@ def _stream(device=None):
 
 def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: bool, sh_coeffs: int, tile_rows, keep,
                num_owners=0, band_ids=None, band_count=None, band_blk=None, band_rows=None, band_dsplat=None,
-               raw_params=False, tile_rank=None, gather_index=None, pid_map=None):
+               raw_params=False, tile_rank=None, gather_index=None, pid_map=None, cov3D_precomp=None):
     dev = s.viewmatrix.device
     vm, pm = _f32c(s.viewmatrix, 'viewmatrix'), _f32c(s.projmatrix, 'projmatrix', dev)
     bg = _f32c(s.bg, 'bg', dev)
@@ -98,6 +100,7 @@ def _make_view(s: GaussianRasterizationSettings, filter_mode: int, want_aux: boo
     v.tile_rank_d = tile_rank.data_ptr() if tile_rank is not None else None
     v.gather_index_d = gather_index.data_ptr() if gather_index is not None else None
     v.pid_map_d = pid_map.data_ptr() if pid_map is not None else None
+    v.cov3D_precomp_d = cov3D_precomp.data_ptr() if cov3D_precomp is not None else None
     v.viewmatrix_d, v.projmatrix_d = vm.data_ptr(), pm.data_ptr()
     v.campos_d = cp.data_ptr() if cp is not None else None
     v.bg_d = bg.data_ptr()
@@ -108,7 +111,7 @@ class RasterState:
     """Buffers produced by the forward and consumed by the backward (kept alive by autograd)."""
     __slots__ = ('view', 'keep', 'n', 'num_instances', 'max_tile_len', 'stock_instances', 'num_visible', 'splat',
                  'radii', 'clamped', 'tile_start', 'sorted_ids', 'final_T', 'n_contrib', 'image', 'sh', 'num_owners',
-                 'band_ids', 'band_count', 'band_counts_host', 'point_count', 'meta')
+                 'band_ids', 'band_count', 'band_counts_host', 'point_count', 'meta', 'cov3D', 'dcov3D')
 
     def read_stats(self):
         """Counters of this forward, read back from meta_d (synchronises): D, longest tile list, D by the stock rule, visible
@@ -120,18 +123,22 @@ class RasterState:
 
 def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_precomp, shs, filter_mode, want_aux,
                       tile_rows=None, num_owners=0, raw_params=False, prezero_dsplat=None, gather_index=None,
-                      instance_capacity=None):
+                      instance_capacity=None, cov3D_precomp=None):
     """Run the forward through the C ABI.  Returns (image, radii, pid, pwp, point_weight, state).
     num_owners > 0 (multi-GPU band mode, see log_b200/sharded.py): also compact the ids of the Gaussians reaching the
     band `tile_rows`, grouped by owner rank; the backward then returns packed gradient rows instead of dense tensors.
     raw_params=True: scales / opacities / rotations / colors_precomp are LoG's RAW parameters; exp / sigmoid / normalize /
     SH2RGB (LoG/model/activation.py:36-44) run inside the projection kernels and the gradients are w.r.t. the raw values.
     With raw_params and BOTH colors_precomp (raw DC, (N,3)) and shs (the rest coefficients, (N,K,3)) LoG's whole colour
-    activation is fused: SH2RGB(dc) + eval_sh_wobase(dir, shs, settings.sh_degree), no clamp, direction detached."""
+    activation is fused: SH2RGB(dc) + eval_sh_wobase(dir, shs, settings.sh_degree), no clamp, direction detached.
+    cov3D_precomp (N,6): the stock API's precomputed world-space covariance (xx xy xz yy yz zz) instead of scales / rotations
+    (pass those as None); the backward then returns its gradient in state.dcov3D."""
     lib = _capi.load()
     dev = means3D.device
+    if cov3D_precomp is not None and (raw_params or num_owners > 0):
+        raise _capi.LgrError('cov3D_precomp is not available with raw_params or in band mode')
     for name, t in (('opacities', opacities), ('scales', scales), ('rotations', rotations), ('colors_precomp', colors_precomp),
-                    ('shs', shs), ('viewmatrix', settings.viewmatrix), ('projmatrix', settings.projmatrix), ('bg', settings.bg)):
+                    ('shs', shs), ('cov3D_precomp', cov3D_precomp), ('viewmatrix', settings.viewmatrix), ('projmatrix', settings.projmatrix), ('bg', settings.bg)):
         if t is not None and t.device != dev:
             raise _capi.LgrError(f'{name} is on {t.device}, means3D on {dev}: all inputs of a call must share one device')
     n = int(means3D.shape[0])
@@ -164,7 +171,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     tile_rank = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev) if RANKED_BIN else None
     keep.append(tile_rank)
     view = _make_view(settings, filter_mode, want_aux, K, tile_rows, keep, num_owners, band_ids, band_count, band_blk, band_rows, band_dsplat,
-                      raw_params, tile_rank, gather_index)
+                      raw_params, tile_rank, gather_index, cov3D_precomp=cov3D_precomp)
     H, W = view.image_height, view.image_width
     gx, gy = (W + 15) // 16, (H + 15) // 16
     rows = gy if tile_rows is None else int(tile_rows[1]) - int(tile_rows[0])
@@ -230,6 +237,7 @@ def rasterize_forward(settings, means3D, opacities, scales, rotations, colors_pr
     s.view, s.keep, s.n, s.num_instances, s.max_tile_len = view, keep, n, D, max_len
     s.stock_instances, s.num_visible = stock_D, (int(m[4]) if m is not None else None)
     s.meta = meta
+    s.cov3D, s.dcov3D = cov3D_precomp, None
     s.splat, s.radii, s.clamped, s.tile_start, s.sorted_ids = splat, radii, clamped, tile_start, sorted_ids
     s.final_T, s.n_contrib, s.image, s.sh = final_T, n_contrib, image, shs is not None
     s.point_count = pc
@@ -272,8 +280,12 @@ def rasterize_backward(state: RasterState, grad_image, means3D, opacities, scale
     dmeans3D = torch.empty((n, 3), **f32)
     dmeans2D = torch.empty((n, 3), **f32)
     dopac = torch.empty((n,), **f32)
-    dscales = torch.empty((n, 3), **f32)
-    drot = torch.empty((n, 4), **f32)
+    cov = state.cov3D is not None
+    dscales = None if cov else torch.empty((n, 3), **f32)
+    drot = None if cov else torch.empty((n, 4), **f32)
+    if cov:      # stock cov3D_precomp: the covariance gradient replaces the scale / rotation gradients
+        state.dcov3D = torch.empty((n, 6), **f32)
+        state.view.dcov3D_d = state.dcov3D.data_ptr()
     dcolors = torch.empty((n, 3), **f32) if colors_precomp is not None else None
     dshs = torch.empty((n,) + tuple(shs.shape[1:]), **f32) if shs is not None else None
     _capi.check(lib.lgr_backward(ctypes.byref(state.view), n, state.num_instances, _ptr(means3D), _ptr(opacities),
@@ -307,25 +319,28 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, colors_precomp, shs, scales, rotations, settings, filter_mode, want_aux,
-                tile_rows, raw_params=False, prezero_dsplat=False, instance_capacity=None, holder=None):
+                tile_rows, raw_params=False, prezero_dsplat=False, instance_capacity=None, holder=None, cov3D_precomp=None):
         dev = means3D.device
         m = _f32c(means3D, 'means3D')
         o = _f32c(opacities, 'opacities', dev)
-        sc = _f32c(scales, 'scales', dev)
-        r = _f32c(rotations, 'rotations', dev)
+        cov = _f32c(cov3D_precomp, 'cov3D_precomp', dev)
+        sc = _f32c(scales, 'scales', dev) if cov is None else None
+        r = _f32c(rotations, 'rotations', dev) if cov is None else None
         c = _f32c(colors_precomp, 'colors_precomp', dev)
         sh = _f32c(shs, 'shs', dev)
         image, radii, pid, pwp, pw, state = rasterize_forward(settings, m, o, sc, r, c, sh, filter_mode, want_aux, tile_rows,
                                                               raw_params=raw_params, prezero_dsplat=prezero_dsplat,
-                                                              instance_capacity=instance_capacity)
+                                                              instance_capacity=instance_capacity, cov3D_precomp=cov)
         if holder is not None:
             holder['state'] = state
         state.image = None          # the backward re-reads the rendered image: saved below so autograd guards it
         ctx.state = state
         ctx.opacity_shape = opacities.shape
-        ctx.save_for_backward(m, o, sc, r, c if c is not None else torch.empty(0, device=dev),
-                              sh if sh is not None else torch.empty(0, device=dev), image)
-        ctx.has_color, ctx.has_sh = c is not None, sh is not None
+        none = torch.empty(0, device=dev)
+        ctx.save_for_backward(m, o, sc if sc is not None else none, r if r is not None else none, c if c is not None else none,
+                              sh if sh is not None else none, image, cov if cov is not None else none)
+        ctx.has_color, ctx.has_sh, ctx.has_cov = c is not None, sh is not None, cov is not None
+        ctx.debug = bool(getattr(settings, 'debug', False))
         if want_aux:      # the winner histogram travels as a sixth (non-differentiable) output: no process-global state
             ctx.mark_non_differentiable(radii, pid, pwp, pw, state.point_count)
             return image, radii, pid, pwp, pw, state.point_count
@@ -334,12 +349,18 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_image, *unused):
-        m, o, sc, r, c, sh, image = ctx.saved_tensors
+        m, o, sc, r, c, sh, image, cov = ctx.saved_tensors
         c = c if ctx.has_color else None
         sh = sh if ctx.has_sh else None
+        if ctx.has_cov:
+            sc = r = None
+            ctx.state.cov3D = cov
         ctx.state.image = image
         dm3, dm2, dop, dsc, drot, dcol, dsh = rasterize_backward(ctx.state, grad_image, m, o, sc, r, c, sh)
-        return dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None, None, None, None, None
+        if ctx.debug and m.is_cuda:
+            torch.cuda.synchronize(m.device)
+        return (dm3, dm2, dop.reshape(ctx.opacity_shape), dcol, dsh, dsc, drot, None, None, None, None, None, None, None, None,
+                ctx.state.dcov3D)
 
 
 class GaussianRasterizer(nn.Module):
@@ -356,11 +377,13 @@ class GaussianRasterizer(nn.Module):
         self.last_state = None
 
     def markVisible(self, positions):
-        """Stock API: boolean mask of points in front of the near plane (view z > 0.2)."""
-        with torch.no_grad():
-            V = self.raster_settings.viewmatrix
-            z = positions @ V[:3, 2] + V[3, 2]
-            return z > 0.2
+        """Stock API: boolean mask of the points in front of the near plane (view z > 0.2), `lgr_mark_visible`."""
+        lib = _capi.load()
+        p = _f32c(positions.detach(), 'positions')
+        V = _f32c(self.raster_settings.viewmatrix, 'viewmatrix', p.device)
+        out = torch.empty((int(p.shape[0]),), dtype=torch.uint8, device=p.device)
+        _capi.check(lib.lgr_mark_visible(int(p.shape[0]), _ptr(p), _ptr(V), _ptr(out), _stream(p.device)), 'lgr_mark_visible')
+        return out.bool()
 
     def compute_radius(self, xyz, scaling, rotation):
         """Fork API (level_of_gaussian.py:59): projected 3-sigma radius in pixels, 0 when culled."""
@@ -373,10 +396,11 @@ class GaussianRasterizer(nn.Module):
         log_sh = raw_params and shs is not None and colors_precomp is not None      # LoG's colour activation fused
         if (shs is None) == (colors_precomp is None) and not log_sh:
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
-        if cov3D_precomp is not None:
-            raise NotImplementedError('cov3D_precomp is not supported: LoG always passes None (renderer.py:134,149)')
-        if scales is None or rotations is None:
-            raise Exception('Please provide scales and rotations')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        if cov3D_precomp is not None and raw_params:
+            raise NotImplementedError('raw_params (LoG\'s fused activations) needs scales and rotations, not cov3D_precomp')
         fork = self.flavour == FLAVOUR_FORK
         if fork:
             filter_mode = LGR_FILTER_MAX if use_filter else LGR_FILTER_NONE
@@ -387,12 +411,14 @@ class GaussianRasterizer(nn.Module):
                                       '(LoG layout, activation.py:27-34) as shs')
         # will a backward follow?  (decided here: inside autograd.Function.forward grad mode is always off)
         needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in
-                                                     (means3D, means2D, opacities, colors_precomp, shs, scales, rotations))
+                                                     (means3D, means2D, opacities, colors_precomp, shs, scales, rotations, cov3D_precomp))
         holder = {}
         out = _RasterizeGaussians.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
                                         self.raster_settings, filter_mode, fork, self.tile_rows, raw_params,
-                                        PREZERO_DSPLAT and needs_grad, self.instance_capacity, holder)
+                                        PREZERO_DSPLAT and needs_grad, self.instance_capacity, holder, cov3D_precomp)
         self.last_state = holder.get('state')
+        if self.raster_settings.debug and means3D.is_cuda:      # stock `debug`: surface a kernel fault at the call that caused it
+            torch.cuda.synchronize(means3D.device)
         # fork flavour: per-Gaussian histogram of the per-pixel winners (feeds point_id_count()); kept on THIS rasterizer
         # object (LoG builds one per view, renderer.py:77), the 5-tuple of the reference is what is returned
         self.last_point_count = out[5] if fork else None

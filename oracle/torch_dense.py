@@ -68,6 +68,14 @@ def cov3d(scales: torch.Tensor, rotations: torch.Tensor, scale_modifier: float =
     return L @ L.transpose(-1, -2)
 
 
+def cov3d_from_precomp(cov6: torch.Tensor) -> torch.Tensor:
+    """The stock API's cov3D_precomp (N,6) = upper triangle (xx, xy, xz, yy, yz, zz) of the world-space covariance
+    (diff_gaussian_rasterization: computeCov3D's output layout, read back by computeCov2D) -> (N,3,3) symmetric.  The
+    stock rasteriser uses it as given: no scale modifier."""
+    xx, xy, xz, yy, yz, zz = cov6.unbind(-1)
+    return torch.stack([xx, xy, xz, xy, yy, yz, xz, yz, zz], dim=-1).reshape(-1, 3, 3)
+
+
 def cov2d(Sigma, means3D, cam: Camera, filter_mode: int):
     """geometry.py:91-130 (computeCov2D0) / compute_radius_kernel.cu:63-105.
     Returns (a, b, c) = (cov_xx, cov_xy, cov_yy) after the low-pass filter, and the view-space point t."""
@@ -141,7 +149,8 @@ def eval_sh(deg: int, shs: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
     return res + 0.5
 
 
-def project(means3D, scales, rotations, cam: Camera, filter_mode: int, means2D: Optional[torch.Tensor] = None):
+def project(means3D, scales, rotations, cam: Camera, filter_mode: int, means2D: Optional[torch.Tensor] = None,
+            cov3D_precomp: Optional[torch.Tensor] = None):
     """Per-Gaussian stage.  Returns dict with pixel centre xy (N,2), depth, conic (N,3), float/ceil radius,
     tile rect (N,4) and `valid`.  [B] for cull/rect rules, [V] for the covariance algebra."""
     P = cam.projmatrix
@@ -151,7 +160,7 @@ def project(means3D, scales, rotations, cam: Camera, filter_mode: int, means2D: 
     ndc = hom[:, :2] * pw[:, None]
     if means2D is not None:          # dummy zero input whose .grad is dL/d(ndc xy)  (renderer.py:135, counter.py:40)
         ndc = ndc + means2D[:, :2]
-    Sigma = cov3d(scales, rotations, cam.scale_modifier)
+    Sigma = cov3d_from_precomp(cov3D_precomp) if cov3D_precomp is not None else cov3d(scales, rotations, cam.scale_modifier)
     a, b, c, t = cov2d(Sigma, means3D, cam, filter_mode)
     depth = t[:, 2]
     radf, det = radius_from_cov(a, b, c)
@@ -175,13 +184,13 @@ def project(means3D, scales, rotations, cam: Camera, filter_mode: int, means2D: 
 
 
 def render(means3D, opacities, scales, rotations, cam: Camera, colors_precomp=None, shs=None,
-           filter_mode: int = FILTER_ADD, means2D=None, pixel_chunk: int = 8192, return_aux: bool = True):
+           filter_mode: int = FILTER_ADD, means2D=None, pixel_chunk: int = 8192, return_aux: bool = True, cov3D_precomp=None):
     """Full forward.  Returns dict(image (3,H,W), radii (N,) int, point_id_pixel (H,W) long, point_weight_pixel (H,W),
     point_weight (N,), final_T (H,W), n_instances D).  Differentiable w.r.t. every float input via autograd."""
     N = means3D.shape[0]
     H_, W_ = cam.image_height, cam.image_width
     dt, dev = means3D.dtype, means3D.device
-    pr = project(means3D, scales, rotations, cam, filter_mode, means2D)
+    pr = project(means3D, scales, rotations, cam, filter_mode, means2D, cov3D_precomp)
     if colors_precomp is None:
         dirs = means3D - cam.campos[None]
         dirs = dirs / torch.linalg.norm(dirs, dim=-1, keepdim=True)

@@ -169,3 +169,12 @@ def test_long_tile_lists(emulated_backend, n):
     """Lists beyond the main sort launch (the long-tile launch) and beyond the shared-memory capacity (LSD fallback over
     global scratch), through the public API, with thousands of splats per pixel."""
     gp.test_long_tile_lists(True, n)
+
+
+@pytest.mark.parametrize('flavour', ['stock', 'fork'])
+def test_cov3D_precomp(emulated_backend, flavour):
+    gp.check_cov3D_precomp(size=(64, 48, 300, 3.0), flavour=flavour)
+
+
+def test_mark_visible(emulated_backend):
+    gp.check_mark_visible(n=600)

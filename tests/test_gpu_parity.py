@@ -633,3 +633,91 @@ def check_fused_log_colour_activation_with_sh(deg, size=(160, 96, 1800)):
     assert rel(img_f, out['image'].detach()) < 1e-4
     for k in g_t:
         assert rel(g_f[k], leaves[k].grad) < TOL, (k, rel(g_f[k], leaves[k].grad))
+
+
+def check_cov3D_precomp(size=(96, 64, 600, 3.0), flavour='stock'):
+    """The stock API's cov3D_precomp (a precomputed world-space covariance instead of scales / rotations; LoG always passes
+    None, renderer.py:133,149, but diff_gaussian_rasterization's public signature has it):
+      * against the fp64 torch oracle given the same (N,6) covariances: image, radii, every gradient incl. dL/dcov3D;
+      * against the scale / rotation path of the same library: same image; dL/dcov3D chain-ruled through
+        Sigma = R S S^T R^T reproduces that path's dscales / drotations;
+      * scale_modifier does not touch a precomputed covariance (stock behaviour)."""
+    W, H, n, r = size
+    fork = flavour == 'fork'
+    cam = f32_camera(O.make_camera(W, H, bg=(0.1, 0.3, 0.2)))
+    sc = f32_scene(O.make_scene(n, W, H, r, seed=23))
+    sc['means3D'][:4, 2] = -1.0                  # behind the camera
+    sc['opacities'][4:8] = 0.001                 # below 1/255
+    G = O.make_cotangent(3, H, W).to(torch.float32).to(torch.float64)
+    fm = O.FILTER_MAX if fork else O.FILTER_ADD
+
+    def sigma6(scales, rotations):
+        S = O.cov3d(scales, rotations, 1.0)
+        return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=-1)
+    cov6 = sigma6(sc['scales'], sc['rotations']).to(torch.float32).to(torch.float64)      # what the kernels are given
+    # ---- fp64 oracle with the same covariances
+    leaf = {k: sc[k].clone().requires_grad_(True) for k in ('means3D', 'opacities', 'colors')}
+    c6 = cov6.clone().requires_grad_(True)
+    m2d = torch.zeros(n, 3, dtype=torch.float64, requires_grad=True)
+    out = O.render(leaf['means3D'], leaf['opacities'], None, None, cam, colors_precomp=leaf['colors'], filter_mode=fm,
+                   means2D=m2d, cov3D_precomp=c6)
+    (out['image'] * G).sum().backward()
+    got = run_gpu(cam, sc, G, flavour=flavour, cov3D=cov6)
+    errs = {'image': rel(got['image'], out['image']), 'dmeans3D': rel(got['dmeans3D'], leaf['means3D'].grad),
+            'dmeans2D': rel(got['dmeans2D'][:, :2], m2d.grad[:, :2]), 'dopacities': rel(got['dopacities'], leaf['opacities'].grad.reshape(-1)),
+            'dcolors': rel(got['dcolors'], leaf['colors'].grad), 'dcov3D': rel(got['dcov3D'], c6.grad)}
+    from util import record_parity
+    record_parity(f'cov3D_precomp[{W}x{H},n={n},sigma={r},{flavour}]', {k: (v, None) for k, v in errs.items()}, TOL)
+    for k, e in errs.items():
+        assert e < TOL, (k, e)
+    rg = got['radii'].cpu().numpy()
+    assert (rg != out['radii'].numpy()).sum() <= 2
+    dead = rg == 0
+    assert dead[:8].all() or (rg[:4] == 0).all()
+    assert not got['dcov3D'].cpu().numpy()[dead].any()                      # culled rows: zero gradient, not garbage
+    # ---- against the scale / rotation path of the library itself
+    base = run_gpu(cam, sc, G, flavour=flavour)
+    assert rel(got['image'], base['image']) < 2e-5                           # Sigma rounded to fp32 once vs built in registers
+    sl = sc['scales'].clone().requires_grad_(True)
+    rl = sc['rotations'].clone().requires_grad_(True)
+    (sigma6(sl, rl) * got['dcov3D'].detach().cpu().to(torch.float64)).sum().backward()
+    assert rel(sl.grad, base['dscales']) < TOL and rel(rl.grad, base['drotations']) < TOL
+    # ---- scale_modifier leaves a precomputed covariance alone
+    mod = run_gpu(cam._replace(scale_modifier=1.7), sc, None, flavour=flavour, cov3D=cov6)
+    assert torch.equal(mod['image'], run_gpu(cam, sc, None, flavour=flavour, cov3D=cov6)['image'])
+    # ---- the stock argument rule
+    from log_b200 import StockGaussianRasterizer
+    from util import settings_from_camera
+    rast = StockGaussianRasterizer(settings_from_camera(cam, device()))
+    t = lambda x: x.to(device=device(), dtype=torch.float32)
+    with pytest.raises(Exception, match='exactly one'):
+        rast(means3D=t(sc['means3D']), means2D=None, opacities=t(sc['opacities']), colors_precomp=t(sc['colors']),
+             scales=t(sc['scales']), rotations=t(sc['rotations']), cov3D_precomp=t(cov6))
+    with pytest.raises(Exception, match='exactly one'):
+        rast(means3D=t(sc['means3D']), means2D=None, opacities=t(sc['opacities']), colors_precomp=t(sc['colors']))
+
+
+def check_mark_visible(n=3000):
+    """GaussianRasterizer.markVisible(positions) of the stock module: view-space z > 0.2 (the projection's near cull)."""
+    from log_b200 import GaussianRasterizer
+    from util import settings_from_camera
+    cam = f32_camera(O.make_camera(128, 96, R=[[0.98, 0.0, 0.199], [0, 1, 0], [-0.199, 0, 0.98]], T=[0.1, -0.05, 0.3]))
+    g = torch.Generator().manual_seed(3)
+    pos = (torch.rand(n, 3, generator=g, dtype=torch.float64) * 8 - 4).to(torch.float32)
+    pos[:7, 2] = torch.tensor([0.2, 0.19999, 0.20001, -5.0, 0.0, 100.0, 0.3]) - 0.3      # around the plane (T_z = 0.3 for x = y = 0)
+    pos[:7, :2] = 0.0
+    rast = GaussianRasterizer(settings_from_camera(cam, device()))
+    got = rast.markVisible(pos.to(device()))
+    assert got.dtype == torch.bool and got.shape == (n,)
+    V = cam.viewmatrix.to(torch.float32)
+    z = pos[:, 0] * V[0, 2] + pos[:, 1] * V[1, 2] + pos[:, 2] * V[2, 2] + V[3, 2]
+    want = z > 0.2
+    sure = (z - 0.2).abs() > 1e-5                 # fp32 summation order may flip a point sitting on the plane
+    assert torch.equal(got.cpu()[sure], want[sure]) and sure.sum() > n - 10
+    assert rast.markVisible(pos[:0].to(device())).shape == (0,)
+    # consistent with the rasteriser's own cull: every point with a radius is marked visible
+    sc = f32_scene(O.make_scene(500, 128, 96, 3.0, seed=8))
+    sc['means3D'][:20, 2] = -1.0
+    res = run_gpu(cam, sc, None)
+    vis = rast.markVisible(sc['means3D'].to(device=device(), dtype=torch.float32))
+    assert bool((vis | (res['radii'] == 0)).all()) and not bool(vis.all())

@@ -61,8 +61,14 @@ def test_argument_validation_mirrors_reference():
         r(means3D=z, means2D=z, shs=torch.zeros(2, 1, 3), colors_precomp=z, opacities=z[:, :1], scales=z, rotations=torch.zeros(2, 4))
     with pytest.raises(Exception):      # neither
         r(means3D=z, means2D=z, shs=None, colors_precomp=None, opacities=z[:, :1], scales=z, rotations=torch.zeros(2, 4))
-    with pytest.raises(NotImplementedError):
-        r(means3D=z, means2D=z, shs=None, colors_precomp=z, opacities=z[:, :1], scales=None, rotations=None, cov3D_precomp=torch.zeros(2, 6))
+    # scales/rotations XOR cov3D_precomp, the stock rule (diff_gaussian_rasterization's forward raises the same sentence)
+    with pytest.raises(Exception, match='exactly one of either scale/rotation pair or precomputed 3D covariance'):
+        r(means3D=z, means2D=z, shs=None, colors_precomp=z, opacities=z[:, :1], scales=z, rotations=torch.zeros(2, 4), cov3D_precomp=torch.zeros(2, 6))
+    with pytest.raises(Exception, match='exactly one of either scale/rotation pair or precomputed 3D covariance'):
+        r(means3D=z, means2D=z, shs=None, colors_precomp=z, opacities=z[:, :1], scales=None, rotations=None, cov3D_precomp=None)
+    with pytest.raises(NotImplementedError):      # LoG's fused activations act on scales / rotations
+        r(means3D=z, means2D=z, shs=None, colors_precomp=z, opacities=z[:, :1], scales=None, rotations=None, cov3D_precomp=torch.zeros(2, 6),
+          raw_params=True)
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -56,8 +56,9 @@ def f32_camera(cam):
                         tanfovx=float(np.float32(cam.tanfovx)), tanfovy=float(np.float32(cam.tanfovy)))
 
 
-def run_gpu(cam, scene, G=None, flavour='fork', use_filter=True, sh_degree=0, device=None, tile_rows=None):
-    """Forward (+backward if G) through the public GaussianRasterizer API.  scene: dict of float tensors."""
+def run_gpu(cam, scene, G=None, flavour='fork', use_filter=True, sh_degree=0, device=None, tile_rows=None, cov3D=None):
+    """Forward (+backward if G) through the public GaussianRasterizer API.  scene: dict of float tensors.
+    cov3D (N,6): passed as the stock API's cov3D_precomp instead of scales / rotations; its gradient comes back as dcov3D."""
     from log_b200 import GaussianRasterizer, StockGaussianRasterizer
     dev = torch.device(device or DEVICE[0])
     s = settings_from_camera(cam, dev, sh_degree)
@@ -68,6 +69,9 @@ def run_gpu(cam, scene, G=None, flavour='fork', use_filter=True, sh_degree=0, de
     m2d = torch.zeros(n, 3, device=dev, requires_grad=G is not None)
     kw = dict(means3D=t['means3D'], means2D=m2d, opacities=t['opacities'], scales=t['scales'], rotations=t['rotations'],
               cov3D_precomp=None)
+    if cov3D is not None:
+        c6 = cov3D.to(device=dev, dtype=torch.float32).requires_grad_(G is not None)
+        kw.update(scales=None, rotations=None, cov3D_precomp=c6)
     if sh_degree > 0 or 'colors' not in t:
         kw.update(shs=t['shs'], colors_precomp=None)
     else:
@@ -80,8 +84,11 @@ def run_gpu(cam, scene, G=None, flavour='fork', use_filter=True, sh_degree=0, de
         res.update(point_id_pixel=out[2], point_weight_pixel=out[3], point_weight=out[4])
     if G is not None:
         (out[0] * G.to(device=dev, dtype=torch.float32)).sum().backward()
-        res.update(dmeans3D=t['means3D'].grad, dmeans2D=m2d.grad, dopacities=t['opacities'].grad.reshape(-1),
-                   dscales=t['scales'].grad, drotations=t['rotations'].grad)
+        res.update(dmeans3D=t['means3D'].grad, dmeans2D=m2d.grad, dopacities=t['opacities'].grad.reshape(-1))
+        if cov3D is not None:
+            res.update(dcov3D=c6.grad)
+        else:
+            res.update(dscales=t['scales'].grad, drotations=t['rotations'].grad)
         if kw['shs'] is not None:
             res['dshs'] = t['shs'].grad
         else:
