@@ -20,12 +20,3 @@ def test_tree_walk_matches_oracle_with_culled_points(built):
 @pytest.mark.parametrize('deg', [1, 3])
 def test_fused_log_colour_activation_with_sh(built, deg):
     gp.check_fused_log_colour_activation_with_sh(deg)
-
-
-@pytest.mark.parametrize('flavour', ['stock', 'fork'])
-def test_cov3D_precomp_matches_oracle_and_the_scale_rotation_path(built, flavour):
-    gp.check_cov3D_precomp(flavour=flavour)
-
-
-def test_mark_visible(built):
-    gp.check_mark_visible()
