@@ -113,3 +113,16 @@ def test_shard_layout_struct_matches_header():
     assert fields == [f[0] for f in LgrShardLayout._fields_]
     assert kinds == [f[1] for f in LgrShardLayout._fields_]
     assert ctypes.sizeof(LgrShardLayout) == 8 + 8 * 8
+
+
+def test_integration_md_binding_matches_the_struct():
+    """INTEGRATION.md section 3 shows the ctypes binding a maintainer would add: its field list must be the real one."""
+    import re
+    from log_b200 import _capi
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = text[text.index('class LgrView(ctypes.Structure)'):]
+    block = block[:block.index(']\n') + 1]
+    block = re.sub(r'#[^\n]*', '', block)
+    shown = re.findall(r"\('(\w+)',\s*(\w+)\)", block)
+    kinds = {'i32': ctypes.c_int32, 'i64': ctypes.c_int64, 'f32': ctypes.c_float, 'vp': ctypes.c_void_p}
+    assert [(n, kinds[k]) for n, k in shown] == list(_capi.LgrView._fields_)
