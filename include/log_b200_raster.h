@@ -244,9 +244,11 @@ int lgr_shard_send(const lgr_view* view, const lgr_shard_layout* layout, int64_t
                    const float* splat_d, const int32_t* radii_d, int32_t* send_scratch_d, void* const* peer_base_d,
                    void* stream);
 
-/* Band owner: view->tile_row_begin/end = its band.  Counts tiles of the received rows, clears the radii of unused slots,
- * zeroes the dsplat_d rows (num_ranks*cap, 12) of used slots, then scans: tile_start_d / tile_cursor_d / meta_d exactly
- * as lgr_forward_project leaves them.  Continue with lgr_forward_render(view, n = num_ranks*cap, ..., splat_d =
+/* Band owner: view->tile_row_begin/end = its band, and the view MUST carry the layout's region map (region_count_d =
+ * (int32*)(exchange_d + off_count), region_cap = cap, num_regions = num_ranks; LGR_E_BADARG otherwise): this call and the
+ * render that follows visit the used rows only, unused rows keep whatever an earlier step left in them.  Counts tiles of
+ * the received rows, zeroes the dsplat_d rows (num_ranks*cap, 12) of used slots, then scans: tile_start_d / tile_cursor_d /
+ * meta_d exactly as lgr_forward_project leaves them.  Continue with the SAME view: lgr_forward_render(view, n = num_ranks*cap, ..., splat_d =
  * exchange_d + off_splat, radii_d = exchange_d + off_radii, ...): point_id_pixel then holds ROW indices (map them
  * through the gid array), point_weight_d / point_count_d are per row. */
 int lgr_shard_recv_bin(const lgr_view* view, const lgr_shard_layout* layout, float* exchange_d, float* dsplat_d,
