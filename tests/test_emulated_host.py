@@ -178,3 +178,31 @@ def test_cov3D_precomp(emulated_backend, flavour):
 
 def test_mark_visible(emulated_backend):
     gp.check_mark_visible(n=600)
+
+
+def test_degenerate_inputs_are_culled_or_contained(emulated_backend):
+    """NaN / inf / zero / out-of-range parameters: rows whose geometry is not finite are culled (radius 0), the others render;
+    nothing reads or writes out of bounds (run this file under the emulator's AddressSanitizer build to check that part:
+    tests/emu/build_emu.py) and the damage of a NaN opacity or colour stays in the pixels that splat touches."""
+    import torch
+    from oracle import torch_dense as O
+    from util import f32_camera, run_gpu
+    W, H, n = 96, 64, 400
+    cam = f32_camera(O.make_camera(W, H))
+    sc = gp.f32_scene(O.make_scene(n, W, H, 3.0, seed=4))
+    nan, inf = float('nan'), float('inf')
+    sc['means3D'][0] = nan; sc['means3D'][1, 0] = inf; sc['means3D'][2, 2] = inf
+    sc['scales'][3] = 0.0; sc['scales'][4] = nan; sc['scales'][5] = 1e20; sc['scales'][6] = inf
+    sc['opacities'][7] = -1.0; sc['opacities'][8] = 5.0; sc['opacities'][9] = nan
+    sc['rotations'][10] = 0.0; sc['rotations'][11] = nan
+    sc['colors'][12] = nan
+    got = run_gpu(cam, sc, O.make_cotangent(3, H, W))
+    radii = got['radii'].tolist()
+    assert [radii[i] for i in (0, 1, 2, 4, 5, 6, 11)] == [0] * 7          # non-finite geometry: culled
+    assert radii[3] > 0                                                   # zero scale: the 0.3 px^2 filter keeps it a splat
+    clean = run_gpu(cam, {k: v[13:] for k, v in sc.items()}, O.make_cotangent(3, H, W))
+    bad = ~torch.isfinite(got['image']).all(dim=0)
+    assert 0 < int(bad.sum()) < 0.05 * H * W                              # the NaN opacity / colour rows poison only their footprint
+    assert torch.isfinite(clean['image']).all()
+    ok_rows = torch.isfinite(got['dmeans3D']).all(dim=1)
+    assert float(ok_rows.float().mean()) > 0.9
