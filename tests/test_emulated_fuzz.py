@@ -11,7 +11,7 @@ from oracle import torch_dense as O
 from util import f32_camera, run_gpu
 
 
-@settings(derandomize=True, max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(derandomize=True, max_examples=8, deadline=None, suppress_health_check=list(HealthCheck))
 @given(W=st.integers(5, 130), H=st.integers(5, 90), n=st.integers(1, 350), sigma=st.sampled_from([0.4, 1.0, 2.5, 6.0, 15.0]),
        flavour=st.sampled_from(['fork', 'stock']), use_filter=st.booleans(), rot=st.booleans(), seed=st.integers(0, 10_000))
 def test_random_small_configurations(emulated_backend, W, H, n, sigma, flavour, use_filter, rot, seed):
@@ -34,3 +34,13 @@ def test_random_small_configurations(emulated_backend, W, H, n, sigma, flavour, 
     gs, ps = gp.borderline_decisions(cam, sc, fm, thr=1e-5)          # pairs within fp32 round-off of the alpha = 1/255 rule
     gp.sc_n[0] = n
     gp.check_all(gp.drop(got, gs, ps), gp.drop(ref, gs, ps), 0, flavour == 'fork', H * W, gp.drop(ref32, gs, ps))
+
+
+@settings(derandomize=True, max_examples=8, deadline=None, suppress_health_check=list(HealthCheck))
+@given(world=st.integers(1, 7), W=st.integers(8, 100), H=st.integers(8, 120), n=st.integers(1, 500))
+def test_random_shard_configurations(emulated_backend, world, W, H, n):
+    """Shard mode (SplatExchange over `world` virtual ranks, two steps through the same buffers) against the single-GPU path:
+    image and radii bit-identical, aux outputs equal, gradients within 2e-5 -- for band counts that leave ranks without tile
+    rows (world > tile rows), shards without Gaussians (n < world) and regions with no row at all."""
+    import shard_checks
+    shard_checks.run_two_steps(world, 0, 'fork', size=(W, H, n))
