@@ -11,7 +11,7 @@ from oracle import torch_dense as O
 from util import f32_camera, run_gpu
 
 
-@settings(derandomize=True, max_examples=8, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(derandomize=True, max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
 @given(W=st.integers(5, 130), H=st.integers(5, 90), n=st.integers(1, 350), sigma=st.sampled_from([0.4, 1.0, 2.5, 6.0, 15.0]),
        flavour=st.sampled_from(['fork', 'stock']), use_filter=st.booleans(), rot=st.booleans(), seed=st.integers(0, 10_000))
 def test_random_small_configurations(emulated_backend, W, H, n, sigma, flavour, use_filter, rot, seed):
