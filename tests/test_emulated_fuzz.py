@@ -13,8 +13,9 @@ from util import f32_camera, run_gpu
 
 @settings(derandomize=True, max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
 @given(W=st.integers(5, 130), H=st.integers(5, 90), n=st.integers(1, 350), sigma=st.sampled_from([0.4, 1.0, 2.5, 6.0, 15.0]),
-       flavour=st.sampled_from(['fork', 'stock']), use_filter=st.booleans(), rot=st.booleans(), seed=st.integers(0, 10_000))
-def test_random_small_configurations(emulated_backend, W, H, n, sigma, flavour, use_filter, rot, seed):
+       flavour=st.sampled_from(['fork', 'stock']), use_filter=st.booleans(), rot=st.booleans(), seed=st.integers(0, 10_000),
+       deg=st.integers(0, 3))
+def test_random_small_configurations(emulated_backend, W, H, n, sigma, flavour, use_filter, rot, seed, deg):
     if flavour == 'stock':
         use_filter = True
     # Far-sub-pixel splats WITHOUT the low-pass filter are left out: the backward forms central moments from tensor-core
@@ -24,16 +25,16 @@ def test_random_small_configurations(emulated_backend, W, H, n, sigma, flavour, 
     # evaluation (renderer.py:151-152), where no backward runs.  DESIGN.md, parity status.
     assume(use_filter or sigma >= 2.5)
     kwc = dict(R=[[0.98, 0.0, 0.199], [0, 1, 0], [-0.199, 0, 0.98]], T=[0.1, -0.05, 0.3]) if rot else {}
-    cam = f32_camera(O.make_camera(W, H, bg=(0.3, 0.1, 0.6), **kwc))
-    sc = gp.f32_scene(O.make_scene(n, W, H, sigma, seed=seed))
+    cam = f32_camera(O.make_camera(W, H, bg=(0.3, 0.1, 0.6), sh_degree=deg, **kwc))
+    sc = gp.f32_scene(O.make_scene(n, W, H, sigma, seed=seed, sh_degree=deg))
     G = O.make_cotangent(3, H, W, seed=seed + 1).to(torch.float32).to(torch.float64)
     fm = O.FILTER_ADD if flavour == 'stock' else (O.FILTER_MAX if use_filter else O.FILTER_NONE)
-    ref = gp.oracle(cam, sc, G, fm, 0)
-    ref32 = gp.oracle(cam, sc, G, fm, 0, dtype=np.float32)
-    got = run_gpu(cam, sc, G, flavour=flavour, use_filter=use_filter)
+    ref = gp.oracle(cam, sc, G, fm, deg)
+    ref32 = gp.oracle(cam, sc, G, fm, deg, dtype=np.float32)
+    got = run_gpu(cam, sc, G, flavour=flavour, use_filter=use_filter, sh_degree=deg)
     gs, ps = gp.borderline_decisions(cam, sc, fm, thr=1e-5)          # pairs within fp32 round-off of the alpha = 1/255 rule
     gp.sc_n[0] = n
-    gp.check_all(gp.drop(got, gs, ps), gp.drop(ref, gs, ps), 0, flavour == 'fork', H * W, gp.drop(ref32, gs, ps))
+    gp.check_all(gp.drop(got, gs, ps), gp.drop(ref, gs, ps), deg, flavour == 'fork', H * W, gp.drop(ref32, gs, ps))
 
 
 @settings(derandomize=True, max_examples=8, deadline=None, suppress_health_check=list(HealthCheck))
