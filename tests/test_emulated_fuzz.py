@@ -45,3 +45,24 @@ def test_random_shard_configurations(emulated_backend, world, W, H, n):
     rows (world > tile rows), shards without Gaussians (n < world) and regions with no row at all."""
     import shard_checks
     shard_checks.run_two_steps(world, 0, 'fork', size=(W, H, n))
+
+
+@settings(derandomize=True, max_examples=6, deadline=None, suppress_health_check=list(HealthCheck))
+@given(world=st.integers(1, 6), W=st.integers(16, 120), H=st.integers(16, 120), n=st.integers(1, 600))
+def test_random_band_mode_configurations(emulated_backend, world, W, H, n):
+    """Band mode (round-1 multi-GPU layout): packed gradient rows of `world` tile-row bands reproduce the dense gradients."""
+    gp.test_band_mode_rows_reproduce_dense_gradients(True, world, size=(W, H, n))
+
+
+@settings(derandomize=True, max_examples=6, deadline=None, suppress_health_check=list(HealthCheck))
+@given(deg=st.integers(0, 3), W=st.integers(5, 120), H=st.integers(5, 100), N=st.integers(2, 800), frac=st.floats(0.01, 1.0))
+def test_random_gather_fused_configurations(emulated_backend, deg, W, H, N, frac):
+    """render_gathered (index + raw parameter tables -> projection) against LoG's get_all -> activations -> call sequence."""
+    gp.test_gather_fused_render_equals_log_get_all(True, deg, size=(W, H, N, max(1, int(N * frac))))
+
+
+@settings(derandomize=True, max_examples=8, deadline=None, suppress_health_check=list(HealthCheck))
+@given(W=st.integers(5, 120), H=st.integers(5, 100), n=st.integers(0, 600), r=st.sampled_from([0.5, 2.0, 6.0, 20.0]))
+def test_random_point_id_count_configurations(emulated_backend, W, H, n, r):
+    """point_id / point_count from the blend's winner histogram equal torch.unique over the H x W winner image."""
+    gp.test_point_id_count_equals_torch_unique(True, W, H, n, r)
